@@ -1,0 +1,12 @@
+"""Alias so that ``import csm_mlx`` / ``from csm_mlx import CSM, csm_1b, generate`` (README.md:29-55 of the
+reference) resolve to the B200 implementation in ``csm_mlx_b200``."""
+
+import sys as _sys
+
+import csm_mlx_b200 as _impl
+from csm_mlx_b200 import *  # noqa: F401,F403
+from csm_mlx_b200 import (attention, config, generation, models, sample_utils, segment, tokenizers, utils)  # noqa: F401
+from csm_mlx_b200 import __all__  # noqa: F401
+
+for _name in ("attention", "config", "generation", "models", "sample_utils", "segment", "tokenizers", "utils"):
+    _sys.modules[f"csm_mlx.{_name}"] = getattr(_impl, _name)

@@ -1,0 +1,42 @@
+"""csm_mlx_b200 — B200-native drop-in for the ``csm_mlx`` generation hot path.
+
+Same export list as ``/root/reference/csm_mlx/__init__.py:1-16``.  The training exports (``CSMDataset``,
+``CSMTrainer``, ``TrainArgs``, ``load_adapters``) are outside the generation hot path and raise
+``NotImplementedError`` when used.  ``import csm_mlx`` resolves to a thin alias package of this one.
+"""
+
+from .generation import generate, generate_batch, generate_frame, make_cache, stream_generate
+from .models import CSM, ModelArgs, csm_1b, csm_tiny
+from .sample_utils import make_logits_processors, make_sampler
+from .segment import Segment
+
+
+def _out_of_scope(name):
+    class _Stub:
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} belongs to the fine-tuning stack, which is outside the generation hot path")
+
+    _Stub.__name__ = name
+    return _Stub
+
+
+CSMDataset = _out_of_scope("CSMDataset")
+CSMTrainer = _out_of_scope("CSMTrainer")
+TrainArgs = _out_of_scope("TrainArgs")
+
+
+def load_adapters(*a, **k):
+    raise NotImplementedError("load_adapters belongs to the fine-tuning stack, which is outside the generation hot path")
+
+
+__all__ = [
+    "generate",
+    "stream_generate",
+    "CSM",
+    "csm_1b",
+    "Segment",
+    "CSMDataset",
+    "CSMTrainer",
+    "TrainArgs",
+    "load_adapters",
+]

@@ -1,0 +1,286 @@
+"""Frame generation and the whole-utterance / streaming drivers.  Mirrors
+``/root/reference/csm_mlx/generation.py``: ``generate_frame`` (:21-92), ``generate`` (:95-178),
+``stream_generate`` (:181-258).  Host logic only — prompt assembly, the frame loop, EOS handling, the API
+surface; all arithmetic runs in libcsm_b200.so through ``runtime.LMState`` and ``mimi.Mimi``.
+
+Differences from the reference, all on the host side and deliberate:
+* ``sampler=`` (the README/CLI form, README.md:43-52) is accepted next to ``temperature=`` (this fork's form).
+* frames are produced with one-frame lookahead: frame t+1 is enqueued before frame t's tokens are inspected
+  for EOS on the host, so the GPU never waits for Python; a frame generated past EOS is discarded.
+* ``generate_batch`` (not in the reference, which is batch-1 by construction, generation.py:124,156) runs B
+  independent utterances in lock-step for the request-sharded throughput configuration.
+"""
+
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Callable, Generator, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .config import MAX_SEQ_LEN
+from .models import CSM
+from .runtime import LMState, SamplerSpec
+from .sample_utils import DeviceSampler
+from .segment import Segment
+from .tokenizers import get_audio_tokenizer, tokenize_segment, tokenize_text_segment
+
+default_stream = None  # the reference exposes an mx.Stream here (generation.py:19); CUDA streams come from torch
+
+LogitsProcessor = Callable[[torch.Tensor, torch.Tensor], torch.Tensor]
+
+
+def make_cache(model: CSM, batch: int = 1, max_len: int = MAX_SEQ_LEN) -> LMState:
+    """What ``[KVCache() for _ in model.backbone.layers]`` (generation.py:127) is to the reference."""
+    return LMState(model, batch, max_len)
+
+
+def _resolve_sampler(temperature: float, sampler, seed: Optional[int]):
+    """-> (SamplerSpec, host_callable or None)."""
+    if sampler is None:
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        return SamplerSpec(temperature=float(temperature), seed=seed), None
+    if isinstance(sampler, DeviceSampler):
+        spec = sampler.spec
+        if seed is not None:
+            spec = SamplerSpec(**{**spec.__dict__, "seed": seed})
+        return spec, None
+    if isinstance(sampler, SamplerSpec):
+        return sampler, None
+    if callable(sampler):
+        return SamplerSpec(temperature=0.0), sampler  # foreign callable: host round trip per codebook
+    raise TypeError("sampler must be a csm_mlx.sample_utils.make_sampler(...) object or a callable logits -> ids")
+
+
+def _frame_after_backbone(state: LMState, frame: torch.Tensor, spec: SamplerSpec, host_sampler,
+                          logits_processors: Optional[List[LogitsProcessor]], c0_history: Optional[list]) -> None:
+    """generation.py:42-90 given h_last / c0_logits already in `state`."""
+    model = state.model
+    logits = state.c0_logits
+    if logits_processors:
+        for proc in logits_processors:
+            hist = torch.stack(c0_history, 0) if c0_history else torch.zeros((0,), device=logits.device)
+            logits = proc(hist, logits)
+    if host_sampler is None:
+        state.sample_c0(frame, spec, logits if logits is not state.c0_logits else None)
+    else:
+        frame[:, 0] = host_sampler(logits).to(torch.int32).reshape(-1)
+    if c0_history is not None:
+        c0_history.append(frame[:, :1].clone())
+    if host_sampler is None:
+        state.depth_decode(frame, spec)
+    else:
+        ncb = model.n_audio_codebooks
+        lg = torch.empty((state.batch, ncb, model.n_audio_vocab), device=state.device, dtype=torch.float32)
+        for i in range(1, ncb):
+            state.depth_decode(frame, spec, logits_out=lg, step_begin=i, step_end=i + 1)
+            frame[:, i] = host_sampler(lg[:, i]).to(torch.int32).reshape(-1)
+
+
+def generate_frame(model: CSM, tokens: torch.Tensor, *, temperature: float = 0.8,
+                   token_mask: Optional[torch.Tensor] = None,
+                   logits_processors: Optional[List[LogitsProcessor]] = None, cache: Optional[LMState] = None,
+                   stream=None, c0_history: Optional[list] = None, sampler=None, seed: Optional[int] = None
+                   ) -> torch.Tensor:
+    """generation.py:21-92: tokens (B,T,33) [+ mask] -> (B,32) int32 on the model's device.  ``cache`` is an
+    ``LMState`` (``make_cache``) carried across calls; ``stream`` is accepted for signature compatibility."""
+    B, T, _ = tokens.shape
+    mask = token_mask if token_mask is not None else torch.ones_like(tokens)
+    state = cache if cache is not None else LMState(model, B, max_len=T)
+    spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
+    frame = torch.zeros((B, model.n_audio_codebooks), device=model.device, dtype=torch.int32)
+    if T == 1 and host_sampler is None and not logits_processors and max(state.pos_host) > 0 and c0_history is None:
+        prev = tokens[:, 0, :-1].to(device=model.device, dtype=torch.int32).contiguous()
+        if bool((mask[:, 0, :-1] != 0).all()) and not bool((mask[:, 0, -1] != 0).any()):
+            state.decode_frame(prev, frame, spec)
+            return frame
+    state.prefill([tokens[b] for b in range(B)], [mask[b] for b in range(B)])
+    _frame_after_backbone(state, frame, spec, host_sampler, logits_processors, c0_history)
+    return frame
+
+
+class _Session:
+    """One lock-step generation over B utterances: prefill once, then a frame per ``step()``."""
+
+    def __init__(self, model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tensor]], max_audio_frames: int,
+                 spec: SamplerSpec, host_sampler, logits_processors):
+        self.model, self.spec, self.host_sampler, self.procs = model, spec, host_sampler, logits_processors
+        B = len(prompts)
+        longest = max(int(p[0].shape[0]) for p in prompts)
+        self.state = LMState(model, B, max_len=longest + max_audio_frames + 1)
+        self.prompts = prompts
+        self.c0_history: Optional[list] = [] if logits_processors else None
+        self.prev: Optional[torch.Tensor] = None
+        self.B = B
+
+    def step(self) -> torch.Tensor:
+        st, model = self.state, self.model
+        frame = torch.zeros((self.B, model.n_audio_codebooks), device=model.device, dtype=torch.int32)
+        if self.prev is None:
+            st.prefill([p[0] for p in self.prompts], [p[1] for p in self.prompts])
+            _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
+        elif self.host_sampler is None and not self.procs:
+            st.decode_frame(self.prev, frame, self.spec)
+        else:
+            st.backbone_step(self.prev)
+            _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
+        self.prev = frame
+        return frame
+
+
+def _build_prompt(model: CSM, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """generation.py:108-121."""
+    toks, masks = [], []
+    for seg in context:
+        t, m = tokenize_segment(seg, n_audio_codebooks=model.n_audio_codebooks)
+        toks.append(t)
+        masks.append(m)
+    t, m = tokenize_text_segment(text, speaker, n_audio_codebooks=model.n_audio_codebooks)
+    toks.append(t)
+    masks.append(m)
+    return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0)
+
+
+def _check_length(model: CSM, n_rows: int, max_audio_frames: int) -> None:
+    """generation.py:131-137."""
+    context_window = model.backbone.args.max_position_embeddings or MAX_SEQ_LEN
+    max_seq_len = context_window - max_audio_frames
+    if n_rows >= max_seq_len:
+        raise ValueError(
+            f"Inputs too long ({n_rows}), must be below max_seq_len - max_audio_frames: {max_seq_len}")
+
+
+class _HostMirror:
+    """Double-buffered pinned host copies of per-frame results + the event that says they have landed."""
+
+    def __init__(self, shapes_dtypes, device):
+        self.bufs = [[torch.empty(s, dtype=d).pin_memory() for s, d in shapes_dtypes] for _ in range(2)]
+        self.events = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self.device = device
+
+    def push(self, tensors) -> int:
+        slot = self.i & 1
+        for dst, src in zip(self.bufs[slot], tensors):
+            dst.copy_(src, non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.device))
+        self.i += 1
+        return slot
+
+    def wait(self, slot: int):
+        self.events[slot].synchronize()
+        return self.bufs[slot]
+
+
+def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tensor]], max_audio_frames: int, *,
+                    temperature: float = 0.8, sampler=None, logits_processors=None, seed: Optional[int] = None
+                    ) -> List[torch.Tensor]:
+    """The frame loop of generation.py:139-161 for B utterances in lock-step: returns, per utterance, the
+    (F_b, 32) int32 CPU tensor of frames before its first all-zero (EOS) frame."""
+    for tok, _ in prompts:
+        _check_length(model, int(tok.shape[0]), max_audio_frames)
+    spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
+    sess = _Session(model, prompts, max_audio_frames, spec, host_sampler, logits_processors)
+    B, ncb = len(prompts), model.n_audio_codebooks
+    mirror = _HostMirror([((B, ncb), torch.int32)], model.device)
+    out: List[List[torch.Tensor]] = [[] for _ in range(B)]
+    done = [False] * B
+    pending: Optional[int] = None
+
+    def drain(slot: int) -> None:
+        (host,) = mirror.wait(slot)
+        for b in range(B):
+            if done[b]:
+                continue
+            if not bool(host[b].any()):
+                done[b] = True  # eos (generation.py:151-152)
+            else:
+                out[b].append(host[b].clone())
+
+    for _ in range(max_audio_frames):
+        frame = sess.step()
+        slot = mirror.push([frame])
+        if pending is not None:
+            drain(pending)
+            if all(done):
+                pending = None
+                break
+        pending = slot
+    if pending is not None:
+        drain(pending)
+    return [torch.stack(f) if f else torch.zeros((0, ncb), dtype=torch.int32) for f in out]
+
+
+def generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, context: List[Segment],
+             max_audio_length_ms: float = 90_000, *, temperature: float = 0.8,
+             logits_processors: Optional[List[LogitsProcessor]] = None, stream=None, sampler=None,
+             seed: Optional[int] = None) -> torch.Tensor:
+    """generation.py:95-178 -> 1-D float32 audio ``(1920*F,)`` (CPU tensor; ``np.asarray`` works on it)."""
+    max_audio_frames = int(max_audio_length_ms / 80)
+    prompt = _build_prompt(model, text, speaker, context)
+    (frames,) = generate_tokens(model, [prompt], max_audio_frames, temperature=temperature, sampler=sampler,
+                                logits_processors=logits_processors, seed=seed)
+    if frames.shape[0] == 0:
+        print("[WARN] No samples generated.")
+        return torch.zeros((0,), dtype=torch.float32)
+    codes = frames.t().unsqueeze(0).to(model.device)  # (1, 32, F)
+    audio = get_audio_tokenizer(model.n_audio_codebooks).decode(codes)
+    # TODO(reference parity): the reference has an unimplemented watermarking TODO here (generation.py:176)
+    return audio.reshape(-1).to("cpu")
+
+
+def generate_batch(model: CSM, texts: Sequence[Union[str, Sequence[int]]], speakers: Sequence[int],
+                   contexts: Optional[Sequence[List[Segment]]] = None, max_audio_length_ms: float = 90_000, *,
+                   temperature: float = 0.8, sampler=None, seed: Optional[int] = None,
+                   return_tokens: bool = False):
+    """B independent utterances in lock-step (request batching; not in the reference).  Returns a list of
+    1-D float32 CPU audio tensors (and the per-utterance (F,32) token tensors if ``return_tokens``)."""
+    max_audio_frames = int(max_audio_length_ms / 80)
+    contexts = contexts if contexts is not None else [[] for _ in texts]
+    prompts = [_build_prompt(model, t, s, c) for t, s, c in zip(texts, speakers, contexts)]
+    frames = generate_tokens(model, prompts, max_audio_frames, temperature=temperature, sampler=sampler, seed=seed)
+    mimi = get_audio_tokenizer(model.n_audio_codebooks)
+    Fmax = max((int(f.shape[0]) for f in frames), default=0)
+    audios: List[torch.Tensor] = []
+    if Fmax == 0:
+        audios = [torch.zeros((0,), dtype=torch.float32) for _ in frames]
+    else:
+        codes = torch.zeros((len(frames), model.n_audio_codebooks, Fmax), dtype=torch.int32)
+        for b, f in enumerate(frames):
+            codes[b, :, : f.shape[0]] = f.t()
+        audio = mimi.decode(codes.to(model.device)).to("cpu")  # causal codec: padding frames only affect the tail
+        audios = [audio[b, 0, : 1920 * int(f.shape[0])].clone() for b, f in enumerate(frames)]
+    return (audios, frames) if return_tokens else audios
+
+
+def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, context: List[Segment],
+                    max_audio_length_ms: float = 90_000, *, temperature: float = 0.8,
+                    logits_processors: Optional[List[LogitsProcessor]] = None, stream=None, sampler=None,
+                    seed: Optional[int] = None) -> Generator[torch.Tensor, None, None]:
+    """generation.py:181-258: yields one ``(1920,)`` float32 CPU chunk per generated frame.  Each generator owns
+    its codec streaming state (the reference shares one global Mimi state, tokenizers.py:14-21)."""
+    max_audio_frames = int(max_audio_length_ms / 80)
+    prompt = _build_prompt(model, text, speaker, context)
+    _check_length(model, int(prompt[0].shape[0]), max_audio_frames)
+    spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
+    sess = _Session(model, [prompt], max_audio_frames, spec, host_sampler, logits_processors)
+    ncb = model.n_audio_codebooks
+    codec = get_audio_tokenizer(ncb).new_decode_stream(batch=1)
+    mirror = _HostMirror([((1, ncb), torch.int32), ((1, 1, 1920), torch.float32)], model.device)
+    pending: Optional[int] = None
+    for _ in range(max_audio_frames):
+        frame = sess.step()
+        audio = codec.step(frame.reshape(1, ncb, 1))
+        slot = mirror.push([frame, audio])
+        if pending is not None:
+            host_frame, host_audio = mirror.wait(pending)
+            if not bool(host_frame.any()):
+                return  # eos: the speculative frame just enqueued is discarded
+            yield host_audio.reshape(-1).clone()
+        pending = slot
+    if pending is not None:
+        host_frame, host_audio = mirror.wait(pending)
+        if bool(host_frame.any()):
+            yield host_audio.reshape(-1).clone()

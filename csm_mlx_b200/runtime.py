@@ -1,0 +1,175 @@
+"""Device-side generation state for a batch of utterances: paged KV pools, block tables, scratch, positions.
+
+Plays the role of the per-call ``KVCache`` lists of the reference (``/root/reference/csm_mlx/generation.py:70``
+decoder cache re-created every frame, ``:127`` backbone cache per ``generate`` call): the caller's ``generate``
+creates one ``LMState`` and drops it at the end.  All arithmetic happens in libcsm_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .config import MAX_SEQ_LEN
+from .models import CSM
+
+
+@dataclass
+class SamplerSpec:
+    """Device-side sampler parameters (mlx_lm ``make_sampler`` arguments, cli/generate.py:168-174)."""
+
+    temperature: float = 0.0
+    top_k: int = 0
+    top_p: float = 0.0
+    min_p: float = 0.0
+    min_tokens_to_keep: int = 1
+    seed: int = 0
+
+    def to_c(self) -> _lib.Sampler:
+        return _lib.Sampler(float(self.temperature), int(self.top_k) if self.top_k and self.top_k > 0 else 0,
+                            float(self.top_p), float(self.min_p), int(self.min_tokens_to_keep),
+                            int(self.seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+class LMState:
+    def __init__(self, model: CSM, batch: int, max_len: int = MAX_SEQ_LEN):
+        model._require_loaded()
+        self.model = model
+        self.device = model.device
+        self.dev_idx = _lib.require_device(self.device)
+        self.batch = batch
+        self.max_len = min(int(max_len), MAX_SEQ_LEN)
+        b, d = model.backbone.args, model.decoder.args
+        ncb = model.n_audio_codebooks
+        P = _lib.PAGE
+        self.pages_per_seq = (self.max_len + P - 1) // P
+        n_pages = batch * self.pages_per_seq
+        page_floats_b = 2 * b.num_key_value_heads * P * b.head_dim
+        self.kv_pool = torch.zeros((b.num_hidden_layers, n_pages, page_floats_b), device=self.device,
+                                   dtype=torch.float32)
+        self.block_table = torch.arange(n_pages, device=self.device, dtype=torch.int32).reshape(batch, self.pages_per_seq)
+        dec_pages = (ncb + P - 1) // P
+        page_floats_d = 2 * d.num_key_value_heads * P * d.head_dim
+        self.dec_kv_pool = torch.zeros((d.num_hidden_layers, batch * dec_pages, page_floats_d), device=self.device,
+                                       dtype=torch.float32)
+        self._ws_rows = 0
+        self.workspace: Optional[torch.Tensor] = None
+        self._ensure_workspace(2 * batch)
+        self.pos = torch.zeros((batch,), device=self.device, dtype=torch.int32)  # next position per sequence
+        self.pos_host = [0] * batch
+        self.h_last = torch.empty((batch, b.hidden_size), device=self.device, dtype=torch.float32)
+        self.c0_logits = torch.empty((batch, model.n_audio_vocab), device=self.device, dtype=torch.float32)
+        self._seq_iota = torch.arange(batch, device=self.device, dtype=torch.int32)
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure_workspace(self, rows: int) -> None:
+        if rows <= self._ws_rows:
+            return
+        nbytes = _lib.lib().csmb_lm_workspace_bytes(C.byref(self.model.desc()), rows)
+        self.workspace = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
+        self._ws_rows = rows
+
+    def _batch_desc(self) -> _lib.Batch:
+        b = _lib.Batch()
+        b.batch, b.max_pages = self.batch, self.pages_per_seq
+        b.kv_pool, b.kv_layer_stride = self.kv_pool.data_ptr(), self.kv_pool.stride(0)
+        b.block_table = self.block_table.data_ptr()
+        b.dec_kv_pool, b.dec_kv_layer_stride = self.dec_kv_pool.data_ptr(), self.dec_kv_pool.stride(0)
+        b.workspace, b.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        return b
+
+    def _stream(self) -> int:
+        return _lib.stream_ptr(self.device)
+
+    # ------------------------------------------------------------------ steps
+    def prefill(self, tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
+        """Backbone over every sequence's prompt rows ((T_b,33) each); leaves h_last / c0_logits of the last
+        row of each sequence and advances positions (generation.py:34-42 with T>1)."""
+        assert len(tokens) == self.batch
+        lens = [int(t.shape[0]) for t in tokens]
+        for b, n in enumerate(lens):
+            if self.pos_host[b] + n > self.max_len:
+                raise ValueError("sequence exceeds the KV pages reserved for it")
+        tok = torch.cat([t.to(torch.int32) for t in tokens], 0).to(self.device).contiguous()
+        msk = torch.cat([m.to(torch.uint8) for m in masks], 0).to(self.device).contiguous()
+        R = int(tok.shape[0])
+        seq = torch.cat([torch.full((n,), b, dtype=torch.int32) for b, n in enumerate(lens)]).to(self.device)
+        pos = torch.cat([torch.arange(self.pos_host[b], self.pos_host[b] + n, dtype=torch.int32)
+                         for b, n in enumerate(lens)]).to(self.device)
+        ends, acc = [], 0
+        for n in lens:
+            acc += n
+            ends.append(acc - 1)
+        last = torch.tensor(ends, dtype=torch.int32, device=self.device)
+        self._ensure_workspace(max(R, 2 * self.batch))
+        bd = self._batch_desc()
+        _lib.check(_lib.lib().csmb_backbone_forward(
+            C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
+            last.data_ptr(), self.batch, self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx,
+            self._stream()))
+        for b, n in enumerate(lens):
+            self.pos_host[b] += n
+        self.pos = torch.tensor(self.pos_host, dtype=torch.int32, device=self.device)
+
+    def sample_c0(self, frame: torch.Tensor, sampler: SamplerSpec, logits: Optional[torch.Tensor] = None) -> None:
+        """frame[:,0] = sample(c0 logits)   (generation.py:51-56).  RNG draw index = (pos-1)*n_codebooks."""
+        lg = self.c0_logits if logits is None else logits.to(device=self.device, dtype=torch.float32).contiguous()
+        ncb = self.model.n_audio_codebooks
+        s = sampler.to_c()
+        # per-sequence draw = frame position * ncb: positions differ across sequences, so sample row by row
+        # only when sampling stochastically with ragged positions; greedy ignores the draw index.
+        if sampler.temperature == 0 or len(set(self.pos_host)) == 1:
+            draw = (self.pos_host[0] - 1) * ncb
+            _lib.check(_lib.lib().csmb_sample(lg.data_ptr(), lg.shape[1], frame.data_ptr(), ncb, self.batch,
+                                              lg.shape[1], C.byref(s), draw, self.dev_idx, self._stream()))
+        else:
+            raise NotImplementedError("stochastic sampling with ragged positions goes through decode_frame")
+
+    def depth_decode(self, frame: torch.Tensor, sampler: SamplerSpec, logits_out: Optional[torch.Tensor] = None,
+                     forced: Optional[torch.Tensor] = None, step_begin: int = 1, step_end: Optional[int] = None) -> None:
+        """generation.py:56-90: fills frame[:, step_begin:step_end] from h_last and frame[:,0]."""
+        ncb = self.model.n_audio_codebooks
+        bd = self._batch_desc()
+        s = sampler.to_c()
+        pos_prev = (self.pos - 1).contiguous()
+        _lib.check(_lib.lib().csmb_depth_decode(
+            C.byref(self.model.desc()), C.byref(bd), self.h_last.data_ptr(), frame.data_ptr(), C.byref(s), 0,
+            pos_prev.data_ptr(), None if logits_out is None else logits_out.data_ptr(),
+            None if forced is None else forced.data_ptr(), step_begin, ncb if step_end is None else step_end,
+            self.dev_idx, self._stream()))
+
+    def backbone_step(self, prev_frame: torch.Tensor) -> None:
+        """One T=1 backbone step from the previous frame (generation.py:156-161 then :34-42)."""
+        ncb = self.model.n_audio_codebooks
+        tok = torch.cat([prev_frame.to(torch.int32), torch.zeros((self.batch, 1), dtype=torch.int32, device=self.device)], 1)
+        msk = torch.cat([torch.ones((self.batch, ncb), dtype=torch.uint8, device=self.device),
+                         torch.zeros((self.batch, 1), dtype=torch.uint8, device=self.device)], 1)
+        self._check_room()
+        bd = self._batch_desc()
+        _lib.check(_lib.lib().csmb_backbone_forward(
+            C.byref(self.model.desc()), C.byref(bd), tok.contiguous().data_ptr(), msk.contiguous().data_ptr(),
+            self._seq_iota.data_ptr(), self.pos.data_ptr(), self.batch, self._seq_iota.data_ptr(), self.batch,
+            self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx, self._stream()))
+        self._advance()
+
+    def decode_frame(self, prev_frame: torch.Tensor, frame: torch.Tensor, sampler: SamplerSpec) -> None:
+        """Whole frame on device, no host round trip (generation.py:21-92 with T=1)."""
+        self._check_room()
+        bd = self._batch_desc()
+        s = sampler.to_c()
+        _lib.check(_lib.lib().csmb_decode_frame(
+            C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
+            C.byref(s), 0, self.dev_idx, self._stream()))
+        self._advance()
+
+    def _check_room(self) -> None:
+        if max(self.pos_host) + 1 > self.max_len:
+            raise ValueError("sequence exceeds the KV pages reserved for it")
+
+    def _advance(self) -> None:
+        self.pos_host = [p + 1 for p in self.pos_host]
+        self.pos.add_(1)

@@ -1,0 +1,219 @@
+/* csm_b200.h — C ABI of libcsm_b200.so: the sm_100a kernels behind the csm_mlx generation hot path.
+ *
+ * The reference (sethdford/csm-mlx) has no FFI of its own: every tensor op is dispatched into
+ * mlx / mlx_lm / moshi_mlx from Python.  This header is the boundary a binding for that path would
+ * target; each entry point cites the reference call it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name says host.
+ *  - activations fp32, Linear/embedding weights bf16 (uint16_t bit patterns), norm weights fp32.
+ *  - every function takes the CUDA device ordinal and a cudaStream_t (as void*), is asynchronous on
+ *    that stream, allocates nothing, keeps no thread-local or global mutable state and may be called
+ *    from any host thread (the reference's demo hops threads between frames,
+ *    run_streaming_csm_mlx.py:984-1000).
+ *  - return value: 0 = ok, negative = csmb_status; csmb_strerror() gives text.
+ *  - "rows": all LM ops work on R flattened token rows; row r belongs to sequence row_seq[r] at
+ *    position row_pos[r] (prefill: many rows per sequence; decode: one row per sequence).
+ *  - KV caches are paged: pool layout [n_pages][2 (K,V)][n_kv_heads][CSMB_PAGE][head_dim] fp32 per
+ *    layer, block_table[seq][logical_page] -> physical page.
+ */
+#ifndef CSM_B200_H
+#define CSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSMB_ABI_VERSION 1
+#define CSMB_PAGE 16          /* tokens per KV page */
+#define CSMB_MAX_LAYERS 16
+#define CSMB_MAX_CODEBOOKS 32
+
+typedef enum {
+  CSMB_OK = 0,
+  CSMB_ERR_INVALID = -1,      /* bad argument (shape, alignment, null pointer) */
+  CSMB_ERR_CUDA = -2,         /* a CUDA runtime call failed; see csmb_last_cuda_error */
+  CSMB_ERR_UNSUPPORTED = -3,  /* configuration not compiled in */
+  CSMB_ERR_DEVICE = -4        /* device is not sm_100 */
+} csmb_status;
+
+int csmb_abi_version(void);
+const char* csmb_strerror(int status);
+/* text of the last CUDA error seen by this library on any thread (diagnostic only; racy by nature). */
+const char* csmb_last_cuda_error(void);
+/* 0 if `device` is an sm_100 part this library was compiled for. */
+int csmb_check_device(int device);
+
+/* ---------------------------------------------------------------- elementary ops (LM) ---------- */
+
+/* CSM.embed_tokens + mask-multiply + sum(-2)  (csm_mlx/models.py:82-92, generation.py:32-36).
+ * tokens/mask [R][n_codebooks+1] (audio codebooks first, text id last); out [R][d] fp32. */
+int csmb_embed_sum(const int32_t* tokens, const uint8_t* mask, const uint16_t* text_emb,
+                   const uint16_t* audio_emb, float* out, int R, int d, int n_codebooks, int audio_vocab,
+                   int device, void* stream);
+
+/* CSM.embed_audio (models.py:79-80): out[r] = audio_emb[tokens[r] + codebook*audio_vocab], fp32. */
+int csmb_embed_audio(const int32_t* tokens, const uint16_t* audio_emb, float* out, int ldo, int R, int d,
+                     int codebook, int audio_vocab, int device, void* stream);
+
+/* nn.RMSNorm of mlx_lm's TransformerBlock (constructed models.py:50-51): y = x*rsqrt(mean(x^2)+eps)*w. */
+int csmb_rmsnorm(const float* x, int ldx, const float* w, float* y, int ldy, int R, int d, float eps,
+                 int device, void* stream);
+
+/* nn.Linear without bias (attention.py:216-218,253; mlx_lm MLP; codebook0_head generation.py:42;
+ * projection generation.py:75):  y[R][N] (+)= x[R][K] . W[N][K]^T.  accumulate!=0 adds into y (residual). */
+int csmb_linear(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
+                int accumulate, int device, void* stream);
+
+/* SwiGLU of mlx_lm MLP: out[r][f] = silu(gu[r][f]) * gu[r][F+f]   (gu = fused gate|up output). */
+int csmb_swiglu(const float* gu, float* out, int R, int F, int device, void* stream);
+
+/* Llama3ScaledRoPE.__call__ on q and k (attention.py:119-177, 226-228) + KVCache.update_and_fetch
+ * (attention.py:236-237).  qkv [R][(H+2*Hkv)*hd] (q heads, then k heads, then v heads): q is rotated in
+ * place; rotated k and v are written to the paged pool at (row_seq, row_pos).
+ * rope [max_pos][hd/2][2] fp32 (cos, sin); adjacent-pair convention. */
+int csmb_rope_kv_append(float* qkv, const float* rope, float* kv_pool, const int32_t* block_table,
+                        int max_pages, const int32_t* row_seq, const int32_t* row_pos, int R, int n_heads,
+                        int n_kv_heads, int head_dim, int device, void* stream);
+
+/* mx.repeat + scaled_dot_product_attention (attention.py:242-249): for row r, head h, softmax over
+ * positions 0..row_pos[r] of sequence row_seq[r] (causal), GQA head h -> kv head h/(H/Hkv).
+ * q is read from qkv (leading dim ldq); out [R][H*hd]. */
+int csmb_attention(const float* qkv, int ldq, const float* kv_pool, const int32_t* block_table,
+                   int max_pages, const int32_t* row_seq, const int32_t* row_pos, float* out, int R,
+                   int n_heads, int n_kv_heads, int head_dim, int device, void* stream);
+
+/* Sampling (generation.py:51-54, 81-84 and mlx_lm.sample_utils.make_sampler as used by
+ * cli/generate.py:168-174).  logits [R][V] fp32 -> out[r*out_stride] int32.
+ * temperature==0: argmax (lowest index on ties).  Otherwise top-k (k>0), top-p (0<p<1), min-p (>0,
+ * keeping at least min_keep) filters on softmax(logits), then categorical(logits/temperature) by the
+ * Gumbel-max trick: argmax_i(logits[i]/temperature - log(-log(u_i))), u_i from Philox4x32-10 with
+ * key = seed and counter = (i/4, draw_lo, draw_hi, r), word i%4 of the output block. */
+typedef struct {
+  float temperature;
+  int top_k;
+  float top_p;
+  float min_p;
+  int min_keep;
+  uint64_t seed;
+} csmb_sampler;
+
+int csmb_sample(const float* logits, int ldl, int32_t* out, int out_stride, int R, int V,
+                const csmb_sampler* sampler /*host*/, uint64_t draw, int device, void* stream);
+
+/* ---------------------------------------------------------------- fused LM path ---------------- */
+
+typedef struct {
+  int n_layers, d_model, n_heads, n_kv_heads, head_dim, d_ff;
+  float eps;
+  const uint16_t* wqkv[CSMB_MAX_LAYERS];   /* [(H+2Hkv)*hd][d]   q rows, k rows, v rows */
+  const uint16_t* wo[CSMB_MAX_LAYERS];     /* [d][H*hd] */
+  const uint16_t* wgu[CSMB_MAX_LAYERS];    /* [2*d_ff][d]        gate rows then up rows */
+  const uint16_t* wdown[CSMB_MAX_LAYERS];  /* [d][d_ff] */
+  const float* norm_in[CSMB_MAX_LAYERS];
+  const float* norm_post[CSMB_MAX_LAYERS];
+  const float* norm_final;
+  const float* rope;                       /* [max_pos][hd/2][2] */
+} csmb_llama;
+
+typedef struct {
+  csmb_llama backbone, decoder;
+  const uint16_t* text_emb;     /* [n_text_vocab][d_b] */
+  const uint16_t* audio_emb;    /* [n_codebooks*audio_vocab][d_b] */
+  const uint16_t* projection;   /* [d_d][d_b] */
+  const uint16_t* c0_head;      /* [audio_vocab][d_b] */
+  const uint16_t* audio_head_t; /* [n_codebooks-1][audio_vocab][d_d]: checkpoint's (in,out) transposed */
+  int n_text_vocab, audio_vocab, n_codebooks, max_pos;
+} csmb_model;
+
+/* Per-call view of a batch of sequences being generated. */
+typedef struct {
+  int batch;                    /* sequences */
+  int max_pages;                /* block_table row length */
+  float* kv_pool;               /* backbone: [n_layers][n_pages_total] pages (see top of file) */
+  size_t kv_layer_stride;       /* floats between consecutive layers in kv_pool */
+  const int32_t* block_table;   /* [batch][max_pages] */
+  float* dec_kv_pool;           /* decoder: [n_layers][batch*ceil(n_codebooks/PAGE)] pages */
+  size_t dec_kv_layer_stride;
+  void* workspace;              /* csmb_lm_workspace_bytes() bytes */
+  size_t workspace_bytes;
+} csmb_batch;
+
+/* bytes of scratch for up to max_rows rows (prefill) / batch sequences (decode). */
+size_t csmb_lm_workspace_bytes(const csmb_model* m /*host*/, int max_rows);
+
+/* model.backbone(...) over R rows, then codebook0_head on the rows listed in last_rows
+ * (generation.py:34-42).  Writes h_last [n_last][d_b] and c0_logits [n_last][audio_vocab]. */
+int csmb_backbone_forward(const csmb_model* m, const csmb_batch* b, const int32_t* tokens,
+                          const uint8_t* mask, const int32_t* row_seq, const int32_t* row_pos, int R,
+                          const int32_t* last_rows, int n_last, float* h_last, float* c0_logits, int device,
+                          void* stream);
+
+/* The 31-step depth-decoder loop of generate_frame (generation.py:56-90) for `batch` sequences:
+ * given h_last and the already-sampled c0 (frame[:,0]), fills frame[:,i] for i in [step_begin, step_end)
+ * (1 <= step_begin <= step_end <= n_codebooks; the whole loop is [1, n_codebooks)); all sampling on device.
+ * Step i reads its input token from frame[:,i-1] (or forced[:,i-1]), so a host that wants to post-process
+ * samples can run one step per call and overwrite frame[:,i] in between.
+ * logits_out (optional) [batch][n_codebooks][audio_vocab] receives every step's logits (slot 0 unused).
+ * forced (optional) [batch][n_codebooks]: teacher forcing — propagate these tokens instead of the samples.
+ * RNG draw index of codebook i for sequence b: draw_base + i + (pos ? pos[b] : 0) * n_codebooks. */
+int csmb_depth_decode(const csmb_model* m, const csmb_batch* b, const float* h_last, int32_t* frame,
+                      const csmb_sampler* sampler, uint64_t draw_base, const int32_t* pos, float* logits_out,
+                      const int32_t* forced, int step_begin, int step_end, int device, void* stream);
+
+/* One whole decode frame for batch sequences whose previous frame is prev_frame [batch][n_codebooks]
+ * at positions pos[batch] (generation.py:21-92 with T=1, plus :156-161 for the input construction):
+ * embed -> backbone -> c0 -> depth loop.  Writes frame [batch][n_codebooks]. */
+int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame,
+                      const int32_t* pos, int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base,
+                      int device, void* stream);
+
+/* ---------------------------------------------------------------- Mimi codec ------------------- */
+/* moshi_mlx Mimi.encode / decode / decode_step (csm_mlx/tokenizers.py:14-21,70,150; generation.py:224-225,
+ * 251,258).  Activations are time-major fp32 [batch][time][channels]; see csrc/mimi.cu for how Conv1d and
+ * ConvTranspose1d map onto the strided-row GEMM. */
+
+/* Y[b][t][n] = epi( sum_{j<K} actA(A[b*a_batch + t*lda + j]) * W[n][j] ), epi = (+bias[n]) -> act_out ->
+ * (*scale[n]) -> (+residual[b*r_batch + t*ldr + n]).  act_in: 0 none, 1 ELU.  act_out: 0 none, 1 GELU(erf). */
+int csmb_gemm_f32(const float* A, long long a_batch, int lda, const float* W, float* Y, long long y_batch, int ldy,
+                  const float* bias, const float* scale, const float* residual, long long r_batch, int ldr, int B,
+                  int T, int N, int K, int act_in, int act_out, int device, void* stream);
+
+int csmb_layernorm(const float* x, long long x_batch, const float* w, const float* b, float* y, int B, int T, int d,
+                   float eps, int device, void* stream);
+
+/* qkv [B][T][3][H][64]: RoPE (adjacent pairs, angle = pos*freqs[i]) on q,k in place; rotated k and v written to
+ * the ring cache [B][cap][2][H][64] at slot pos%cap; out [B][T][H*64] = causal attention over the last `ctx`
+ * positions.  *pos0 (device int) = absolute position of step 0 of this call; cap >= ctx + T - 1. */
+int csmb_mimi_attention(float* qkv, float* cache, const float* freqs, const int* pos0, float* out, int B, int T,
+                        int H, int cap, int ctx, int device, void* stream);
+
+/* RVQ dequantise gather: codes [B][K][F] -> sem [B][F][D] = C_0[c_0], ac [B][F][D] = sum_{k>=1} C_k[c_k];
+ * codebooks [K][bins][D].  Ids outside [0,bins) are clamped. */
+int csmb_rvq_gather(const int32_t* codes, const float* codebooks, float* sem, float* ac, int B, int K, int F,
+                    int bins, int D, int device, void* stream);
+
+/* depthwise ConvTranspose1d(k=4,s=2) x2 upsampler: x [B][T][C], xprev [B][C] (row before t=0), w [C][4] ->
+ * y [B][2T][C]. */
+int csmb_upsample_dw(const float* x, const float* xprev, const float* w, float* y, int B, int T, int C, int device,
+                     void* stream);
+
+/* One residual-VQ encode step: idx = argmin_j (c2[j] - 2*dots[m][j]); codes[b][k][f] = idx; r[m] -= C[idx]. */
+int csmb_rvq_argmin_update(const float* dots, const float* c2, const float* codebook, float* r, int32_t* codes,
+                           int M, int bins, int D, int K, int k, int F, int device, void* stream);
+
+/* dst[b][dst_t0+t][:] = src[b][src_t0 + (replicate ? 0 : t)][:] for t < T (padding / context fill). */
+int csmb_copy_rows(const float* src, long long s_batch, int src_t0, float* dst, long long d_batch, int dst_t0, int B,
+                   int T, int C, int replicate, int device, void* stream);
+/* streaming context carry: buf[b][0:pad] = buf[b][T:T+pad]. */
+int csmb_shift_rows(float* buf, long long batch, int B, int T, int pad, int C, int device, void* stream);
+/* *p += v on the device (position counters of captured graphs). */
+int csmb_add_int(int* p, int v, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSM_B200_H */

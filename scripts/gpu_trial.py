@@ -1,0 +1,178 @@
+"""Developer bring-up script (run under gpurun): exercises every product path once against the oracle and prints
+max errors / timings.  Not a test; tests/ holds the assertions."""
+import sys, os, time, traceback
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from csm_mlx_b200 import CSM, csm_1b
+from csm_mlx_b200 import generation, tokenizers
+from csm_mlx_b200.mimi import Mimi
+from csm_mlx_b200.random_init import random_csm_weights, random_mimi_weights
+from csm_mlx_b200.runtime import LMState, SamplerSpec
+from oracle import lm as olm, mimi as omimi
+
+torch.manual_seed(0)
+dev = torch.device("cuda", 0)
+SECTIONS = sys.argv[1:] or ["ops", "lm", "mimi", "time"]
+
+
+def section(name):
+    def deco(fn):
+        if name in SECTIONS:
+            print(f"\n===== {name} =====", flush=True)
+            try:
+                fn()
+            except Exception:
+                traceback.print_exc()
+        return fn
+    return deco
+
+
+t0 = time.time()
+W = random_csm_weights()
+print("weights", time.time() - t0, flush=True)
+model = CSM(csm_1b(), device=dev).load_weights(W)
+torch.cuda.synchronize()
+print("loaded", time.time() - t0, flush=True)
+g = torch.Generator().manual_seed(7)
+ids = [128000] + torch.randint(0, 128000, (8,), generator=g).tolist() + [128001]
+ptok, pmask = tokenizers.tokenize_text_segment(ids, 0)
+
+
+@section("ops")
+def _ops():
+    from csm_mlx_b200 import _lib
+    lib = _lib.lib()
+    for (R, N, K) in [(1, 3072, 2048), (1, 2048, 2048), (1, 16384, 2048), (1, 2048, 8192), (1, 2051, 2048), (2, 1536, 1024),
+                      (1, 1024, 1024), (1, 16384, 1024), (1, 1024, 8192), (2, 1024, 2048), (1, 2051, 1024), (10, 3072, 2048), (5, 2051, 1024)]:
+        x = torch.randn(R, K, device=dev)
+        w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+        y = torch.zeros(R, N, device=dev)
+        _lib.check(lib.csmb_linear(x.data_ptr(), K, w.data_ptr(), y.data_ptr(), N, R, N, K, 0, 0, _lib.stream_ptr(dev)))
+        ref = x.double() @ w.double().t()
+        print(f"linear R={R} N={N} K={K} maxerr {(y.double() - ref).abs().max().item():.3e} ref {ref.abs().max().item():.2f}")
+        # timing
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ws = [(torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16) for _ in range(max(2, int(400e6 / (N * K * 2))))]
+        e0.record()
+        for wi in ws:
+            lib.csmb_linear(x.data_ptr(), K, wi.data_ptr(), y.data_ptr(), N, R, N, K, 0, 0, _lib.stream_ptr(dev))
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / len(ws)
+        print(f"   {ms * 1e3:.1f} us  {N * K * 2 / ms / 1e6:.0f} GB/s")
+
+
+@section("lm")
+def _lm():
+    orc = olm.OracleCSM(olm.CSM_1B, W)
+    st = LMState(model, 1, max_len=64)
+    st.prefill([ptok], [pmask])
+    torch.cuda.synchronize()
+    ocache = orc.new_backbone_cache()
+    forced = torch.randint(0, 2051, (1, 32), generator=g)
+    tr = {}
+    olm.generate_frame(orc, ptok[None].long(), pmask[None], ocache, forced=forced, trace=tr)
+    print("h_last err", (st.h_last.cpu() - tr["h"]).abs().max().item(), "scale", tr["h"].abs().max().item())
+    print("c0 logits err", (st.c0_logits.cpu() - tr["logits"][0]).abs().max().item(), "scale", tr["logits"][0].abs().max().item())
+    frame = torch.zeros((1, 32), device=dev, dtype=torch.int32)
+    lg = torch.zeros((1, 32, 2051), device=dev)
+    fdev = forced.to(dev, torch.int32).contiguous()
+    st.depth_decode(frame, SamplerSpec(), logits_out=lg, forced=fdev)
+    torch.cuda.synchronize()
+    errs = [(lg[0, i].cpu() - tr["logits"][i][0]).abs().max().item() for i in range(1, 32)]
+    print("depth logits max err", max(errs), "frame==forced", bool((frame.cpu()[:, 1:] == forced[:, 1:].int()).all()))
+    # free-running greedy
+    t1 = time.time()
+    (toks,) = generation.generate_tokens(model, [(ptok, pmask)], 6, temperature=0.0)
+    torch.cuda.synchronize()
+    print("gpu 6 frames", time.time() - t1)
+    t1 = time.time()
+    otoks = olm.generate_tokens(orc, ptok.long(), pmask, 6)
+    print("oracle 6 frames", time.time() - t1)
+    print("tokens equal", bool((toks.long() == otoks).all()), (toks.long() != otoks).sum().item())
+    print(toks[:2, :8], otoks[:2, :8])
+
+
+@section("mimi")
+def _mimi():
+    MW = random_mimi_weights()
+    mimi = Mimi(32, device=dev).load_pytorch_weights(MW)
+    codes = torch.randint(0, 2048, (1, 32, 25))
+    a_or = omimi.decode(codes, MW)
+    a = mimi.decode(codes.to(dev)).cpu()
+    err = (a - a_or)
+    print("decode shape", a.shape, "max err", err.abs().max().item(), "snr dB", (10 * torch.log10(a_or.pow(2).mean() / err.pow(2).mean())).item())
+    # batch 2 + long (window)
+    codes2 = torch.randint(0, 2048, (2, 32, 140))
+    a2_or = omimi.decode(codes2, MW)
+    a2 = mimi.decode(codes2.to(dev)).cpu()
+    err = a2 - a2_or
+    print("decode B2 F140 snr dB", (10 * torch.log10(a2_or.pow(2).mean() / err.pow(2).mean())).item())
+    # streaming
+    stream = mimi.new_decode_stream(1, use_graph=True)
+    chunks = [stream.step(codes[:, :, i:i + 1].to(dev)).cpu().clone() for i in range(25)]
+    s = torch.cat(chunks, -1)
+    err = s - a_or
+    print("stream snr dB", (10 * torch.log10(a_or.pow(2).mean() / err.pow(2).mean())).item(), "graph", stream.graph is not None)
+    # encode
+    t = torch.arange(24000 * 5) / 24000.
+    gg = torch.Generator().manual_seed(11)
+    audio = (0.3 * torch.sin(2 * torch.pi * 220 * t) + 0.2 * torch.sin(2 * torch.pi * 3300 * t) + 0.05 * torch.randn(t.shape, generator=gg)).clamp(-1, 1)
+    for n in (120000, 120000 - 700):
+        c_or = omimi.encode(audio[None, None, :n], MW)
+        c = mimi.encode(audio[None, None, :n].to(dev)).cpu()
+        print("encode", n, c.shape, c_or.shape, "agree", (c.long() == c_or).float().mean().item(), "cb0", (c[0, 0].long() == c_or[0, 0]).float().mean().item())
+    tokenizers.set_audio_tokenizer(mimi)
+    # timing
+    for F in (25, 125):
+        cc = torch.randint(0, 2048, (1, 32, F), device=dev)
+        mimi.decode(cc); torch.cuda.synchronize()
+        t1 = time.time(); mimi.decode(cc); torch.cuda.synchronize()
+        print(f"decode F={F} {1e3 * (time.time() - t1):.2f} ms")
+    t1 = time.time()
+    for i in range(50):
+        stream.step(codes[:, :, :1].to(dev))
+    torch.cuda.synchronize()
+    print(f"stream step {1e3 * (time.time() - t1) / 50:.3f} ms")
+    x = audio[None, None].to(dev)
+    mimi.encode(x); torch.cuda.synchronize()
+    t1 = time.time(); mimi.encode(x); torch.cuda.synchronize()
+    print(f"encode 5s {1e3 * (time.time() - t1):.2f} ms")
+
+
+@section("time")
+def _time():
+    st = LMState(model, 1, max_len=256)
+    st.prefill([ptok], [pmask])
+    spec = SamplerSpec()
+    frame = torch.zeros((1, 32), device=dev, dtype=torch.int32)
+    st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+    prev = frame
+    for _ in range(3):
+        nf = torch.zeros_like(prev); st.decode_frame(prev, nf, spec); prev = nf
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t1 = time.time(); e0.record()
+    n = 20
+    for _ in range(n):
+        nf = torch.zeros_like(prev); st.decode_frame(prev, nf, spec); prev = nf
+    e1.record(); torch.cuda.synchronize()
+    print(f"decode_frame eager: {e0.elapsed_time(e1) / n:.3f} ms/frame (wall {1e3 * (time.time() - t1) / n:.3f})")
+    # CUDA graph of one frame
+    sprev = prev.clone(); sout = torch.zeros_like(prev)
+    gr = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        st.decode_frame(sprev, sout, spec)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(gr):
+        st.decode_frame(sprev, sout, spec)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        gr.replay(); sprev.copy_(sout)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"decode_frame graph: {ms:.3f} ms/frame -> {0.08 / (ms / 1e3):.1f} audio-s/s, {9.1067e9 / ms / 1e6:.0f} GB/s algorithmic")
