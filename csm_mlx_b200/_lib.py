@@ -61,6 +61,7 @@ _SIGS = {
     "csmb_strerror": (C.c_char_p, [_I]),
     "csmb_last_cuda_error": (C.c_char_p, []),
     "csmb_check_device": (C.c_int, [_I]),
+    "csmb_debug_launch_count": (C.c_ulonglong, []),
     "csmb_embed_sum": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "csmb_embed_audio": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_rmsnorm": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
@@ -68,7 +69,7 @@ _SIGS = {
     "csmb_swiglu": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "csmb_rope_kv_append": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "csmb_attention": (C.c_int, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "csmb_sample": (C.c_int, [_P, _I, _P, _I, _I, _I, C.POINTER(Sampler), C.c_uint64, _I, _P]),
+    "csmb_sample": (C.c_int, [_P, _I, _P, _I, _I, _I, C.POINTER(Sampler), C.c_uint64, _P, C.c_uint32, _I, _P]),
     "csmb_lm_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I]),
     "csmb_backbone_forward": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, _P, _I, _P, _I, _P, _P,
                                         _I, _P]),

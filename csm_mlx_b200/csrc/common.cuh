@@ -11,6 +11,7 @@ namespace csmb {
 
 // ---- host-side error plumbing -------------------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char* what);
+void count_launch();  // diagnostic counter behind csmb_debug_launch_count()
 
 #define CSMB_CUDA(expr)                                  \
   do {                                                   \
@@ -23,6 +24,7 @@ void set_cuda_error(cudaError_t e, const char* what);
 
 #define CSMB_LAUNCH_CHECK()                              \
   do {                                                   \
+    ::csmb::count_launch();                              \
     cudaError_t _e = cudaGetLastError();                 \
     if (_e != cudaSuccess) {                             \
       ::csmb::set_cuda_error(_e, "kernel launch");       \

@@ -29,6 +29,10 @@ void set_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 // ------------------------------------------------------------------------------------------------
 // embed_sum: one block per row; thread t handles 8 consecutive channels per iteration.
 __global__ void __launch_bounds__(256) k_embed_sum(const int32_t* __restrict__ tokens,
@@ -582,6 +586,8 @@ const char* csmb_strerror(int status) {
 
 const char* csmb_last_cuda_error(void) { return g_err; }
 
+unsigned long long csmb_debug_launch_count(void) { return csmb::launch_count(); }
+
 int csmb_check_device(int device) {
   cudaDeviceProp p;
   CSMB_CUDA(cudaGetDeviceProperties(&p, device));
@@ -636,10 +642,11 @@ int csmb_attention(const float* qkv, int ldq, const float* kv_pool, const int32_
 }
 
 int csmb_sample(const float* logits, int ldl, int32_t* out, int out_stride, int R, int V,
-                const csmb_sampler* sampler, uint64_t draw, int device, void* stream) {
+                const csmb_sampler* sampler, uint64_t draw, const int32_t* row_pos, uint32_t pos_mul, int device,
+                void* stream) {
   CSMB_ENTER(device);
   CSMB_REQUIRE(sampler != nullptr);
-  return launch_sample(logits, ldl, out, out_stride, R, V, *sampler, draw, nullptr, 0, nullptr, 0,
+  return launch_sample(logits, ldl, out, out_stride, R, V, *sampler, draw, row_pos, pos_mul, nullptr, 0,
                        (cudaStream_t)stream);
 }
 

@@ -122,7 +122,7 @@ class _Session:
             st.prefill([p[0] for p in self.prompts], [p[1] for p in self.prompts])
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
         elif self.host_sampler is None and not self.procs:
-            st.decode_frame(self.prev, frame, self.spec)
+            frame = st.decode_frame_graphed(self.prev, self.spec)
         else:
             st.backbone_step(self.prev)
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)

@@ -347,6 +347,17 @@ class MimiDecodeStream:
         self.use_graph = use_graph and not offline
         self._warm = 0
 
+    def reset(self) -> None:
+        """Back to the start-of-stream state (zero conv contexts, position 0); buffers and graph are kept."""
+        self.pos.zero_()
+        self.up_prev.zero_()
+        self.buf0[:, :6].zero_()
+        self.tr_in[:, :1].zero_()
+        for res_in, _ in self.bufs:
+            res_in[:, :2].zero_()
+        for i, nxt in enumerate(self.next_in):
+            nxt[:, : (2 if i == len(self.next_in) - 1 else 1)].zero_()
+
     def _run(self) -> None:
         m, B, F, T = self.m, self.B, self.F, self.T
         lib = _lib.lib()

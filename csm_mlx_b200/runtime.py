@@ -86,48 +86,54 @@ class LMState:
         return _lib.stream_ptr(self.device)
 
     # ------------------------------------------------------------------ steps
-    def prefill(self, tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
-        """Backbone over every sequence's prompt rows ((T_b,33) each); leaves h_last / c0_logits of the last
-        row of each sequence and advances positions (generation.py:34-42 with T>1)."""
+    def stage_prefill(self, tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> dict:
+        """Host -> device staging of prompt rows and their (sequence, position) maps; see ``prefill``."""
         assert len(tokens) == self.batch
         lens = [int(t.shape[0]) for t in tokens]
         for b, n in enumerate(lens):
             if self.pos_host[b] + n > self.max_len:
                 raise ValueError("sequence exceeds the KV pages reserved for it")
-        tok = torch.cat([t.to(torch.int32) for t in tokens], 0).to(self.device).contiguous()
-        msk = torch.cat([m.to(torch.uint8) for m in masks], 0).to(self.device).contiguous()
-        R = int(tok.shape[0])
-        seq = torch.cat([torch.full((n,), b, dtype=torch.int32) for b, n in enumerate(lens)]).to(self.device)
+        nb = dict(non_blocking=True)
+        tok = torch.cat([t.to(torch.int32) for t in tokens], 0).contiguous().to(self.device, **nb)
+        msk = torch.cat([m.to(torch.uint8) for m in masks], 0).contiguous().to(self.device, **nb)
+        seq = torch.cat([torch.full((n,), b, dtype=torch.int32) for b, n in enumerate(lens)]).to(self.device, **nb)
         pos = torch.cat([torch.arange(self.pos_host[b], self.pos_host[b] + n, dtype=torch.int32)
-                         for b, n in enumerate(lens)]).to(self.device)
+                         for b, n in enumerate(lens)]).to(self.device, **nb)
         ends, acc = [], 0
         for n in lens:
             acc += n
             ends.append(acc - 1)
-        last = torch.tensor(ends, dtype=torch.int32, device=self.device)
+        last = torch.tensor(ends, dtype=torch.int32).to(self.device, **nb)
+        new_pos = torch.tensor([p + n for p, n in zip(self.pos_host, lens)], dtype=torch.int32).to(self.device, **nb)
+        return {"tok": tok, "msk": msk, "seq": seq, "pos": pos, "last": last, "lens": lens, "new_pos": new_pos,
+                "h2d_bytes": tok.numel() * 4 + msk.numel() + seq.numel() * 4 + pos.numel() * 4 + last.numel() * 4
+                + new_pos.numel() * 4}
+
+    def run_prefill(self, staged: dict) -> None:
+        R = int(staged["tok"].shape[0])
         self._ensure_workspace(max(R, 2 * self.batch))
         bd = self._batch_desc()
         _lib.check(_lib.lib().csmb_backbone_forward(
-            C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
-            last.data_ptr(), self.batch, self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx,
-            self._stream()))
-        for b, n in enumerate(lens):
+            C.byref(self.model.desc()), C.byref(bd), staged["tok"].data_ptr(), staged["msk"].data_ptr(),
+            staged["seq"].data_ptr(), staged["pos"].data_ptr(), R, staged["last"].data_ptr(), self.batch,
+            self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx, self._stream()))
+        for b, n in enumerate(staged["lens"]):
             self.pos_host[b] += n
-        self.pos = torch.tensor(self.pos_host, dtype=torch.int32, device=self.device)
+        self.pos.copy_(staged["new_pos"])
+
+    def prefill(self, tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
+        """Backbone over every sequence's prompt rows ((T_b,33) each); leaves h_last / c0_logits of the last
+        row of each sequence and advances positions (generation.py:34-42 with T>1)."""
+        self.run_prefill(self.stage_prefill(tokens, masks))
 
     def sample_c0(self, frame: torch.Tensor, sampler: SamplerSpec, logits: Optional[torch.Tensor] = None) -> None:
         """frame[:,0] = sample(c0 logits)   (generation.py:51-56).  RNG draw index = (pos-1)*n_codebooks."""
         lg = self.c0_logits if logits is None else logits.to(device=self.device, dtype=torch.float32).contiguous()
         ncb = self.model.n_audio_codebooks
         s = sampler.to_c()
-        # per-sequence draw = frame position * ncb: positions differ across sequences, so sample row by row
-        # only when sampling stochastically with ragged positions; greedy ignores the draw index.
-        if sampler.temperature == 0 or len(set(self.pos_host)) == 1:
-            draw = (self.pos_host[0] - 1) * ncb
-            _lib.check(_lib.lib().csmb_sample(lg.data_ptr(), lg.shape[1], frame.data_ptr(), ncb, self.batch,
-                                              lg.shape[1], C.byref(s), draw, self.dev_idx, self._stream()))
-        else:
-            raise NotImplementedError("stochastic sampling with ragged positions goes through decode_frame")
+        pos_prev = (self.pos - 1).contiguous()  # position of the row that produced these logits
+        _lib.check(_lib.lib().csmb_sample(lg.data_ptr(), lg.shape[1], frame.data_ptr(), ncb, self.batch, lg.shape[1],
+                                          C.byref(s), 0, pos_prev.data_ptr(), ncb, self.dev_idx, self._stream()))
 
     def depth_decode(self, frame: torch.Tensor, sampler: SamplerSpec, logits_out: Optional[torch.Tensor] = None,
                      forced: Optional[torch.Tensor] = None, step_begin: int = 1, step_end: Optional[int] = None) -> None:
@@ -165,6 +171,35 @@ class LMState:
             C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
             C.byref(s), 0, self.dev_idx, self._stream()))
         self._advance()
+
+    def decode_frame_graphed(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
+        """decode_frame through a CUDA graph captured on first use (fixed buffers; positions live on the device
+        and advance inside the graph).  Returns a fresh (B, n_codebooks) int32 tensor."""
+        key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep, sampler.seed)
+        if getattr(self, "_graph_key", None) != key:
+            ncb = self.model.n_audio_codebooks
+            self._g_prev = torch.zeros((self.batch, ncb), device=self.device, dtype=torch.int32)
+            self._g_out = torch.zeros((self.batch, ncb), device=self.device, dtype=torch.int32)
+            self._g_prev.copy_(prev_frame)
+            pos_save, host_save = self.pos.clone(), list(self.pos_host)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.decode_frame(self._g_prev, self._g_out, sampler)
+            self.pos.copy_(pos_save)  # capture does not execute, but keep host/device views in lock-step
+            self.pos_host = host_save
+            self._graph, self._graph_key = g, key
+        self._check_room()
+        self._g_prev.copy_(prev_frame)
+        self._graph.replay()
+        self.pos_host = [p + 1 for p in self.pos_host]
+        return self._g_out.clone()
+
+    def reset(self) -> None:
+        """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply
+        overwritten; captured graphs stay valid because no buffer moves."""
+        self.pos_host = [0] * self.batch
+        self.pos.zero_()
 
     def _check_room(self) -> None:
         if max(self.pos_host) + 1 > self.max_len:

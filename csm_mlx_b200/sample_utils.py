@@ -34,7 +34,7 @@ class DeviceSampler:
         out = torch.empty((lg.shape[0],), device=lg.device, dtype=torch.int32)
         s = self.spec.to_c()
         _lib.check(_lib.lib().csmb_sample(lg.data_ptr(), lg.shape[1], out.data_ptr(), 1, lg.shape[0], lg.shape[1],
-                                          C.byref(s), self._calls, dev, _lib.stream_ptr(lg.device)))
+                                          C.byref(s), self._calls, None, 0, dev, _lib.stream_ptr(lg.device)))
         self._calls += 1
         return out[0] if squeeze else out
 

@@ -44,6 +44,8 @@ int csmb_abi_version(void);
 const char* csmb_strerror(int status);
 /* text of the last CUDA error seen by this library on any thread (diagnostic only; racy by nature). */
 const char* csmb_last_cuda_error(void);
+/* number of kernels this library has launched (enqueued or captured) so far in this process; diagnostic. */
+unsigned long long csmb_debug_launch_count(void);
 /* 0 if `device` is an sm_100 part this library was compiled for. */
 int csmb_check_device(int device);
 
@@ -91,7 +93,8 @@ int csmb_attention(const float* qkv, int ldq, const float* kv_pool, const int32_
  * temperature==0: argmax (lowest index on ties).  Otherwise top-k (k>0), top-p (0<p<1), min-p (>0,
  * keeping at least min_keep) filters on softmax(logits), then categorical(logits/temperature) by the
  * Gumbel-max trick: argmax_i(logits[i]/temperature - log(-log(u_i))), u_i from Philox4x32-10 with
- * key = seed and counter = (i/4, draw_lo, draw_hi, r), word i%4 of the output block. */
+ * key = seed and counter = (i/4, d_lo, d_hi, r), word i%4 of the output block, where the draw index
+ * d = draw + (row_pos ? row_pos[r] : 0) * pos_mul  (row_pos: optional DEVICE array [R]). */
 typedef struct {
   float temperature;
   int top_k;
@@ -102,7 +105,8 @@ typedef struct {
 } csmb_sampler;
 
 int csmb_sample(const float* logits, int ldl, int32_t* out, int out_stride, int R, int V,
-                const csmb_sampler* sampler /*host*/, uint64_t draw, int device, void* stream);
+                const csmb_sampler* sampler /*host*/, uint64_t draw, const int32_t* row_pos, uint32_t pos_mul,
+                int device, void* stream);
 
 /* ---------------------------------------------------------------- fused LM path ---------------- */
 

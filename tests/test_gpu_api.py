@@ -1,0 +1,92 @@
+"""End-to-end through the public csm_mlx API on the GPU (README.md:29-55 usage of the reference)."""
+import numpy as np
+import pytest
+import torch
+
+import csm_mlx
+from csm_mlx import Segment, generate, stream_generate
+from csm_mlx_b200 import generation, tokenizers
+from oracle import lm as olm
+from oracle import mimi as omimi
+from tests.conftest import snr_db
+from tests.workloads import cfg1_prompt_ids, synthetic_audio
+
+pytestmark = pytest.mark.gpu
+
+
+def test_generate_cfg1_audio_matches_oracle_pipeline(model_1b, mimi_gpu, oracle_1b, mimi_weights):
+    """generate() == oracle LM tokens -> oracle Mimi decode, for 5 frames of configs[0] (ids ≥ 2048 clamped)."""
+    audio = generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=400, temperature=0.0)
+    assert audio.dtype == torch.float32 and audio.shape == (5 * 1920,) and audio.device.type == "cpu"
+    assert np.asarray(audio).shape == (9600,)
+    tok, mask = olm.text_rows(cfg1_prompt_ids())
+    toks = olm.generate_tokens(oracle_1b, tok, mask, 5)
+    ref = omimi.decode(toks.t()[None].clamp(max=2047), mimi_weights)[0, 0]
+    assert snr_db(ref, audio) > 80
+
+
+def test_stream_generate_chunks_concat_to_generate(model_1b, mimi_gpu):
+    ids = cfg1_prompt_ids()
+    full = generate(model_1b, ids, 0, [], max_audio_length_ms=640, temperature=0.0)
+    chunks = list(stream_generate(model_1b, ids, 0, [], max_audio_length_ms=640, temperature=0.0))
+    assert len(chunks) == 8 and all(c.shape == (1920,) and c.dtype == torch.float32 for c in chunks)
+    assert snr_db(full, torch.cat(chunks)) > 80
+
+
+def test_generate_with_segment_context(model_1b, mimi_gpu, oracle_1b, mimi_weights):
+    """BASELINE.json configs[2] in miniature: one context Segment (1 s of synthetic audio, Mimi-encoded on the GPU)
+    then 3 generated frames; tokens equal the oracle fed with the oracle's own encode of the same audio."""
+    tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+    try:
+        clip = synthetic_audio(12, 1.0)
+        seg = Segment(speaker=1, text="context line", audio=clip)
+        prompt = generation._build_prompt(model_1b, "hello there", 0, [seg])
+        (got,) = generation.generate_tokens(model_1b, [prompt], 3, temperature=0.0)
+        tt = olm.text_rows(tokenizers.SyntheticTextTokenizer().encode("[1]context line"))
+        aa = olm.audio_rows(omimi.encode(clip[None, None], mimi_weights)[0])
+        t2 = olm.text_rows(tokenizers.SyntheticTextTokenizer().encode("[0]hello there"))
+        otok = torch.cat([tt[0], aa[0], t2[0]])
+        omask = torch.cat([tt[1], aa[1], t2[1]])
+        assert prompt[0].shape == otok.shape
+        if torch.equal(prompt[0].long(), otok):  # codes identical (expected) -> tokens must be identical
+            exp = olm.generate_tokens(oracle_1b, otok, omask, 3)
+            assert torch.equal(got.long(), exp)
+        else:  # a near-tie flipped an RVQ code: fall back to comparing on the product's own prompt
+            exp = olm.generate_tokens(oracle_1b, prompt[0].long(), prompt[1], 3)
+            assert torch.equal(got.long(), exp)
+    finally:
+        tokenizers.set_text_tokenizer(None)
+
+
+def test_sampler_argument_forms(model_1b, mimi_gpu):
+    ids = cfg1_prompt_ids()
+    a = generate(model_1b, ids, 0, [], max_audio_length_ms=160, sampler=csm_mlx.make_sampler(temp=0.8, top_k=50, seed=3))
+    b = generate(model_1b, ids, 0, [], max_audio_length_ms=160, sampler=csm_mlx.make_sampler(temp=0.8, top_k=50, seed=3))
+    c = generate(model_1b, ids, 0, [], max_audio_length_ms=160, temperature=0.8, seed=4)
+    assert torch.equal(a, b) and a.shape == c.shape == (3840,) and not torch.equal(a, c)
+    s = csm_mlx.make_sampler(temp=0.0)
+    assert int(s(torch.tensor([0.1, 0.9, 0.3], device=model_1b.device))) == 1
+
+
+def test_generate_frame_signature(model_1b):
+    """generate_frame(model, tokens, *, temperature, token_mask, cache, …) -> (B,32) int32 (generation.py:21-31,92)."""
+    tok, mask = tokenizers.tokenize_text_segment(cfg1_prompt_ids(), 0)
+    cache = generation.make_cache(model_1b, 1, 64)
+    f0 = generation.generate_frame(model_1b, tok[None], temperature=0.0, token_mask=mask[None], cache=cache)
+    assert f0.shape == (1, 32) and f0.dtype == torch.int32
+    nxt = torch.cat([f0.cpu(), torch.zeros(1, 1, dtype=torch.int32)], 1)[:, None]
+    nmask = torch.cat([torch.ones(1, 32), torch.zeros(1, 1)], 1)[:, None].bool()
+    f1 = generation.generate_frame(model_1b, nxt, temperature=0.0, token_mask=nmask, cache=cache)
+    (ref,) = generation.generate_tokens(model_1b, [(tok, mask)], 2, temperature=0.0)
+    assert torch.equal(torch.cat([f0, f1]).cpu(), ref)
+
+
+def test_generate_batch(model_1b, mimi_gpu):
+    from tests.workloads import prompt_ids
+
+    texts = [prompt_ids(21 + i, 8 + i) for i in range(3)]
+    audios, frames = csm_mlx.generate_batch(model_1b, texts, [0, 1, 2], max_audio_length_ms=240, temperature=0.0,
+                                            return_tokens=True)
+    assert len(audios) == 3 and all(a.shape == (3 * 1920,) for a in audios)
+    single = generate(model_1b, texts[1], 1, [], max_audio_length_ms=240, temperature=0.0)
+    assert snr_db(single, audios[1]) > 80

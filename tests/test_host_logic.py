@@ -1,0 +1,192 @@
+"""Host-side logic of the product package, no GPU: API surface, frame assembly, RoPE table, guards, samplers."""
+import os
+import re
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+import csm_mlx
+from csm_mlx_b200 import CSM, Segment, csm_1b, csm_tiny, tokenizers
+from csm_mlx_b200.attention import llama3_rope_table
+from csm_mlx_b200.random_init import csm_param_shapes, mimi_param_shapes, random_csm_weights
+from oracle import lm as olm
+from oracle import sampling as osamp
+
+
+def test_export_surface_matches_reference():
+    # /root/reference/csm_mlx/__init__.py:6-16
+    assert csm_mlx.__all__ == ["generate", "stream_generate", "CSM", "csm_1b", "Segment", "CSMDataset", "CSMTrainer",
+                               "TrainArgs", "load_adapters"]
+    from csm_mlx.generation import generate, generate_frame, stream_generate  # noqa: F401
+    from csm_mlx.tokenizers import decode_audio, tokenize_audio, tokenize_segment, tokenize_text_segment  # noqa: F401
+    from csm_mlx.utils import read_audio, write_audio  # noqa: F401
+    with pytest.raises(NotImplementedError):
+        csm_mlx.CSMTrainer()
+    with pytest.raises(NotImplementedError):
+        csm_mlx.load_adapters(None, "x")
+
+
+def test_model_args_and_param_tree():
+    a = csm_1b()
+    assert (a.backbone_name, a.decoder_name, a.n_text_vocab, a.n_audio_vocab, a.n_audio_codebooks) == \
+        ("1b", "100m", 128256, 2051, 32)
+    shapes = {n: s for n, s, _ in csm_param_shapes()}
+    assert shapes["audio_head"] == (31, 1024, 2051)
+    assert shapes["backbone.layers.15.mlp.down_proj.weight"] == (2048, 8192)
+    assert shapes["decoder.layers.3.self_attn.k_proj.weight"] == (256, 1024)
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    assert abs(n - 1552.8e6) < 1e6
+    m = CSM(a)
+    assert len(m.backbone.layers) == 16 and len(m.decoder.layers) == 4
+    assert m.backbone.args.max_position_embeddings is None
+    n_mimi = sum(int(np.prod(s)) for _, s, _ in mimi_param_shapes())
+    assert abs(n_mimi - 96.15e6) < 0.1e6
+
+
+def test_load_weights_strictness():
+    m = CSM(csm_tiny())
+    W = random_csm_weights(csm_tiny(), seed=1)
+    bad = dict(W)
+    bad["nope"] = torch.zeros(1)
+    with pytest.raises(ValueError, match="not in model"):
+        m.load_weights(bad)
+    miss = dict(W)
+    del miss["audio_head"]
+    with pytest.raises(ValueError, match="Missing"):
+        m.load_weights(miss)
+    shp = dict(W)
+    shp["projection.weight"] = torch.zeros(3, 3)
+    with pytest.raises(ValueError, match="shape"):
+        m.load_weights(shp)
+    with pytest.raises(ValueError, match="Unsupported"):
+        m.load_weights("weights.bin")
+    with pytest.raises(RuntimeError, match="not loaded"):
+        m.parameters()
+
+
+def test_random_init_is_deterministic_and_fills_everything():
+    a, b = random_csm_weights(csm_tiny(), seed=3), random_csm_weights(csm_tiny(), seed=3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert float(a["audio_head"].float().abs().max()) > 0  # the reference leaves audio_head at zeros (models.py:65-67)
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_rope_table_matches_oracle_bit_for_bit(hd):
+    t = llama3_rope_table(hd, 500_000.0, 32.0, 2048)
+    o = olm.rope_table(hd, 500_000.0, 32.0, 2048)
+    assert t.shape == (2048, hd // 2, 2) and torch.equal(t, o)
+    # attention.py:102-117: high frequencies untouched, low ones divided by 32
+    base = 1.0 / (500_000.0 ** (torch.arange(0, hd, 2).float() / hd))
+    f = olm.rope_scaled_freqs(hd, 500_000.0, 32.0)
+    lo, hi = (14, 18) if hd == 64 else (28, 35)
+    assert torch.equal(f[: lo + 1], base[: lo + 1])
+    torch.testing.assert_close(f[hi:], base[hi:] / 32.0)
+
+
+def test_text_and_audio_rows():
+    tok, mask = tokenizers.tokenize_text_segment([128000, 5, 6, 128001], speaker=0)
+    assert tok.shape == (4, 33) and tok.dtype == torch.int32
+    assert tok[:, 32].tolist() == [128000, 5, 6, 128001] and int(tok[:, :32].abs().sum()) == 0
+    assert mask[:, 32].all() and not mask[:, :32].any()
+    otok, omask = olm.text_rows([128000, 5, 6, 128001])
+    assert torch.equal(tok.long(), otok) and torch.equal(mask, omask)
+
+    class FakeMimi:
+        def encode(self, x):
+            assert x.shape == (1, 1, 4000)
+            return torch.arange(32 * 3, dtype=torch.int32).reshape(1, 32, 3) + 1
+
+    tokenizers.set_audio_tokenizer(FakeMimi())
+    try:
+        at, am = tokenizers.tokenize_audio(torch.zeros(4000))
+        assert at.shape == (4, 33) and int(at[3].abs().sum()) == 0  # appended EOS frame (tokenizers.py:73-75)
+        assert am[:, :32].all() and not am[:, 32].any()
+        oat, oam = olm.audio_rows(torch.arange(32 * 3).reshape(32, 3) + 1)
+        assert torch.equal(at.long(), oat) and torch.equal(am, oam)
+        seg = Segment(1, "x", torch.zeros(4000))
+        tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+        st, sm = tokenizers.tokenize_segment(seg)
+        n_text = len(tokenizers.SyntheticTextTokenizer().encode("[1]x"))
+        assert st.shape == (n_text + 4, 33) and st[0, 32] == 128000 and st[n_text - 1, 32] == 128001
+    finally:
+        tokenizers.set_audio_tokenizer(None)
+        tokenizers.set_text_tokenizer(None)
+
+
+def test_segment_contract(tmp_path):
+    s = Segment(0, "hi", None, None)  # positional order of cli/generate.py:186-189
+    with pytest.raises(ValueError):
+        _ = s.audio
+    s.audio = torch.ones(3)
+    assert s.audio.shape == (3,)
+    # audio_path is read + resampled to 24 kHz mono on access (segment.py:23-28, utils.py:9-21)
+    p = tmp_path / "a.wav"
+    sr = 48000
+    sig = (np.sin(2 * np.pi * 440 * np.arange(sr) / sr) * 0.5 * 32767).astype("<i2")
+    with wave.open(str(p), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes(np.stack([sig, sig], 1).tobytes())
+    a = Segment(0, "hi", None, p).audio
+    assert a.dtype == torch.float32 and a.shape == (24000,) and 0.3 < float(a.abs().max()) < 0.6
+    from csm_mlx_b200.utils import read_audio, write_audio
+    q = tmp_path / "b.wav"
+    write_audio(a, q, 24000)
+    b = read_audio(q, 24000)
+    assert b.shape == a.shape and float((a - b).abs().max()) < 1e-3
+
+
+def test_prompt_length_guard():
+    from csm_mlx_b200.generation import _check_length
+
+    m = CSM(csm_1b())
+    _check_length(m, 10, 125)
+    with pytest.raises(ValueError, match="Inputs too long"):
+        _check_length(m, 2048 - 125, 125)  # generation.py:132-137
+
+
+def test_no_cpu_fallback():
+    from csm_mlx_b200 import _lib
+
+    with pytest.raises(_lib.CsmbError):
+        _lib.require_device(torch.device("cpu"))
+    with pytest.raises(_lib.CsmbError):
+        _lib.ptr(torch.zeros(4))
+    if not torch.cuda.is_available():
+        m = CSM(csm_tiny())
+        with pytest.raises(Exception):
+            m.load_weights(random_csm_weights(csm_tiny(), seed=1))  # must not silently run on the CPU
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for base in ("csm_mlx_b200", "csm_mlx"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_philox_known_answers():
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]  # Random123 kat_vectors, philox4x32 10 rounds
+    for ctr, key, out in kat:
+        r = osamp.philox4x32_10(np.array(ctr, dtype=np.uint32), key)
+        assert tuple(int(x) for x in r) == out
+
+
+def test_oracle_sampler_filters():
+    lg = np.log(np.array([0.5, 0.2, 0.15, 0.1, 0.05], dtype=np.float32))
+    assert osamp.keep_mask(lg, top_k=2).tolist() == [True, True, False, False, False]
+    assert osamp.keep_mask(lg, top_p=0.6).tolist() == [True, True, False, False, False]   # 0 < .6, .5 < .6, .7 !< .6
+    assert osamp.keep_mask(lg, min_p=0.25).tolist() == [True, True, True, False, False]   # p >= .125
+    assert osamp.keep_mask(lg, min_p=0.9, min_keep=3).tolist() == [True, True, True, False, False]
+    assert osamp.sample(lg, 0.0) == 0
+    draws = [osamp.sample(lg, 1.0, seed=1, draw=d) for d in range(400)]
+    freq = np.bincount(draws, minlength=5) / 400
+    assert abs(freq[0] - 0.5) < 0.1 and abs(freq[1] - 0.2) < 0.08
+    assert set(osamp.sample(lg, 1.0, seed=1, draw=d, top_k=2) for d in range(100)) == {0, 1}
