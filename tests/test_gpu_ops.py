@@ -68,8 +68,9 @@ def test_embed_sum_and_embed_audio(device):
     tok[2:, :32] = torch.randint(0, V, (4, 32), generator=g).int(); mask[2:, :32] = 1
     mask[5, 3] = 0  # ragged mask
     out = torch.empty(6, d, device=device)
-    _lib.check(_lib.lib().csmb_embed_sum(tok.to(device).data_ptr(), mask.to(device).data_ptr(), text.to(device).data_ptr(),
-                                         audio.to(device).data_ptr(), out.data_ptr(), 6, d, ncb, V, 0, _st(device)))
+    tok_d, mask_d, text_d, adev = tok.to(device), mask.to(device), text.to(device), audio.to(device)  # keep alive
+    _lib.check(_lib.lib().csmb_embed_sum(tok_d.data_ptr(), mask_d.data_ptr(), text_d.data_ptr(), adev.data_ptr(),
+                                         out.data_ptr(), 6, d, ncb, V, 0, _st(device)))
     W = {"text_embeddings.weight": text.float(), "audio_embeddings.weight": audio.float()}
     orc = olm.OracleCSM.__new__(olm.OracleCSM)
     orc.cfg, orc.W = olm.CSM_1B, W
@@ -77,7 +78,6 @@ def test_embed_sum_and_embed_audio(device):
     assert float((out.cpu() - ref).abs().max()) < 1e-6
     ids = torch.tensor([0, 2050, 77], dtype=torch.int32, device=device)
     o2 = torch.empty(3, d, device=device)
-    adev = audio.to(device)
     _lib.check(_lib.lib().csmb_embed_audio(ids.data_ptr(), adev.data_ptr(), o2.data_ptr(), d, 3, d, 5, V, 0, _st(device)))
     assert torch.equal(o2.cpu(), audio[ids.cpu().long() + 5 * V].float())
 
