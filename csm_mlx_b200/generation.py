@@ -114,6 +114,7 @@ class _Session:
         self.c0_history: Optional[list] = [] if logits_processors else None
         self.prev: Optional[torch.Tensor] = None
         self.B = B
+        self.fused = os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"
 
     def step(self) -> torch.Tensor:
         st, model = self.state, self.model
@@ -122,7 +123,10 @@ class _Session:
             st.prefill([p[0] for p in self.prompts], [p[1] for p in self.prompts])
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
         elif self.host_sampler is None and not self.procs:
-            frame = st.decode_frame_graphed(self.prev, self.spec)
+            if self.fused and st.fused_supported(self.spec):
+                frame = st.decode_frame_fused(self.prev, self.spec)
+            else:
+                frame = st.decode_frame_graphed(self.prev, self.spec)
         else:
             st.backbone_step(self.prev)
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
@@ -210,6 +214,7 @@ def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tens
         pending = slot
     if pending is not None:
         drain(pending)
+    sess.state.check_status()
     return [torch.stack(f) if f else torch.zeros((0, ncb), dtype=torch.int32) for f in out]
 
 
@@ -277,6 +282,7 @@ def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, c
         if pending is not None:
             host_frame, host_audio = mirror.wait(pending)
             if not bool(host_frame.any()):
+                sess.state.check_status()
                 return  # eos: the speculative frame just enqueued is discarded
             yield host_audio.reshape(-1).clone()
         pending = slot
@@ -284,3 +290,4 @@ def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, c
         host_frame, host_audio = mirror.wait(pending)
         if bool(host_frame.any()):
             yield host_audio.reshape(-1).clone()
+    sess.state.check_status()

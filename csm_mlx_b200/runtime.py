@@ -195,6 +195,38 @@ class LMState:
         self.pos_host = [p + 1 for p in self.pos_host]
         return self._g_out.clone()
 
+    # ------------------------------------------------------------------ fused persistent frame kernel (B = 1)
+    def fused_supported(self, sampler: SamplerSpec) -> bool:
+        a, d = self.model.backbone.args, self.model.decoder.args
+        shape = (a.hidden_size, a.num_attention_heads, a.num_key_value_heads, a.head_dim, d.hidden_size,
+                 d.num_attention_heads, d.num_key_value_heads, d.head_dim) == (2048, 32, 8, 64, 1024, 8, 2, 128)
+        plain = sampler.temperature == 0 or not ((sampler.top_k and sampler.top_k > 0) or 0 < sampler.top_p < 1
+                                                 or sampler.min_p > 0)
+        return self.batch == 1 and shape and plain and 3 <= self.model.n_audio_codebooks <= 32
+
+    def decode_frame_fused(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
+        """One whole frame in the persistent kernel (csmb_frame_b1).  Returns a fresh (1, n_codebooks) tensor."""
+        if getattr(self, "_fws", None) is None:
+            nbytes = _lib.lib().csmb_frame_workspace_bytes(C.byref(self.model.desc()))
+            self._fws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)
+            self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)
+        self._check_room()
+        frame = torch.empty((1, self.model.n_audio_codebooks), device=self.device, dtype=torch.int32)
+        s = sampler.to_c()
+        prev = prev_frame if prev_frame.dtype == torch.int32 and prev_frame.is_contiguous() else prev_frame.to(torch.int32).contiguous()
+        _lib.check(_lib.lib().csmb_frame_b1(
+            C.byref(self.model.desc()), self.kv_pool.data_ptr(), self.kv_pool.stride(0), self.block_table.data_ptr(),
+            prev.data_ptr(), self.pos.data_ptr(), frame.data_ptr(), C.byref(s), 0, self._fws.data_ptr(),
+            self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
+        self._advance()
+        return frame
+
+    def check_status(self) -> None:
+        """Raises if the persistent kernel reported a timed-out wait (synchronises)."""
+        st = getattr(self, "frame_status", None)
+        if st is not None and int(st.item()) != 0:
+            raise _lib.CsmbError(f"persistent frame kernel aborted (code {int(st.item())})")
+
     def reset(self) -> None:
         """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply
         overwritten; captured graphs stay valid because no buffer moves."""
