@@ -174,6 +174,8 @@ def run_ours(args):
 
     st = LMState(model, 1, max_len=tok.shape[0] + frames + 1)
     codec = mimi.new_decode_stream(1)
+    fused = st.fused_supported(spec) and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"
+    next_frame = (lambda fr: st.decode_frame_fused(fr, spec)) if fused else (lambda fr: st.decode_frame_graphed(fr, spec))
 
     def device_step(timed: bool):
         st.reset()
@@ -191,7 +193,7 @@ def run_ours(args):
             tokens_dev[f].copy_(frame[0])
             audio_dev[f].copy_(codec.step(frame.reshape(1, ncb, 1)).reshape(-1))
             if f + 1 < frames:
-                frame = st.decode_frame_graphed(frame, spec)
+                frame = next_frame(frame)
         e1.record()
         torch.cuda.synchronize(dev)
         launches["eager"] = lib.csmb_debug_launch_count() - c0
@@ -270,13 +272,13 @@ def run_ours(args):
     st.sample_c0(fr, spec)
     st.depth_decode(fr, spec)
     for _ in range(3):
-        fr = st.decode_frame_graphed(fr, spec)
+        fr = next_frame(fr)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nf = 60
     e0.record()
     for _ in range(nf):
-        fr = st.decode_frame_graphed(fr, spec)
+        fr = next_frame(fr)
     e1.record()
     torch.cuda.synchronize(dev)
     frame_ms = e0.elapsed_time(e1) / nf
@@ -312,10 +314,14 @@ def run_ours(args):
                 "ms_per_step": 1e3 * t_e2e, "api": "csm_mlx.stream_generate"},
         "latency_ms": {"p50": pct(0.5), "p90": pct(0.9), "what": "time between successive stream_generate chunks on the host"},
         "gpu_launches": int(launches.get("eager", 0)) + 0,
-        "gpu_launches_note": "kernels enqueued eagerly per device step; each frame's CUDA graph replays its captured kernels on top",
+        "gpu_launches_note": "kernels of libcsm_b200 enqueued per device step: prefill + first frame per-op, then 1 persistent k_frame per frame; "
+                             "the Mimi streaming step replays a CUDA graph of ~110 captured kernels per frame on top",
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "LM frame (backbone step + 31-step depth loop)", "ms_per_frame": frame_ms,
+                     "traffic": 9.1139e9 if fused else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_frame, profiles/r01_frame_kernel_ncu.md" if fused else None,
+                     "kernel": "csmb::k_frame (persistent whole-frame kernel)" if fused else "LM frame as a CUDA graph of per-op kernels",
+                     "ms_per_frame": frame_ms,
                      "algorithmic_bytes_per_frame": alg, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
         "cpu_baseline": cpu,
         "tokens_checksum": int(sum(int(t.long().sum()) for t in all_tokens)) if all_tokens else None,

@@ -3,38 +3,44 @@
 // One cooperative launch computes one 80 ms frame of generate_frame (csm_mlx/generation.py:21-92, T=1) for ONE
 // sequence: embedding sum of the previous frame, 16-layer backbone step over the paged KV cache, codebook0 head +
 // sample, then the 31-step depth-decoder loop with per-step head, sampling and next-embedding gather — without
-// returning to the host.  ~640 dependent GEMV phases per frame make per-kernel launches latency-bound; here
-//   * one PRODUCER warp per CTA walks the statically known weight schedule (its row slice of every matrix, in
-//     order) and streams it HBM -> shared memory with cp.async.bulk into a 12 x 16 KiB ring guarded by mbarriers;
-//     it never waits for activations, so HBM stays busy across phase boundaries (ring = 28 MB chip-wide);
-//   * eight CONSUMER warps per CTA wait at a grid-wide barrier only for the activation vector of the phase, keep
-//     their K-slice of it in registers and reduce 1024-weight units (bf16 -> fp32 by bit shift, fp32 FMA) out of
-//     the ring; rows are split evenly across the 148 CTAs so every matrix is read exactly once per use;
-//   * activations (fp32) travel between CTAs through L2 (ld.global.cg), the depth decoder's per-frame KV state
-//     (256 KiB) stays L2-resident, attention of the small decoder is recomputed by every CTA, the backbone's
-//     attention is split over (kv-head, key-chunk) work items and merged by the consumers of the o-projection.
-// Algorithmic bytes per launch: 9.107 GB of bf16 weights; nothing is read twice.
+// returning to the host.  ~700 dependent GEMV phases per frame make per-kernel launches latency-bound; here
+//   * one PRODUCER thread per CTA walks the statically known weight schedule (its row slice of every matrix, in
+//     order) and streams it HBM -> shared memory with cp.async.bulk (L2 evict-first) into an 8 x 16 KiB ring guarded
+//     by mbarriers; it never waits for activations;
+//   * eight CONSUMER warps per CTA keep their K-slice of the phase's activation vector in registers and reduce
+//     1024-weight units (bf16 -> fp32 by bit shift, fp32 FMA) out of the ring; rows are split evenly across the 148
+//     CTAs so every matrix is read from HBM exactly once per use (9.107 GB per frame);
+//   * there is NO grid barrier: every cross-CTA activation is stored as an 8-byte {fp32 value, tag} word (the tag
+//     names the launch and the phase that produced it, like NCCL's LL protocol) and readers poll the data itself
+//     with L1-bypassing loads, so a phase boundary costs one store flight + one L2 round trip instead of
+//     release-fence + atomic + poll + acquire-fence (measured 2.1 us per barrier, x640 per frame).  A CTA can run at
+//     most one phase ahead of the slowest one — to start phase q it needs every CTA's output of phase q-1 — which is
+//     exactly what the buffer reuse distances tolerate (every buffer is rewritten only after its last reading phase);
+//   * attention of the small decoder is recomputed by every CTA from its PRIVATE copy of the frame's decoder KV (no
+//     cross-CTA dependency); the backbone's attention is split over (kv-head, 128-key chunk) work items.
 //
 // All spin loops are bounded: on timeout a sticky abort flag is raised, every wait falls through and the host
 // reports an error instead of hanging the GPU.
-#include <cooperative_groups.h>
 #include <math.h>
+
+#include <atomic>
 
 #include "ops.cuh"
 
 namespace csmb {
 
 constexpr int NCW = 8;                  // consumer warps
+constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int NTHREADS = (NCW + 1) * 32;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGES = 8;
 constexpr int UNIT = 1024;              // weights per (warp, stage) unit
 constexpr int MAXU = 128;               // max units per range per CTA (csm_1b: <= 112)
 constexpr int MAX_SPLIT = 16;           // backbone attention chunks (128 keys each) per head
-constexpr int PSTRIDE = 68;             // floats per attention partial: acc[64], m, l, pad (16-byte aligned rows)
-constexpr int KROW = 512;               // floats per staged decoder-KV position: K (2 x 128) then V (2 x 128)
+constexpr int PSTRIDE = 72;             // words per attention partial: acc[64], m, l, pad (32 heads x 72 = 9 x 256)
+constexpr int KROW = 512;               // floats per decoder-KV position: K (2 x 128) then V (2 x 128)
 constexpr int KVS_BYTES = 32 * KROW * 4;  // shared-memory staging of one decoder layer's K/V
-constexpr unsigned SPIN_LIMIT = 1u << 22;     // ~1-2 s of polling before a wait gives up
+constexpr unsigned SPIN_LIMIT = 1u << 22;  // ~1-2 s of polling before a wait gives up
 
 struct FrameParams {
   csmb_model m;
@@ -42,25 +48,24 @@ struct FrameParams {
   float* kv_pool;
   unsigned long long kv_layer_stride;
   const int32_t* block_table;  // this sequence's row
-  float* dec_kv;               // [Ld][32 pos][2][Hkv_d*hd_d]
   const int32_t* prev_frame;   // [ncb]
   const int32_t* pos_ptr;      // position of this frame's backbone row
   int32_t* frame_out;          // [ncb]
-  // scratch (global, L2-resident)
-  float *xa, *xb;              // backbone residual stream ping-pong [d_b]
-  float* qkv;                  // [2][max qkv]
-  float* attn_part;            // [H_b][MAX_SPLIT][PSTRIDE]
-  float* attn_out;             // [H_b*hd_b] merged attention output (single-chunk fast path)
-  float* act;                  // [2][d_ff]
-  float* h_last;               // [d_b]
-  float* logits;               // [V]
-  float *dxa, *dxb;            // decoder residual stream ping-pong [2][d_d]
-  int pf_max;                  // producer: L2 prefetch distance in 16 KiB stages (0 = off)
-  int pf_interval;             // producer: SM cycles between L2 prefetches (paces them at the HBM fair share)
-  int dbg;                     // debug switches (0 in production): 1 = skip GEMV math, 2 = skip decoder attention math
-  unsigned long long* prof;    // optional [gridDim][16] phase timers in ns (debug); null in production
-  unsigned int* bar;           // grid barrier counter (zeroed by the host before launch)
+  float* h_last;               // [d_b] (plain; output only)
+  float* dec_kv;               // [CTA][Ld][32 pos][KROW]: every CTA keeps its own copy of the frame's decoder KV
+  // cross-CTA activations: tagged words {value bits, tag}
+  uint2 *xa, *xb;              // backbone residual stream ping-pong [d_b]
+  uint2* qkv;                  // [2][max qkv]
+  uint2* attn_part;            // [MAX_SPLIT chunks][H_b][PSTRIDE]
+  uint2* attn_out;             // [H_b*hd_b] attention output (single-chunk fast path)
+  uint2* act;                  // [2][d_ff]
+  uint2* logits;               // [V]
+  uint2 *dxa, *dxb;            // decoder residual stream ping-pong [2][d_d]
+  unsigned* nonce;             // launch counter in the workspace: read by every CTA at start, bumped by CTA 0 at the
+                               // end, so consecutive launches (also CUDA-graph replays) never share tags
   int* abort_flag;
+  int dbg;                     // debug switches (0 in production): 1 = skip GEMV math, 8 = no weight streaming
+  unsigned long long* prof;    // optional [gridDim][16] phase timers in SM cycles (debug); null in production
   // sampling
   float inv_temp;
   uint32_t seed_lo, seed_hi;
@@ -101,29 +106,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_plain(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+
+// ---- tagged ("LL") words: value and tag travel in one 8-byte (or two in one 16-byte) store/load
+__device__ __forceinline__ void ll_st(uint2* p, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_st2(uint2* p, float a, float b, unsigned tag) {  // p 16-byte aligned
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag),
+               "r"(__float_as_uint(b)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ll_ld(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ll_ld2(const uint2* p) {  // two consecutive words, p 16-byte aligned
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// Activation loads.  Cross-CTA data is always consumed after a grid barrier whose acquire fence (fence.acq_rel.gpu
-// by thread 0, then bar.sync) invalidates this SM's L1, so ordinary weak loads are both legal under the PTX memory
-// model and fresh; ld.global.cg compiles to LDG.STRONG.GPU, which was measured to cost several L2 round trips per
-// batch of eight (the "load" phase took 2.5-4.6k cycles).
-#ifndef CSMB_FRAME_STRONG_LOADS
-__device__ __forceinline__ float4 ldcg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-#else
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-#endif
 
 struct Ring {
   unsigned char* data;
@@ -136,39 +145,27 @@ struct Ctx {
   Ring ring;
   float* part;     // smem [2 ranges][2 rows][MAXU][4]
   float* sred;     // smem scratch [NCW*4]
-  float* sattn;    // smem scratch for attention
+  float* sattn;    // smem: [0,2048) gathered activation vector / decoder attention output; then attention scratch
   float* kvs;      // smem staging of one decoder layer's cached K/V
   uint64_t* kvbar; // mbarrier of that staging copy
   uint32_t kv_phase;
   int G, cta, warp, lane, tid;
   uint32_t q;      // ring stage sequence number (same sequence in producer and consumers)
-  uint32_t epoch;  // grid barrier epoch
+  uint32_t phase;  // activation phase counter (same sequence in every CTA); part of the tag
+  uint32_t launch; // tag nonce of this launch (1 .. 2^20-1)
   bool aborted;
-  volatile int* s_abort;  // smem: thread 0 publishes the abort state to its CTA at every grid barrier
-  uint64_t policy;  // L2 evict-first policy of the weight stream (producer)
+  uint64_t policy;
   unsigned long long t_acc[12];
   unsigned long long t_last;
-  int ntrace;
 };
 
-__device__ __forceinline__ unsigned long long gtime() { return (unsigned long long)clock64(); }  // SM cycles
-// phase timers: thread 0 of every CTA accumulates the time since the previous mark into category `cat`
-enum { T_SYNC = 0, T_LOAD = 1, T_GEMV = 2, T_FIN = 3, T_DATT = 4, T_BATT = 5, T_SAMPLE = 6, T_MERGE = 7, T_WAIT = 8, T_ARRIVE = 9 };
+// phase timers (debug): thread 0 of every CTA accumulates the cycles since the previous mark into category `cat`
+enum { T_POLL = 0, T_LOAD = 1, T_GEMV = 2, T_FIN = 3, T_DATT = 4, T_BATT = 5, T_SAMPLE = 6, T_MERGE = 7, T_WAIT = 8 };
 __device__ __forceinline__ void mark(Ctx& c, int cat) {
   if (c.p->prof != nullptr && c.tid == 0) {
-    const unsigned long long t = gtime();
+    const unsigned long long t = (unsigned long long)clock64();
     c.t_acc[cat] += t - c.t_last;
     c.t_last = t;
-  }
-}
-
-// raw event trace (debug bit 4): thread 0 of CTA 1 appends (id, clock) pairs after the per-CTA timer block
-__device__ __forceinline__ void trace(Ctx& c, int id) {
-  if ((c.p->dbg & 4) && c.p->prof != nullptr && c.tid == 0 && c.cta == 1 && c.ntrace < 6000) {
-    unsigned long long* t = c.p->prof + 148 * 16 + 2 * (size_t)c.ntrace;
-    t[0] = (unsigned long long)id;
-    t[1] = (unsigned long long)clock64();
-    c.ntrace++;
   }
 }
 
@@ -180,7 +177,6 @@ __device__ __forceinline__ void raise_abort(Ctx& c, int code) {
   atomicCAS(c.p->abort_flag, 0, code);
   c.aborted = true;
 }
-
 __device__ __forceinline__ void mbar_wait(Ctx& c, uint64_t* b, uint32_t parity, int code) {
   if (c.aborted) return;
   unsigned spins = 0;
@@ -192,35 +188,18 @@ __device__ __forceinline__ void mbar_wait(Ctx& c, uint64_t* b, uint32_t parity, 
     if ((spins & 1023) == 0 && check_abort(c)) return;
   }
 }
-
-// Grid-wide barrier among the consumer warps of all CTAs: one monotonically increasing counter (zeroed by the host
-// before the launch), one arriving/polling thread per CTA.  (A per-CTA flag array polled by every CTA was measured
-// 3x slower: 148 x 160 loads per poll round serialise on a handful of L2 lines.)
-__device__ __forceinline__ void grid_sync(Ctx& c) {
-  trace(c, 10);
-  named_bar_sync(1, NCW * 32);
-  trace(c, 11);
-  c.epoch++;
-  if (c.tid == 0) {
-    red_release_add(c.p->bar, 1u);
-    trace(c, 12);
-    mark(c, T_ARRIVE);
-    const unsigned target = c.epoch * (unsigned)c.G;
-    unsigned spins = 0;
-    while (!c.aborted && ld_relaxed(c.p->bar) < target) {
-      if (++spins > SPIN_LIMIT) raise_abort(c, 100 + (int)(c.epoch & 0xffff));
-      if ((spins & 255) == 0) check_abort(c);
-    }
-    trace(c, 13);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    trace(c, 14);
-    if (c.aborted) *c.s_abort = 1;
+// bookkeeping of a tag-poll loop: returns false when the caller must give up
+__device__ __forceinline__ bool poll_continue(Ctx& c, unsigned& spins, int code) {
+  if (++spins > SPIN_LIMIT) {
+    raise_abort(c, code);
+    return false;
   }
-  named_bar_sync(1, NCW * 32);
-  trace(c, 15);
-  if (*c.s_abort) c.aborted = true;
-  mark(c, T_SYNC);
+  if ((spins & 255) == 0 && check_abort(c)) return false;
+  return true;
 }
+__device__ __forceinline__ unsigned cur_tag(const Ctx& c) { return (c.launch << 12) | (c.phase & 0xfffu); }
+// consumer-side sync (shared-memory results visible to all consumer warps)
+__device__ __forceinline__ void csync() { named_bar_sync(2, NCT); }
 
 // ------------------------------------------------------------------------------------------------ row partition
 struct Range {
@@ -235,30 +214,19 @@ __device__ __forceinline__ int n_stages(const Range& r) {
   return (int)(((size_t)r.rows * r.K * 2 + STAGE_BYTES - 1) / STAGE_BYTES);
 }
 
-// consumer: partial dot products of R activation rows with every unit of the range.  Two ring stages are processed
-// per iteration so that the two units' load -> FMA -> shuffle chains overlap; the lane reduction stops after three
-// shuffle steps and leaves 4 partials per unit in shared memory: part[(r*MAXU + u)*4 + 0..3], summed by the finaliser.
-template <int R>
-__device__ __forceinline__ void unit_dot(const unsigned char* base, const float (&xr)[R][32], float (&acc)[R]) {
-#pragma unroll
-  for (int i = 0; i < R; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    const uint4 w = *reinterpret_cast<const uint4*>(base + ch * 512);
-    const float wf[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y),
-                         bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[i] = fmaf(wf[e], xr[i][ch * 8 + e], acc[i]);
-  }
-}
+// ------------------------------------------------------------------------------------------------ consumer GEMV
+// Partial dot products of R activation rows with every unit of the range.  Two ring stages are processed per
+// iteration, both unconditionally (a missing second stage just produces an unused value) so that their LDS -> FMA ->
+// shuffle chains interleave; two accumulators per (unit, row) halve the dependent-FMA chain.  The lane reduction
+// stops after three shuffle steps and leaves 4 partials per unit: part[(r*MAXU + u)*4 + 0..3].
 template <int R>
 __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float* part) {
   if (c.p->dbg & 8) return;  // timing experiment: no streaming at all (pure latency chain)
   const int KS = r.K / UNIT;
   const int units = r.rows * KS;
   const int nst = n_stages(r);
+  const bool math = !(c.p->dbg & 1);
+  const size_t woff = (size_t)c.warp * (UNIT * 2) + c.lane * 16;
   for (int s = 0; s < nst; s += 2) {
     const bool two = s + 1 < nst;
     const int slot0 = c.q % NSTAGES, slot1 = (c.q + 1) % NSTAGES;
@@ -268,26 +236,45 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     if (two) mbar_wait(c, &c.ring.full[slot1], par1, 2);
     mark(c, T_WAIT);
     const int u0 = s * NCW + c.warp, u1 = u0 + NCW;
-    const bool run = !c.aborted && !(c.p->dbg & 1);
-    const bool do0 = u0 < units && run, do1 = two && u1 < units && run;
-    float a0[R], a1[R];
+    float a0[R][2], a1[R][2];
 #pragma unroll
-    for (int i = 0; i < R; ++i) a0[i] = a1[i] = 0.f;
-    const size_t woff = (size_t)c.warp * (UNIT * 2) + c.lane * 16;
-    if (do0) unit_dot<R>(c.ring.data + (size_t)slot0 * STAGE_BYTES + woff, xr, a0);
-    if (do1) unit_dot<R>(c.ring.data + (size_t)slot1 * STAGE_BYTES + woff, xr, a1);
+    for (int i = 0; i < R; ++i) a0[i][0] = a0[i][1] = a1[i][0] = a1[i][1] = 0.f;
+    if (math && !c.aborted) {
+      const unsigned char* b0 = c.ring.data + (size_t)slot0 * STAGE_BYTES + woff;
+      const unsigned char* b1 = c.ring.data + (size_t)slot1 * STAGE_BYTES + woff;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint4 w0 = *reinterpret_cast<const uint4*>(b0 + ch * 512);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(b1 + ch * 512);
+        const float f0[8] = {bf16lo(w0.x), bf16hi(w0.x), bf16lo(w0.y), bf16hi(w0.y), bf16lo(w0.z), bf16hi(w0.z), bf16lo(w0.w), bf16hi(w0.w)};
+        const float f1[8] = {bf16lo(w1.x), bf16hi(w1.x), bf16lo(w1.y), bf16hi(w1.y), bf16lo(w1.z), bf16hi(w1.z), bf16lo(w1.w), bf16hi(w1.w)};
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a0[i][e & 1] = fmaf(f0[e], xr[i][ch * 8 + e], a0[i][e & 1]);
+            a1[i][e & 1] = fmaf(f1[e], xr[i][ch * 8 + e], a1[i][e & 1]);
+          }
+      }
+    }
+    float s0[R], s1[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      s0[i] = a0[i][0] + a0[i][1];
+      s1[i] = a1[i][0] + a1[i][1];
+    }
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1)
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        if (do0) a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
-        if (do1) a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+        s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
+        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
       }
     if (c.lane < 4) {
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        if (do0) part[((size_t)i * MAXU + u0) * 4 + c.lane] = a0[i];
-        if (do1) part[((size_t)i * MAXU + u1) * 4 + c.lane] = a1[i];
+        if (u0 < units) part[((size_t)i * MAXU + u0) * 4 + c.lane] = s0[i];
+        if (two && u1 < units) part[((size_t)i * MAXU + u1) * 4 + c.lane] = s1[i];
       }
     }
     __syncwarp();
@@ -299,37 +286,58 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
   }
 }
 
-// consumer-side sync (shared-memory results visible to all consumer warps)
-__device__ __forceinline__ void csync() { named_bar_sync(2, NCW * 32); }
+// sum the 4*KS partials of local row j (fixed order -> deterministic)
+__device__ __forceinline__ float row_total(const float* part, int j, int KS) {
+  const float4* p4 = reinterpret_cast<const float4*>(part + (size_t)j * KS * 4);
+  float4 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = k < KS ? p4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  return s;
+}
 
-// load the warp's K-slice (kseg = warp % KS) of R rows of a global fp32 vector into registers
+// ------------------------------------------------------------------------------------------------ activations
+// Cooperative gather of NL*512 tagged words into shared memory: every thread polls its own 16-byte pairs until both
+// carry `tag`.  The caller issues csync() before reading dst.
+template <int NL>
+__device__ __forceinline__ void gather_ll(Ctx& c, const uint2* src, unsigned tag, float* dst) {
+  uint4 v[NL];
+  unsigned spins = 0;
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < NL; ++j) v[j] = ll_ld2(src + (size_t)j * (NCT * 2) + c.tid * 2);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) ok = ok && (v[j].y == tag) && (v[j].w == tag);
+    if (ok || c.aborted) break;
+    if (!poll_continue(c, spins, 200 + (int)(c.phase & 0x3ff))) break;
+  }
+#pragma unroll
+  for (int j = 0; j < NL; ++j)
+    *reinterpret_cast<float2*>(dst + (size_t)j * (NCT * 2) + c.tid * 2) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+}
+
+// this warp's K-slice (kseg = warp % KS) of R rows out of the gathered vector xs[R][K]
 template <int R>
-__device__ __forceinline__ void load_slice(Ctx& c, const float* x, int ldx, int K, float (&xr)[R][32]) {
+__device__ __forceinline__ void slice_from_smem(Ctx& c, const float* xs, int K, float (&xr)[R][32]) {
   const int kseg = c.warp % (K / UNIT);
-  float4 v[R][8];
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      const float* p = x + (size_t)i * ldx + kseg * UNIT + ch * 256 + c.lane * 8;
-      v[i][ch * 2] = ldcg4(p);
-      v[i][ch * 2 + 1] = ldcg4(p + 4);
-    }
-#pragma unroll
-  for (int i = 0; i < R; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      xr[i][j * 4 + 0] = v[i][j].x; xr[i][j * 4 + 1] = v[i][j].y; xr[i][j * 4 + 2] = v[i][j].z; xr[i][j * 4 + 3] = v[i][j].w;
+      const float* p = xs + (size_t)i * K + kseg * UNIT + ch * 256 + c.lane * 8;
+      const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      xr[i][ch * 8 + 0] = a.x; xr[i][ch * 8 + 1] = a.y; xr[i][ch * 8 + 2] = a.z; xr[i][ch * 8 + 3] = a.w;
+      xr[i][ch * 8 + 4] = b.x; xr[i][ch * 8 + 5] = b.y; xr[i][ch * 8 + 6] = b.z; xr[i][ch * 8 + 7] = b.w;
     }
 }
 
-// RMSNorm-ed K-slices of R rows: every load (norm weights, the slice, and for K = 2048 the other half that only
-// feeds the statistics) is issued before the first dependent instruction, so the phase pays ONE L2 round trip.
 struct NormW {
   float4 g[8];
 };
-// this warp's slice of a norm weight vector; issued BEFORE the grid barrier of the previous phase so that the (possibly
-// HBM-cold) load is off the critical path
+// this warp's slice of a norm weight vector; issued a phase early so that the (possibly HBM-cold) load is hidden
 template <int KS>
 __device__ __forceinline__ NormW prefetch_norm(Ctx& c, const float* w) {
   NormW n;
@@ -342,49 +350,95 @@ __device__ __forceinline__ NormW prefetch_norm(Ctx& c, const float* w) {
   }
   return n;
 }
+// RMSNorm-ed K-slices of R rows from the gathered vector xs[R][K] (every warp recomputes the row statistics)
 template <int R, int KS>
-__device__ __forceinline__ void load_slice_norm(Ctx& c, const float* x, int ldx, int K, const NormW& nw, float eps,
-                                                float (&xr)[R][32]) {
-  const int kseg = c.warp % KS;
-  float4 v[R][8], o[R][KS == 2 ? 8 : 1];
-  const float4(&g)[8] = nw.g;
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const float* p = x + (size_t)i * ldx + kseg * UNIT + ch * 256 + c.lane * 8;
-      v[i][ch * 2] = ldcg4(p);
-      v[i][ch * 2 + 1] = ldcg4(p + 4);
-    }
-    if (KS == 2) {
-      const float* q = x + (size_t)i * ldx + (kseg ^ 1) * UNIT + c.lane * 4;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[i][j] = ldcg4(q + j * 128);
-    }
-  }
+__device__ __forceinline__ void norm_from_smem(Ctx& c, const float* xs, const NormW& nw, float eps, float (&xr)[R][32]) {
+  constexpr int K = KS * UNIT;
+  slice_from_smem<R>(c, xs, K, xr);
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ss += v[i][j].x * v[i][j].x + v[i][j].y * v[i][j].y + v[i][j].z * v[i][j].z + v[i][j].w * v[i][j].w;
-    if (KS == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ss += o[i][j].x * o[i][j].x + o[i][j].y * o[i][j].y + o[i][j].z * o[i][j].z + o[i][j].w * o[i][j].w;
+    for (int j = 0; j < K / 128; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)i * K + j * 128 + c.lane * 4);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     const float rstd = rsqrtf(warp_sum(ss) / (float)K + eps);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      xr[i][j * 4 + 0] = v[i][j].x * rstd * g[j].x; xr[i][j * 4 + 1] = v[i][j].y * rstd * g[j].y;
-      xr[i][j * 4 + 2] = v[i][j].z * rstd * g[j].z; xr[i][j * 4 + 3] = v[i][j].w * rstd * g[j].w;
+      xr[i][j * 4 + 0] *= rstd * nw.g[j].x; xr[i][j * 4 + 1] *= rstd * nw.g[j].y;
+      xr[i][j * 4 + 2] *= rstd * nw.g[j].z; xr[i][j * 4 + 3] *= rstd * nw.g[j].w;
     }
   }
 }
 
-// sum the KS partials of local row j (fixed order -> deterministic)
-__device__ __forceinline__ float row_total(const float* part, int j, int KS) {
-  float s = 0.f;
-  for (int k = 0; k < KS * 4; ++k) s += part[(size_t)j * KS * 4 + k];
-  return s;
+// K = 8192 (MLP activation): every warp needs only its own 1024-slice, read straight from the tagged buffer
+template <int R>
+__device__ __forceinline__ void load_act_slice(Ctx& c, const uint2* act, int F, unsigned tag, float (&xr)[R][32]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const uint2* base = act + (size_t)i * F + c.warp * UNIT + c.lane * 8;
+    uint4 v[16];
+    unsigned spins = 0;
+    while (true) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[ch * 4 + j] = ll_ld2(base + ch * 256 + j * 2);
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ok = ok && (v[j].y == tag) && (v[j].w == tag);
+      if (ok || c.aborted) break;
+      if (!poll_continue(c, spins, 300)) break;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      xr[i][j * 2] = __uint_as_float(v[j].x);
+      xr[i][j * 2 + 1] = __uint_as_float(v[j].z);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GEMV phases
+// y[row] = (res ? res[row] : 0) + W[row,:] . x  for this CTA's rows, written as tagged words with the current tag
+template <int R>
+__device__ void phase_linear(Ctx& c, const uint16_t* W, int N, int K, const float (&xr)[R][32], uint2* y, int ldy,
+                             const uint2* res, int ldr) {
+  const Range r = cta_range(W, N, K, c.cta, c.G);
+  // this thread finalises output j = tid (rows*R <= 44): fetch its residual early (its producer phase is long over)
+  const int j = c.tid;
+  const bool mine = j < r.rows * R;
+  const int ri = mine ? j / r.rows : 0, rrow = mine ? j % r.rows : 0;
+  float rv = 0.f;
+  if (mine && res) rv = __uint_as_float(ll_ld(res + (size_t)ri * ldr + r.row0 + rrow).x);
+  mark(c, T_LOAD);
+  consume<R>(c, r, xr, c.part);
+  mark(c, T_GEMV);
+  csync();
+  if (mine) ll_st(y + (size_t)ri * ldy + r.row0 + rrow, rv + row_total(c.part + (size_t)ri * MAXU * 4, rrow, K / UNIT), cur_tag(c));
+  mark(c, T_FIN);
+}
+
+// SwiGLU MLP first half: act[f] = silu(Wg[f,:].x) * (Wu[f,:].x)
+template <int R>
+__device__ void phase_gate_up(Ctx& c, const uint16_t* Wgu, int F, int K, const float (&xr)[R][32], uint2* act) {
+  const Range rg = cta_range(Wgu, F, K, c.cta, c.G);
+  const Range ru = cta_range(Wgu + (size_t)F * K, F, K, c.cta, c.G);
+  float* pg = c.part;
+  float* pu = c.part + 2 * MAXU * 4;
+  mark(c, T_LOAD);
+  consume<R>(c, rg, xr, pg);
+  consume<R>(c, ru, xr, pu);
+  mark(c, T_GEMV);
+  csync();
+  const int KS = K / UNIT;
+  const unsigned tag = cur_tag(c);
+  for (int j = c.tid; j < rg.rows * R; j += NCT) {
+    const int i = j / rg.rows, row = j % rg.rows;
+    const float g = row_total(pg + (size_t)i * MAXU * 4, row, KS), u = row_total(pu + (size_t)i * MAXU * 4, row, KS);
+    ll_st(act + (size_t)i * F + rg.row0 + row, (g / (1.f + expf(-g))) * u, tag);
+  }
+  mark(c, T_FIN);
 }
 
 // ------------------------------------------------------------------------------------------------ sampling
@@ -393,27 +447,34 @@ __device__ __forceinline__ float gumbel_at(int idx, uint32_t dlo, uint32_t dhi, 
   philox4x32_10(ctr, k0, k1);
   return -logf(-logf(u01(ctr[idx & 3])));
 }
-// every CTA computes the same token from the logits in global memory (consumer warps only)
-__device__ int sample_token(Ctx& c, const float* logits, int V, unsigned long long draw) {
+// every CTA computes the same token from the tagged logits (consumer warps only); V <= 9 * 256
+__device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, unsigned long long draw) {
   const FrameParams& p = *c.p;
+  uint2 v[9];
+  unsigned spins = 0;
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int i = c.tid + j * NCT;
+      v[j] = i < V ? ll_ld(logits + i) : make_uint2(0xff800000u, tag);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) ok = ok && (v[j].y == tag);
+    if (ok || c.aborted) break;
+    if (!poll_continue(c, spins, 400)) break;
+  }
+  mark(c, T_POLL);
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   const uint32_t dlo = (uint32_t)draw, dhi = (uint32_t)(draw >> 32);
-  for (int i0 = c.tid; i0 < V; i0 += NCW * 32 * 8) {
-    float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + j * NCW * 32;
-      v[j] = i < V ? __ldcg(logits + i) : -INFINITY;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + j * NCW * 32;
-      if (i < V) {
-        float t = v[j];
-        if (p.inv_temp != 0.f) t = t * p.inv_temp + gumbel_at(i, dlo, dhi, p.seed_lo, p.seed_hi);
-        argmax_combine(bv, bi, t, i);
-      }
+  for (int j = 0; j < 9; ++j) {
+    const int i = c.tid + j * NCT;
+    if (i < V) {
+      float t = __uint_as_float(v[j].x);
+      if (p.inv_temp != 0.f) t = t * p.inv_temp + gumbel_at(i, dlo, dhi, p.seed_lo, p.seed_hi);
+      argmax_combine(bv, bi, t, i);
     }
   }
   warp_argmax(bv, bi);
@@ -432,97 +493,56 @@ __device__ int sample_token(Ctx& c, const float* logits, int V, unsigned long lo
   return bi == 0x7fffffff ? 0 : bi;
 }
 
-// ------------------------------------------------------------------------------------------------ GEMV phases
-// y[row] = (res ? res[row] : 0) + W[row,:] . x      for this CTA's rows; x given as register slices
-template <int R>
-__device__ void phase_linear(Ctx& c, const uint16_t* W, int N, int K, const float (&xr)[R][32], float* y, int ldy,
-                             const float* res, int ldr) {
-  const Range r = cta_range(W, N, K, c.cta, c.G);
-  // this thread finalises output j = tid (rows*R <= 256 always: <= 21 rows per CTA x 2): fetch its residual early
-  const int j = c.tid;
-  const bool mine = j < r.rows * R;
-  const int ri = mine ? j / r.rows : 0, rrow = mine ? j % r.rows : 0;
-  float rv = 0.f;
-  if (mine && res) rv = __ldcg(res + (size_t)ri * ldr + r.row0 + rrow);
-  mark(c, T_LOAD);
-  trace(c, 20);
-  consume<R>(c, r, xr, c.part);
-  trace(c, 21);
-  mark(c, T_GEMV);
-  csync();
-  trace(c, 22);
-  if (mine) y[(size_t)ri * ldy + r.row0 + rrow] = rv + row_total(c.part + (size_t)ri * MAXU * 4, rrow, K / UNIT);
-  mark(c, T_FIN);
-}
-
-// SwiGLU MLP first half: act[f] = silu(Wg[f,:].x) * (Wu[f,:].x)
-template <int R>
-__device__ void phase_gate_up(Ctx& c, const uint16_t* Wgu, int F, int K, const float (&xr)[R][32], float* act) {
-  const Range rg = cta_range(Wgu, F, K, c.cta, c.G);
-  const Range ru = cta_range(Wgu + (size_t)F * K, F, K, c.cta, c.G);
-  float* pg = c.part;
-  float* pu = c.part + 2 * MAXU * 4;
-  mark(c, T_LOAD);
-  trace(c, 30);
-  consume<R>(c, rg, xr, pg);
-  consume<R>(c, ru, xr, pu);
-  trace(c, 31);
-  mark(c, T_GEMV);
-  csync();
-  trace(c, 32);
-  const int KS = K / UNIT;
-  for (int j = c.tid; j < rg.rows * R; j += NCW * 32) {
-    const int i = j / rg.rows, row = j % rg.rows;
-    const float g = row_total(pg + (size_t)i * MAXU * 4, row, KS), u = row_total(pu + (size_t)i * MAXU * 4, row, KS);
-    act[(size_t)i * F + rg.row0 + row] = (g / (1.f + expf(-g))) * u;
-  }
-  mark(c, T_FIN);
-}
-
 // ------------------------------------------------------------------------------------------------ attention
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Stage the cached K/V rows (positions < pos0) of one decoder layer into shared memory with ONE bulk copy (the rows
-// are contiguous in dec_kv).  Issued right after a grid barrier, two phases before the attention that reads them.
-__device__ __forceinline__ void bulk_g2s_plain(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void stage_decoder_kv(Ctx& c, int layer, int pos0) {
+// Stage this CTA's cached decoder K/V rows (positions < pos0) of one layer into shared memory with ONE bulk copy.
+// The rows were written by this same CTA (ordinary stores, earlier steps): a proxy fence orders them before the copy.
+__device__ __forceinline__ void stage_decoder_kv(Ctx& c, const float* kvl, int pos0) {
   if (pos0 == 0 || c.tid != 0 || c.aborted) return;
-  const FrameParams& p = *c.p;
-  const float* src = p.dec_kv + (size_t)layer * 32 * KROW;
   const uint32_t bytes = (uint32_t)pos0 * KROW * 4;
-  asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows were written with ordinary stores (by CTA 0)
+  asm volatile("fence.proxy.async;" ::: "memory");
   mbar_arrive_expect_tx(c.kvbar, bytes);
-  bulk_g2s_plain(c.kvs, src, bytes, c.kvbar);
+  bulk_g2s_plain(c.kvs, kvl, bytes, c.kvbar);
 }
 
 // Depth decoder attention, recomputed by every CTA: warp h = query head h (8 heads x 128), kv head h/4.
-// qkv: this step's raw projections for R rows (positions pos0 .. pos0+R-1); cs: their RoPE (cos,sin) pairs for this
-// lane (dims 4*lane .. 4*lane+3).  Keys < pos0 come from the staged shared-memory copy: QK is lane-per-key, PV is
-// dims-over-lanes.  Result: sattn[R][1024] (every warp of the o-projection needs the whole vector).
+// qkv: this step's raw tagged projections for R rows (positions pos0 .. pos0+R-1); cs: their RoPE (cos,sin) pairs for
+// this lane (dims 4*lane .. 4*lane+3).  Keys < pos0 come from the staged shared-memory copy: QK is lane-per-key with a
+// rotated chunk order (conflict-free although rows are 2 KiB apart), PV is dims-over-lanes.
+// Result: sattn[R][1024] (every warp of the o-projection needs the whole vector).
 template <int R>
-__device__ void decoder_attention(Ctx& c, int layer, int pos0, const float* qkv, int ldq, const float4 (&cs)[R]) {
-  const FrameParams& p = *c.p;
-  constexpr int HD = 128, H = 8, HKV = 2, ROW = 2 * HKV * HD;
+__device__ void decoder_attention(Ctx& c, float* kvl, int pos0, const uint2* qkv, int ldq, unsigned tag, const float4 (&cs)[R]) {
+  constexpr int HD = 128, H = 8, HKV = 2;
   const int h = c.warp, kvh = h / (H / HKV);
-  float* kvl = p.dec_kv + (size_t)layer * 32 * ROW;
   float* sq = c.sattn + 2 * 1024 + c.warp * (2 * HD);  // this warp's rotated q rows, broadcast-read below
   const float scale = rsqrtf((float)HD);
   float4 q[R], k[R], v[R];
+  {
+    uint4 t[R][6];
+    unsigned spins = 0;
+    while (true) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const float* row = qkv + (size_t)i * ldq;
-    q[i] = ldcg4(row + h * HD + c.lane * 4);
-    k[i] = ldcg4(row + (H + kvh) * HD + c.lane * 4);
-    v[i] = ldcg4(row + (H + HKV + kvh) * HD + c.lane * 4);
+      for (int i = 0; i < R; ++i) {
+        const uint2* row = qkv + (size_t)i * ldq + c.lane * 4;
+        t[i][0] = ll_ld2(row + h * HD);               t[i][1] = ll_ld2(row + h * HD + 2);
+        t[i][2] = ll_ld2(row + (H + kvh) * HD);       t[i][3] = ll_ld2(row + (H + kvh) * HD + 2);
+        t[i][4] = ll_ld2(row + (H + HKV + kvh) * HD); t[i][5] = ll_ld2(row + (H + HKV + kvh) * HD + 2);
+      }
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ok = ok && (t[i][j].y == tag) && (t[i][j].w == tag);
+      if (ok || c.aborted) break;
+      if (!poll_continue(c, spins, 500)) break;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      q[i] = make_float4(__uint_as_float(t[i][0].x), __uint_as_float(t[i][0].z), __uint_as_float(t[i][1].x), __uint_as_float(t[i][1].z));
+      k[i] = make_float4(__uint_as_float(t[i][2].x), __uint_as_float(t[i][2].z), __uint_as_float(t[i][3].x), __uint_as_float(t[i][3].z));
+      v[i] = make_float4(__uint_as_float(t[i][4].x), __uint_as_float(t[i][4].z), __uint_as_float(t[i][5].x), __uint_as_float(t[i][5].z));
+    }
   }
+  mark(c, T_POLL);
   float qn[R][4], kn[R][4];
 #pragma unroll
   for (int i = 0; i < R; ++i) {
@@ -531,8 +551,8 @@ __device__ void decoder_attention(Ctx& c, int layer, int pos0, const float* qkv,
     kn[i][0] = k[i].x * cs[i].x - k[i].y * cs[i].y; kn[i][1] = k[i].y * cs[i].x + k[i].x * cs[i].y;
     kn[i][2] = k[i].z * cs[i].z - k[i].w * cs[i].w; kn[i][3] = k[i].w * cs[i].z + k[i].z * cs[i].w;
     *reinterpret_cast<float4*>(sq + i * HD + c.lane * 4) = make_float4(qn[i][0], qn[i][1], qn[i][2], qn[i][3]);
-    if (c.cta == 0 && (h % (H / HKV)) == 0) {  // one writer per kv head persists K/V for later steps
-      float* dst = kvl + (size_t)(pos0 + i) * ROW + kvh * HD + c.lane * 4;
+    if ((h % (H / HKV)) == 0) {  // one writer per kv head keeps this CTA's private K/V copy for later steps
+      float* dst = kvl + (size_t)(pos0 + i) * KROW + kvh * HD + c.lane * 4;
       *reinterpret_cast<float4*>(dst) = make_float4(kn[i][0], kn[i][1], kn[i][2], kn[i][3]);
       *reinterpret_cast<float4*>(dst + HKV * HD) = v[i];
     }
@@ -541,7 +561,7 @@ __device__ void decoder_attention(Ctx& c, int layer, int pos0, const float* qkv,
     mbar_wait(c, c.kvbar, c.kv_phase, 4);
     c.kv_phase ^= 1;
   }
-  csync();  // every warp's sq visible
+  __syncwarp();  // sq is per-warp
   const float* krow = c.kvs + (size_t)c.lane * KROW + kvh * HD;   // lane-per-key
   const float* vcol = c.kvs + HKV * HD + kvh * HD + c.lane * 4;   // dims-over-lanes
 #pragma unroll
@@ -549,8 +569,6 @@ __device__ void decoder_attention(Ctx& c, int layer, int pos0, const float* qkv,
     const int pos = pos0 + i;
     float dot = 0.f;
     if (c.lane < pos0) {
-      // lane j starts at 16-byte chunk j and wraps: rows are 2 KB apart (same bank), the rotation makes the
-      // quarter-warps hit 8 distinct bank groups, and the per-lane q reads cover 512 contiguous bytes
 #pragma unroll 8
       for (int t = 0; t < HD / 4; ++t) {
         const int d = ((t + c.lane) & (HD / 4 - 1)) * 4;
@@ -598,29 +616,40 @@ __device__ void decoder_attention(Ctx& c, int layer, int pos0, const float* qkv,
 // Backbone attention work item: kv head `kvh`, chunk `chunk` of 128 keys of S = pos+1.  8 warps = 4 query heads x
 // 2 halves of 64 keys (2 keys per lane, lane-per-key for both QK and PV, reduce-scatter for the PV sum).  The two
 // halves are merged in shared memory; the item writes either the final normalised head output (single chunk) or one
-// partial (acc[64], m, l) per head to attn_part.
-__device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, int nchunks, int pos, const float* qkv) {
+// partial (acc[64], m, l) per head, as tagged words.
+__device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, int nchunks, int pos, const uint2* qkv,
+                                        unsigned tag_in) {
   const FrameParams& p = *c.p;
   constexpr int HD = 64, H = 32, HKV = 8;
   const int hq = kvh * (H / HKV) + (c.warp & 3), half = c.warp >> 2;
-  const int S = pos + 1;
   const int kbeg = chunk * 128 + half * 64;
   float* pool = p.kv_pool + (size_t)layer * p.kv_layer_stride;
   const size_t page_stride = (size_t)2 * HKV * CSMB_PAGE * HD;
   const float* rope = p.m.backbone.rope + (size_t)pos * (HD / 2) * 2;
-  float* sq = c.sattn + c.warp * HD;             // rotated q of this warp's head
+  float* sq = c.sattn + c.warp * HD;                  // rotated q of this warp's head
   float* sm = c.sattn + NCW * HD + c.warp * PSTRIDE;  // this warp's partial for the intra-CTA merge
+  float2 qraw, kraw, vnew;
   {
-    const float2 q = __ldcg(reinterpret_cast<const float2*>(qkv + hq * HD + c.lane * 2));
-    const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + c.lane * 2));
-    *reinterpret_cast<float2*>(sq + c.lane * 2) = make_float2(q.x * cs.x - q.y * cs.y, q.y * cs.x + q.x * cs.y);
+    uint4 t[3];
+    unsigned spins = 0;
+    while (true) {
+      t[0] = ll_ld2(qkv + hq * HD + c.lane * 2);
+      t[1] = ll_ld2(qkv + (H + kvh) * HD + c.lane * 2);
+      t[2] = ll_ld2(qkv + (H + HKV + kvh) * HD + c.lane * 2);
+      const bool ok = t[0].y == tag_in && t[0].w == tag_in && t[1].y == tag_in && t[1].w == tag_in && t[2].y == tag_in && t[2].w == tag_in;
+      if (ok || c.aborted) break;
+      if (!poll_continue(c, spins, 600)) break;
+    }
+    qraw = make_float2(__uint_as_float(t[0].x), __uint_as_float(t[0].z));
+    kraw = make_float2(__uint_as_float(t[1].x), __uint_as_float(t[1].z));
+    vnew = make_float2(__uint_as_float(t[2].x), __uint_as_float(t[2].z));
   }
-  const float2 kraw = __ldcg(reinterpret_cast<const float2*>(qkv + (H + kvh) * HD + c.lane * 2));
+  mark(c, T_POLL);
   const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + c.lane * 2));
+  *reinterpret_cast<float2*>(sq + c.lane * 2) = make_float2(qraw.x * cs.x - qraw.y * cs.y, qraw.y * cs.x + qraw.x * cs.y);
   const float2 knew = make_float2(kraw.x * cs.x - kraw.y * cs.y, kraw.y * cs.x + kraw.x * cs.y);
-  const float2 vnew = __ldcg(reinterpret_cast<const float2*>(qkv + (H + HKV + kvh) * HD + c.lane * 2));
   const bool has_new = (pos >= kbeg && pos < kbeg + 64);
-  if (has_new && (c.warp & 3) == 0) {  // one writer per kv head: append to the paged cache
+  if (has_new && (c.warp & 3) == 0) {  // one writer per kv head: append to the paged cache (read by later launches)
     const int page = p.block_table[pos / CSMB_PAGE];
     float* kd = pool + (size_t)page * page_stride + (size_t)kvh * CSMB_PAGE * HD + (size_t)(pos % CSMB_PAGE) * HD;
     *reinterpret_cast<float2*>(kd + c.lane * 2) = knew;
@@ -644,7 +673,7 @@ __device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, i
   for (int t = 0; t < 2; ++t) {
     float4 kv[16];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) kv[d] = valid[t] ? ldcg4(kptr[t] + d * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < 16; ++d) kv[d] = valid[t] ? *reinterpret_cast<const float4*>(kptr[t] + d * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float dot = 0.f;
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
@@ -671,7 +700,7 @@ __device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, i
     const float* vp = kptr[t] + (size_t)HKV * CSMB_PAGE * HD;
     float4 vv[16];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) vv[d] = valid[t] ? ldcg4(vp + d * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < 16; ++d) vv[d] = valid[t] ? *reinterpret_cast<const float4*>(vp + d * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
       acc[d * 4] = fmaf(e[t], vv[d].x, acc[d * 4]);
@@ -700,7 +729,7 @@ __device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, i
   }
   *reinterpret_cast<float2*>(sm + c.lane * 2) = out;
   if (c.lane == 0) {
-    sm[HD] = m;      // -inf if this half saw no key
+    sm[HD] = m;  // -inf if this half saw no key
     sm[HD + 1] = sum;
   }
   csync();
@@ -712,67 +741,79 @@ __device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, i
     const float w0 = (m0 == -INFINITY) ? 0.f : expf(m0 - M), w1 = (m1 == -INFINITY) ? 0.f : expf(m1 - M);
     const float L = w0 * s0[HD + 1] + w1 * s1[HD + 1];
     const float2 a0 = *reinterpret_cast<const float2*>(s0 + c.lane * 2), a1 = *reinterpret_cast<const float2*>(s1 + c.lane * 2);
-    float2 o2 = make_float2(w0 * a0.x + w1 * a1.x, w0 * a0.y + w1 * a1.y);
+    const float2 o2 = make_float2(w0 * a0.x + w1 * a1.x, w0 * a0.y + w1 * a1.y);
+    const unsigned tag = cur_tag(c);
     if (nchunks == 1) {
       const float inv = 1.f / L;
-      *reinterpret_cast<float2*>(p.attn_out + hq * HD + c.lane * 2) = make_float2(o2.x * inv, o2.y * inv);
+      ll_st2(p.attn_out + hq * HD + c.lane * 2, o2.x * inv, o2.y * inv, tag);
     } else {
-      float* dst = p.attn_part + ((size_t)hq * MAX_SPLIT + chunk) * PSTRIDE;
-      *reinterpret_cast<float2*>(dst + c.lane * 2) = o2;
-      if (c.lane == 0) {
-        dst[HD] = M;
-        dst[HD + 1] = L;
-      }
+      uint2* dst = p.attn_part + ((size_t)chunk * H + hq) * PSTRIDE;
+      ll_st2(dst + c.lane * 2, o2.x, o2.y, tag);
+      if (c.lane == 0) ll_st2(dst + HD, M, L, tag);
+      if (c.lane >= 1 && c.lane <= 3) ll_st2(dst + HD + c.lane * 2, 0.f, 0.f, tag);  // pad words: the reader polls whole rows
     }
   }
   csync();
 }
 
 // merge of the per-chunk partials into the o-projection's register slice (K = 2048 -> 2 ksegs; a lane's 8
-// consecutive k share one head).  Loads are issued in independent batches, two head-chunks at a time.
-__device__ void merged_attention_slice(Ctx& c, int nchunks, float (&xr)[1][32]) {
+// consecutive k share one head).  Path for S > 128: chunk after chunk, the 32 x 72 tagged words of a chunk are
+// gathered cooperatively into shared memory (one polled L2 round trip), then every lane folds its 4 head-slices into
+// running (max, sum, acc) registers.
+__device__ void merged_attention_slice(Ctx& c, int nchunks, unsigned tag, float (&xr)[1][32]) {
   const FrameParams& p = *c.p;
-  constexpr int HD = 64;
+  constexpr int HD = 64, H = 32, WORDS = H * PSTRIDE;  // 2304 = 9 x 256
   const int kseg = c.warp % 2;
+  float M[4], L[4], o[4][8];
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
-    const int k = kseg * UNIT + ch * 256 + c.lane * 8;
-    const int h = k / HD, d = k % HD;
-    const float* base = p.attn_part + (size_t)h * MAX_SPLIT * PSTRIDE;
-    float2 ml[MAX_SPLIT];
+    M[ch] = -INFINITY;
+    L[ch] = 0.f;
 #pragma unroll
-    for (int s = 0; s < MAX_SPLIT; ++s)
-      ml[s] = s < nchunks ? __ldcg(reinterpret_cast<const float2*>(base + s * PSTRIDE + HD)) : make_float2(-INFINITY, 0.f);
-    float M = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < MAX_SPLIT; ++s) M = fmaxf(M, ml[s].x);
-    float L = 0.f, o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.f;
-#pragma unroll
-    for (int s0 = 0; s0 < MAX_SPLIT; s0 += 4) {
-      if (s0 >= nchunks) break;
-      float4 a[4][2];
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const bool ok = s0 + s < nchunks;
-        a[s][0] = ok ? ldcg4(base + (s0 + s) * PSTRIDE + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a[s][1] = ok ? ldcg4(base + (s0 + s) * PSTRIDE + d + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const float wgt = (ml[s0 + s].x == -INFINITY) ? 0.f : expf(ml[s0 + s].x - M);
-        L = fmaf(wgt, ml[s0 + s].y, L);
-        o[0] = fmaf(wgt, a[s][0].x, o[0]); o[1] = fmaf(wgt, a[s][0].y, o[1]);
-        o[2] = fmaf(wgt, a[s][0].z, o[2]); o[3] = fmaf(wgt, a[s][0].w, o[3]);
-        o[4] = fmaf(wgt, a[s][1].x, o[4]); o[5] = fmaf(wgt, a[s][1].y, o[5]);
-        o[6] = fmaf(wgt, a[s][1].z, o[6]); o[7] = fmaf(wgt, a[s][1].w, o[7]);
-      }
-    }
-    const float inv = 1.f / L;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) xr[0][ch * 8 + e] = o[e] * inv;
+    for (int e = 0; e < 8; ++e) o[ch][e] = 0.f;
   }
+  for (int s = 0; s < nchunks; ++s) {
+    const uint2* src = p.attn_part + (size_t)s * WORDS;
+    uint2 v[9];
+    unsigned spins = 0;
+    while (true) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) v[j] = ll_ld(src + j * NCT + c.tid);
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) ok = ok && (v[j].y == tag);
+      if (ok || c.aborted) break;
+      if (!poll_continue(c, spins, 700)) break;
+    }
+    csync();  // previous chunk fully consumed
+#pragma unroll
+    for (int j = 0; j < 9; ++j) c.sattn[j * NCT + c.tid] = __uint_as_float(v[j].x);
+    csync();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int k = kseg * UNIT + ch * 256 + c.lane * 8;
+      const int h = k / HD, d = k % HD;
+      const float* base = c.sattn + h * PSTRIDE;
+      const float ms = base[HD], ls = base[HD + 1];
+      if (ms == -INFINITY) continue;
+      const float Mn = fmaxf(M[ch], ms);
+      const float wo = (M[ch] == -INFINITY) ? 0.f : expf(M[ch] - Mn), wn = expf(ms - Mn);
+      L[ch] = L[ch] * wo + ls * wn;
+      const float4 a = *reinterpret_cast<const float4*>(base + d), b = *reinterpret_cast<const float4*>(base + d + 4);
+      o[ch][0] = o[ch][0] * wo + wn * a.x; o[ch][1] = o[ch][1] * wo + wn * a.y;
+      o[ch][2] = o[ch][2] * wo + wn * a.z; o[ch][3] = o[ch][3] * wo + wn * a.w;
+      o[ch][4] = o[ch][4] * wo + wn * b.x; o[ch][5] = o[ch][5] * wo + wn * b.y;
+      o[ch][6] = o[ch][6] * wo + wn * b.z; o[ch][7] = o[ch][7] * wo + wn * b.w;
+      M[ch] = Mn;
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const float inv = 1.f / L[ch];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xr[0][ch * 8 + e] = o[ch][e] * inv;
+  }
+  csync();  // sattn is reused by the next gather
 }
 
 // ------------------------------------------------------------------------------------------------ schedule
@@ -810,78 +851,22 @@ __device__ bool sched_range(const FrameParams& p, int idx, int cta, int G, Range
   return true;
 }
 
-struct Cursor {
-  int idx, stage, nst;
-  Range r;
-  bool valid;
-};
-__device__ __forceinline__ void cursor_load(const FrameParams& p, Cursor& k, int cta, int G) {
-  k.valid = sched_range(p, k.idx, cta, G, k.r);
-  k.stage = 0;
-  k.nst = k.valid ? n_stages(k.r) : 0;
-}
-__device__ __forceinline__ void cursor_chunk(const Cursor& k, const char*& src, uint32_t& bytes) {
-  const size_t total = (size_t)k.r.rows * k.r.K * 2, off = (size_t)k.stage * STAGE_BYTES;
-  src = reinterpret_cast<const char*>(k.r.p) + off;
-  bytes = (uint32_t)((total - off) < (size_t)STAGE_BYTES ? (total - off) : (size_t)STAGE_BYTES);
-}
-__device__ __forceinline__ void cursor_advance(const FrameParams& p, Cursor& k, int cta, int G) {
-  if (++k.stage >= k.nst) {
-    k.idx++;
-    cursor_load(p, k, cta, G);
-  }
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(b)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-// Producer (one thread per CTA).  Two cursors walk the schedule: the RING cursor copies 16 KiB stages into shared
-// memory as slots free up; whenever the ring is full (the consumers are in a latency phase: barrier, activation
-// load, attention) the PREFETCH cursor runs ahead, pulling future stages HBM -> L2 with cp.async.bulk.prefetch.L2 at
-// this SM's fair share of the HBM rate (one stage per pf_interval cycles), at most pf_max stages ahead.  HBM thus
-// keeps streaming through the latency phases; the ring later refills from L2.  Every byte still leaves HBM once.
+// Producer (one thread per CTA): copies the schedule, stage by stage, into the ring as slots free up.
 __device__ void producer_main(Ctx& c) {
   const FrameParams& p = *c.p;
   if (p.dbg & 8) return;
-  Cursor rc, pc;
-  rc.idx = 0;
-  cursor_load(p, rc, c.cta, c.G);
-  pc = rc;
-  int ahead = 0;  // stages the prefetch cursor is ahead of the ring cursor
-  const int pf_max = p.pf_max, pf_interval = p.pf_interval;
-  long long last_pf = clock64() - pf_interval;
-  unsigned idle = 0;
-  while (rc.valid && !c.aborted) {
-    const int slot = c.q % NSTAGES;
-    const uint32_t par = (c.q / NSTAGES) & 1;
-    if (mbar_test(&c.ring.empty[slot], par ^ 1)) {
-      const char* src;
-      uint32_t n;
-      cursor_chunk(rc, src, n);
+  Range r;
+  for (int idx = 0; sched_range(p, idx, c.cta, c.G, r) && !c.aborted; ++idx) {
+    const size_t bytes = (size_t)r.rows * r.K * 2;
+    const char* src = reinterpret_cast<const char*>(r.p);
+    for (size_t off = 0; off < bytes; off += STAGE_BYTES, ++c.q) {
+      const int slot = c.q % NSTAGES;
+      const uint32_t par = (c.q / NSTAGES) & 1;
+      mbar_wait(c, &c.ring.empty[slot], par ^ 1, 1);
+      if (c.aborted) continue;
+      const uint32_t n = (uint32_t)((bytes - off) < (size_t)STAGE_BYTES ? (bytes - off) : (size_t)STAGE_BYTES);
       mbar_arrive_expect_tx(&c.ring.full[slot], n);
-      bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src, n, &c.ring.full[slot], c.policy);
-      cursor_advance(p, rc, c.cta, c.G);
-      ++c.q;
-      if (ahead > 0) --ahead; else pc = rc;
-      idle = 0;
-    } else if (ahead < pf_max && pc.valid && clock64() - last_pf >= pf_interval) {
-      const char* src;
-      uint32_t n;
-      cursor_chunk(pc, src, n);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
-      cursor_advance(p, pc, c.cta, c.G);
-      ++ahead;
-      last_pf = clock64();
-      idle = 0;
-    } else {
-      if (++idle > SPIN_LIMIT * 4u) raise_abort(c, 1);
-      if ((idle & 1023) == 0) check_abort(c);
+      bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src + off, n, &c.ring.full[slot], c.policy);
     }
   }
 }
@@ -893,54 +878,59 @@ __device__ void decoder_step(Ctx& c, int step, int pos0, float (&xr)[R][32]) {
   const csmb_llama& D = p.m.decoder;
   const int db = p.m.backbone.d_model, dd = D.d_model, V = p.m.audio_vocab, F = D.d_ff;
   const int nqkv = (D.n_heads + 2 * D.n_kv_heads) * D.head_dim;
+  constexpr int NLX = R * 1024 / (NCT * 2);  // gather loads per thread for an [R][1024] vector
+  float* kv_mine = p.dec_kv + (size_t)c.cta * D.n_layers * 32 * KROW;
   // RoPE rows of this step's positions (same for all layers): loaded now, used two phases later
   float4 cs[R];
 #pragma unroll
   for (int i = 0; i < R; ++i)
     cs[i] = __ldg(reinterpret_cast<const float4*>(D.rope + ((size_t)(pos0 + i) * (D.head_dim / 2) + c.lane * 2) * 2));
   // projection: xr already holds the input row slices (K = 2048)
+  unsigned tag_x = cur_tag(c);
   phase_linear<R>(c, p.m.projection, dd, db, xr, p.dxa, dd, nullptr, 0);
+  c.phase++;
   NormW nw = prefetch_norm<1>(c, D.norm_in[0]);
-  grid_sync(c);
-  float* x = p.dxa;
-  float* x1 = p.dxb;
+  uint2* x = p.dxa;
+  uint2* x1 = p.dxb;
   for (int l = 0; l < D.n_layers; ++l) {
-    trace(c, 40);
-    stage_decoder_kv(c, l, pos0);
-    trace(c, 41);
-    load_slice_norm<R, 1>(c, x, dd, dd, nw, D.eps, xr);
+    float* kvl = kv_mine + (size_t)l * 32 * KROW;
+    stage_decoder_kv(c, kvl, pos0);
+    gather_ll<NLX>(c, x, tag_x, c.sattn);
+    mark(c, T_POLL);
+    csync();
+    norm_from_smem<R, 1>(c, c.sattn, nw, D.eps, xr);
+    const unsigned tag_qkv = cur_tag(c);
     phase_linear<R>(c, D.wqkv[l], nqkv, dd, xr, p.qkv, nqkv, nullptr, 0);
-    grid_sync(c);
-    trace(c, 50);
-    decoder_attention<R>(c, l, pos0, p.qkv, nqkv, cs);
-    trace(c, 51);
+    c.phase++;
+    decoder_attention<R>(c, kvl, pos0, p.qkv, nqkv, tag_qkv, cs);
     mark(c, T_DATT);
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const float* sp = c.sattn + i * 1024 + ch * 256 + c.lane * 8;
-        const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
-        xr[i][ch * 8 + 0] = a.x; xr[i][ch * 8 + 1] = a.y; xr[i][ch * 8 + 2] = a.z; xr[i][ch * 8 + 3] = a.w;
-        xr[i][ch * 8 + 4] = b.x; xr[i][ch * 8 + 5] = b.y; xr[i][ch * 8 + 6] = b.z; xr[i][ch * 8 + 7] = b.w;
-      }
+    slice_from_smem<R>(c, c.sattn, dd, xr);
+    const unsigned tag_x1 = cur_tag(c);
     phase_linear<R>(c, D.wo[l], dd, dd, xr, x1, dd, x, dd);
+    c.phase++;
     nw = prefetch_norm<1>(c, D.norm_post[l]);
-    grid_sync(c);
-    load_slice_norm<R, 1>(c, x1, dd, dd, nw, D.eps, xr);
+    gather_ll<NLX>(c, x1, tag_x1, c.sattn);
+    mark(c, T_POLL);
+    csync();
+    norm_from_smem<R, 1>(c, c.sattn, nw, D.eps, xr);
+    const unsigned tag_act = cur_tag(c);
     phase_gate_up<R>(c, D.wgu[l], F, dd, xr, p.act);
-    grid_sync(c);
-    load_slice<R>(c, p.act, F, F, xr);
-    phase_linear<R>(c, D.wdown[l], dd, F, xr, x, dd, x1, dd);
+    c.phase++;
     nw = prefetch_norm<1>(c, l + 1 < D.n_layers ? D.norm_in[l + 1] : D.norm_final);
-    grid_sync(c);
+    load_act_slice<R>(c, p.act, F, tag_act, xr);
+    mark(c, T_POLL);
+    tag_x = cur_tag(c);
+    phase_linear<R>(c, D.wdown[l], dd, F, xr, x, dd, x1, dd);
+    c.phase++;
   }
   // head on the last row
+  gather_ll<NLX>(c, x, tag_x, c.sattn);
+  mark(c, T_POLL);
+  csync();
   float xh[1][32];
-  const float* last = x + (size_t)(R - 1) * dd;
-  load_slice_norm<1, 1>(c, last, dd, dd, nw, D.eps, xh);
+  norm_from_smem<1, 1>(c, c.sattn + (size_t)(R - 1) * dd, nw, D.eps, xh);
   phase_linear<1>(c, p.m.audio_head_t + (size_t)(step - 1) * V * dd, V, dd, xh, p.logits, V, nullptr, 0);
-  grid_sync(c);
+  c.phase++;
 }
 
 __device__ __forceinline__ void embed_row_slice(Ctx& c, const uint16_t* row, int K, float* dst32) {
@@ -962,11 +952,11 @@ __device__ void consumer_main(Ctx& c) {
   const int nqkv = (B.n_heads + 2 * B.n_kv_heads) * B.head_dim;
   const int pos = *p.pos_ptr;
   const int S = pos + 1;
-  // ---- input embedding: x = sum_k audio_emb[prev[k] + k*V]   (generation.py:156-161 + models.py:82-92)
-  // every CTA keeps its own copy in registers (slice) and CTA-distributed rows are not needed: the full vector is
-  // written once to xa by CTA 0 for the residual path.
-  {
-    for (int k = c.tid * 8; k < db && c.cta == 0; k += NCW * 32 * 8) {
+  // ---- phase 0: input embedding x = sum_k audio_emb[prev[k] + k*V]   (generation.py:156-161 + models.py:82-92),
+  // computed by CTA 0 and published as tagged words
+  unsigned tag_x = cur_tag(c);
+  if (c.cta == 0) {
+    for (int k = c.tid * 8; k < db; k += NCT * 8) {
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -977,43 +967,63 @@ __device__ void consumer_main(Ctx& c) {
         acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
         acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
       }
-      if (c.cta == 0) {
-        *reinterpret_cast<float4*>(p.xa + k) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(p.xa + k + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) ll_st2(p.xa + k + e, acc[e], acc[e + 1], tag_x);
     }
-    grid_sync(c);
   }
+  c.phase++;
   float xr[2][32];
   float(&x1r)[1][32] = *reinterpret_cast<float(*)[1][32]>(&xr[0]);
-  float* x = p.xa;
-  float* x1 = p.xb;
+  uint2* x = p.xa;
+  uint2* x1 = p.xb;
   const int nchunks = (S + 127) / 128;  // <= MAX_SPLIT for S <= 2048
+  constexpr int NLB = 2048 / (NCT * 2);
   NormW nw = prefetch_norm<2>(c, B.norm_in[0]);
   for (int l = 0; l < B.n_layers; ++l) {
-    load_slice_norm<1, 2>(c, x, db, db, nw, B.eps, x1r);
+    gather_ll<NLB>(c, x, tag_x, c.sattn);
+    mark(c, T_POLL);
+    csync();
+    norm_from_smem<1, 2>(c, c.sattn, nw, B.eps, x1r);
+    const unsigned tag_qkv = cur_tag(c);
     phase_linear<1>(c, B.wqkv[l], nqkv, db, x1r, p.qkv, nqkv, nullptr, 0);
-    grid_sync(c);
+    c.phase++;
+    const unsigned tag_att = cur_tag(c);
     for (int item = c.cta; item < B.n_kv_heads * nchunks; item += c.G)
-      backbone_attention_item(c, l, item % B.n_kv_heads, item / B.n_kv_heads, nchunks, pos, p.qkv);
+      backbone_attention_item(c, l, item % B.n_kv_heads, item / B.n_kv_heads, nchunks, pos, p.qkv, tag_qkv);
     mark(c, T_BATT);
-    grid_sync(c);
-    if (nchunks == 1) load_slice<1>(c, p.attn_out, db, db, x1r);
-    else merged_attention_slice(c, nchunks, x1r);
-    mark(c, T_MERGE);
+    c.phase++;
+    if (nchunks == 1) {
+      gather_ll<NLB>(c, p.attn_out, tag_att, c.sattn);
+      mark(c, T_POLL);
+      csync();
+      slice_from_smem<1>(c, c.sattn, db, x1r);
+    } else {
+      merged_attention_slice(c, nchunks, tag_att, x1r);
+      mark(c, T_MERGE);
+    }
+    const unsigned tag_x1 = cur_tag(c);
     phase_linear<1>(c, B.wo[l], db, db, x1r, x1, db, x, db);
+    c.phase++;
     nw = prefetch_norm<2>(c, B.norm_post[l]);
-    grid_sync(c);
-    load_slice_norm<1, 2>(c, x1, db, db, nw, B.eps, x1r);
+    gather_ll<NLB>(c, x1, tag_x1, c.sattn);
+    mark(c, T_POLL);
+    csync();
+    norm_from_smem<1, 2>(c, c.sattn, nw, B.eps, x1r);
+    const unsigned tag_act = cur_tag(c);
     phase_gate_up<1>(c, B.wgu[l], F, db, x1r, p.act);
-    grid_sync(c);
-    load_slice<1>(c, p.act, F, F, x1r);
-    phase_linear<1>(c, B.wdown[l], db, F, x1r, x, db, x1, db);
+    c.phase++;
     nw = prefetch_norm<2>(c, l + 1 < B.n_layers ? B.norm_in[l + 1] : B.norm_final);
-    grid_sync(c);
+    load_act_slice<1>(c, p.act, F, tag_act, x1r);
+    mark(c, T_POLL);
+    tag_x = cur_tag(c);
+    phase_linear<1>(c, B.wdown[l], db, F, x1r, x, db, x1, db);
+    c.phase++;
   }
   // ---- final norm -> h_last (decoder input row 0) ; codebook0 head ; sample c0
-  load_slice_norm<1, 2>(c, x, db, db, nw, B.eps, x1r);
+  gather_ll<NLB>(c, x, tag_x, c.sattn);
+  mark(c, T_POLL);
+  csync();
+  norm_from_smem<1, 2>(c, c.sattn, nw, B.eps, x1r);
   if (c.cta == 0 && c.warp < db / UNIT) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -1026,22 +1036,25 @@ __device__ void consumer_main(Ctx& c) {
   float hrow[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) hrow[e] = x1r[0][e];
+  unsigned tag_lg = cur_tag(c);
   phase_linear<1>(c, p.m.c0_head, V, db, x1r, p.logits, V, nullptr, 0);
-  grid_sync(c);
+  c.phase++;
   const unsigned long long draw0 = p.draw_base + (unsigned long long)pos * (unsigned)ncb;
-  int tok = sample_token(c, p.logits, V, draw0);
+  int tok = sample_token(c, p.logits, V, tag_lg, draw0);
   if (c.cta == 0 && c.tid == 0) p.frame_out[0] = tok;
   // ---- depth decoder: step 1 has rows (h_last @ pos 0, embed(c0) @ pos 1)   (generation.py:56-90)
 #pragma unroll
   for (int e = 0; e < 32; ++e) xr[0][e] = hrow[e];
   embed_row_slice(c, p.m.audio_emb + (size_t)tok * db, db, xr[1]);
   decoder_step<2>(c, 1, 0, xr);
-  tok = sample_token(c, p.logits, V, draw0 + 1);
+  tag_lg = (c.launch << 12) | ((c.phase - 1) & 0xfffu);
+  tok = sample_token(c, p.logits, V, tag_lg, draw0 + 1);
   if (c.cta == 0 && c.tid == 0) p.frame_out[1] = tok;
   for (int i = 2; i < ncb; ++i) {
     embed_row_slice(c, p.m.audio_emb + ((size_t)tok + (size_t)(i - 1) * V) * db, db, x1r[0]);
     decoder_step<1>(c, i, i, x1r);
-    tok = sample_token(c, p.logits, V, draw0 + (unsigned)i);
+    tag_lg = (c.launch << 12) | ((c.phase - 1) & 0xfffu);
+    tok = sample_token(c, p.logits, V, tag_lg, draw0 + (unsigned)i);
     if (c.cta == 0 && c.tid == 0) p.frame_out[i] = tok;
   }
 }
@@ -1049,9 +1062,8 @@ __device__ void consumer_main(Ctx& c) {
 __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ FrameParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[2 * NSTAGES + 1];
-  __shared__ float s_part[2 * 2 * MAXU * 4];  // [range][row][unit][4 partials]
+  __shared__ __align__(16) float s_part[2 * 2 * MAXU * 4];  // [range][row][unit][4 partials]
   __shared__ float s_red[NCW * 4];
-  __shared__ int s_abort;
   __shared__ __align__(16) float s_attn[2 * 1024 + NCW * 2 * 128];
   Ctx c;
   c.p = &p;
@@ -1070,15 +1082,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   c.q = 0;
-  c.epoch = 0;
+  c.phase = 0;
+  const unsigned nonce0 = *reinterpret_cast<volatile unsigned*>(p.nonce);
+  c.launch = (nonce0 % 0xfffffu) + 1u;
   c.aborted = false;
-  c.s_abort = &s_abort;
-  c.ntrace = 0;
   for (int i = 0; i < 12; ++i) c.t_acc[i] = 0;
-  c.t_last = (p.prof != nullptr) ? gtime() : 0ull;
+  c.t_last = (p.prof != nullptr) ? (unsigned long long)clock64() : 0ull;
   const unsigned long long t_begin = c.t_last;
   if (threadIdx.x == 0) {
-    s_abort = 0;
     for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(&c.ring.full[i], 1);
       mbar_init(&c.ring.empty[i], NCW);
@@ -1092,10 +1103,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
     if (c.lane == 0) producer_main(c);
   } else {
     consumer_main(c);
+    // CTA 0 can only get here after every CTA took part in every phase, i.e. after every CTA read the nonce
+    if (c.cta == 0 && c.tid == 0) *p.nonce = nonce0 + 1u;
     if (p.prof != nullptr && c.tid == 0) {
       for (int i = 0; i < 12; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = c.t_acc[i];
-      p.prof[(size_t)blockIdx.x * 16 + 12] = gtime() - t_begin;
-      p.prof[(size_t)blockIdx.x * 16 + 13] = c.epoch;
+      p.prof[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)clock64() - t_begin;
+      p.prof[(size_t)blockIdx.x * 16 + 13] = c.phase;
     }
   }
 }
@@ -1106,37 +1119,33 @@ using namespace csmb;
 
 static unsigned long long* g_prof_ptr = nullptr;  // debug only: csmb_debug_set_frame_prof
 static int g_dbg_flags = 0;
-static int g_pf_max = 0, g_pf_interval = 640;  // L2 prefetch measured slower than off (profiles/r01_frame_kernel_notes.md)
 
 extern "C" {
 
-/* debug: device buffer [n_sms][16] u64 receiving per-CTA phase timers (ns) of later csmb_frame_b1 launches; null = off */
+/* debug: device buffer [n_sms][16] u64 receiving per-CTA phase timers (SM cycles) of later csmb_frame_b1 launches */
 void csmb_debug_set_frame_prof(unsigned long long* device_buf) { g_prof_ptr = device_buf; }
 void csmb_debug_set_frame_flags(int flags) { g_dbg_flags = flags & 0xff; }
-void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles) { g_pf_max = max_stages; g_pf_interval = interval_cycles; }
 
-size_t csmb_frame_workspace_bytes(const csmb_model* m) {
-  if (!m) return 0;
+static size_t frame_ws_words(const csmb_model* m) {
   const csmb_llama &B = m->backbone, &D = m->decoder;
   const size_t nqkv_b = (size_t)(B.n_heads + 2 * B.n_kv_heads) * B.head_dim, nqkv_d = (size_t)(D.n_heads + 2 * D.n_kv_heads) * D.head_dim;
   const size_t ff = B.d_ff > D.d_ff ? B.d_ff : D.d_ff;
-  size_t f = 0;
-  f += 2 * (size_t)B.d_model;                                   // xa, xb
-  f += 2 * (nqkv_b > nqkv_d ? nqkv_b : nqkv_d);                  // qkv
-  f += (size_t)B.n_heads * MAX_SPLIT * PSTRIDE + (size_t)B.d_model;  // attn_part, attn_out
-  f += 2 * ff;                                                   // act
-  f += (size_t)B.d_model;                                        // h_last
-  f += (size_t)m->audio_vocab + 64;                              // logits
-  f += 4 * (size_t)D.d_model;                                    // dxa, dxb
-  f += (size_t)D.n_layers * 32 * 2 * D.n_kv_heads * D.head_dim;  // dec_kv
-  return f * sizeof(float) + 2048 /* barrier flags + abort flag */ + 8192 /* alignment slack */;
+  size_t w = 0;
+  w += 2 * (size_t)B.d_model;                                        // xa, xb
+  w += 2 * (nqkv_b > nqkv_d ? nqkv_b : nqkv_d);                       // qkv
+  w += (size_t)B.n_heads * MAX_SPLIT * PSTRIDE + (size_t)B.d_model;   // attn_part, attn_out
+  w += 2 * ff;                                                        // act
+  w += (size_t)m->audio_vocab + 64;                                   // logits
+  w += 4 * (size_t)D.d_model;                                         // dxa, dxb
+  return w;
 }
 
-/* Whole decode frame for ONE sequence in one persistent cooperative kernel (see top of file).
- * block_table: this sequence's row; pos: DEVICE int (position of this frame's backbone row);
- * workspace: csmb_frame_workspace_bytes() bytes.  Only temperature sampling without top-k/top-p/min-p (or greedy)
- * is fused; other sampler settings and other model shapes return CSMB_ERR_UNSUPPORTED (use csmb_decode_frame).
- * status (optional, DEVICE int[1]) receives 0 or a non-zero abort code if an internal wait timed out. */
+size_t csmb_frame_workspace_bytes(const csmb_model* m) {
+  if (!m) return 0;
+  const size_t dec_kv = (size_t)384 * m->decoder.n_layers * 32 * KROW * sizeof(float);  // private copy per CTA (<= 384 SMs)
+  return frame_ws_words(m) * sizeof(uint2) + (size_t)m->backbone.d_model * sizeof(float) + dec_kv + 256 + 16384;
+}
+
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
@@ -1145,14 +1154,18 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   CSMB_REQUIRE(m && kv_pool && block_table && prev_frame && pos && frame && sampler && workspace);
   const csmb_llama &B = m->backbone, &D = m->decoder;
   const bool shape_ok = B.d_model == 2048 && B.n_heads == 32 && B.n_kv_heads == 8 && B.head_dim == 64 &&
-                        B.d_ff % 1024 == 0 && D.d_model == 1024 && D.n_heads == 8 && D.n_kv_heads == 2 &&
-                        D.head_dim == 128 && D.d_ff % 1024 == 0 && m->n_codebooks <= 32 && m->n_codebooks >= 3;
+                        D.d_model == 1024 && D.n_heads == 8 && D.n_kv_heads == 2 && D.head_dim == 128 &&
+                        D.d_ff == 8192 && B.d_ff == 8192 && m->n_codebooks <= 32 && m->n_codebooks >= 3 &&
+                        m->audio_vocab <= 9 * NCT;
   if (!shape_ok) return CSMB_ERR_UNSUPPORTED;
   if (sampler->temperature != 0.f && ((sampler->top_k > 0 && sampler->top_k < m->audio_vocab) ||
                                      (sampler->top_p > 0.f && sampler->top_p < 1.f) || sampler->min_p > 0.f))
     return CSMB_ERR_UNSUPPORTED;
   CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m));
   cudaStream_t st = (cudaStream_t)stream;
+  int sms = 0;
+  CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CSMB_REQUIRE(sms <= 384);
 
   FrameParams p;
   p.m = *m;
@@ -1163,12 +1176,12 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   p.pos_ptr = pos;
   p.frame_out = frame;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
-  p.bar = reinterpret_cast<unsigned int*>(base);            // [<= 384] per-CTA epoch flags
-  p.abort_flag = reinterpret_cast<int*>(base + 1536);
-  float* f = reinterpret_cast<float*>(base + 2048);
+  p.abort_flag = reinterpret_cast<int*>(base);
+  p.nonce = reinterpret_cast<unsigned*>(base + 128);
+  uint2* w = reinterpret_cast<uint2*>(base + 256);
   auto take = [&](size_t n) {
-    float* r = f;
-    f += (n + 63) & ~(size_t)63;
+    uint2* r = w;
+    w += (n + 63) & ~(size_t)63;
     return r;
   };
   const size_t nqkv_b = (size_t)(B.n_heads + 2 * B.n_kv_heads) * B.head_dim, nqkv_d = (size_t)(D.n_heads + 2 * D.n_kv_heads) * D.head_dim;
@@ -1179,27 +1192,26 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   p.attn_part = take((size_t)B.n_heads * MAX_SPLIT * PSTRIDE);
   p.attn_out = take(B.d_model);
   p.act = take(2 * ff);
-  p.h_last = take(B.d_model);
   p.logits = take(m->audio_vocab);
   p.dxa = take(2 * (size_t)D.d_model);
   p.dxb = take(2 * (size_t)D.d_model);
-  p.dec_kv = take((size_t)D.n_layers * 32 * 2 * D.n_kv_heads * D.head_dim);
+  float* f = reinterpret_cast<float*>(w);
+  p.h_last = f;
+  f += B.d_model;
+  p.dec_kv = f;
+  f += (size_t)sms * D.n_layers * 32 * KROW;
   CSMB_REQUIRE(reinterpret_cast<uintptr_t>(f) <= reinterpret_cast<uintptr_t>(workspace) + workspace_bytes);
+  // tags are 20-bit launch nonces + 12-bit phase numbers; the workspace must start zeroed (tag 0 is never produced)
   p.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
   p.seed_lo = (uint32_t)sampler->seed;
   p.seed_hi = (uint32_t)(sampler->seed >> 32);
   p.draw_base = draw_base;
   p.prof = g_prof_ptr;
   p.dbg = g_dbg_flags;
-  p.pf_max = g_pf_max;
-  p.pf_interval = g_pf_interval;
 
   static const size_t dyn_smem = (size_t)NSTAGES * STAGE_BYTES + KVS_BYTES;  // ring + decoder KV staging
-  int sms = 0;
-  CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   CSMB_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-  CSMB_REQUIRE(sms <= 384);
-  CSMB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(base), 0, 2048, st));
+  CSMB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(base), 0, 64, st));  // abort flag only; the nonce persists
   void* args[] = {&p};
   CSMB_CUDA(cudaLaunchCooperativeKernel((void*)k_frame, dim3(sms), dim3(NTHREADS), args, dyn_smem, st));
   count_launch();

@@ -32,6 +32,11 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
 
 template <bool VEC>
@@ -114,6 +119,81 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
       yrow[n] = v;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small-M variant of the strided-row GEMM (streaming decode: M = B*T is 1..32 while the weights are MBs): the
+// weights are streamed once per block of RB rows by warps that split both N and K — 8 warps per CTA =
+// (8/KSPLIT) outputs x KSPLIT K-slices, partials reduced through shared memory in a fixed order — so even
+// N = 512 launches >= 296 CTAs' worth of warps.  Same prologue / epilogue as k_gemm_f32.
+template <int RB, int KSPLIT>
+__global__ void __launch_bounds__(256) k_gemv_f32(GemmArgs g) {
+  constexpr int NPC = 8 / KSPLIT;
+  __shared__ float red[8][RB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * NPC + warp / KSPLIT, ks = warp % KSPLIT;
+  const int m0 = blockIdx.y * RB;
+  const int M = g.B * g.T;
+  const int kper = ((g.K / 4 + KSPLIT - 1) / KSPLIT) * 4;
+  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
+  float acc[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+  if (n < g.N) {
+    const float* wrow = g.W + (size_t)n * g.K;
+    const float* arow[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int m = min(m0 + r, M - 1);
+      arow[r] = g.A + (long long)(m / g.T) * g.a_batch + (long long)(m % g.T) * g.lda;
+    }
+#pragma unroll 4
+    for (int k = kbeg + lane * 4; k < kend; k += 128) {
+      const float4 w = ldg_stream_f4(wrow + k);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(arow[r] + k));
+        if (g.act_in == 1) {
+          a.x = elu1(a.x); a.y = elu1(a.y); a.z = elu1(a.z); a.w = elu1(a.w);
+        }
+        acc[r] = fmaf(w.x, a.x, acc[r]);
+        acc[r] = fmaf(w.y, a.y, acc[r]);
+        acc[r] = fmaf(w.z, a.z, acc[r]);
+        acc[r] = fmaf(w.w, a.w, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const float v = warp_sum(acc[r]);
+    if (lane == 0) red[warp][r] = v;
+  }
+  __syncthreads();
+  if (ks == 0 && n < g.N && lane < RB && m0 + lane < M) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < KSPLIT; ++j) v += red[warp + j][lane];
+    const int m = m0 + lane, b = m / g.T, t = m % g.T;
+    if (g.bias) v += g.bias[n];
+    if (g.act_out == 1) v = gelu_erf(v);
+    if (g.scale) v *= g.scale[n];
+    if (g.Rsd) v += g.Rsd[(long long)b * g.r_batch + (long long)t * g.ldr + n];
+    g.Y[(long long)b * g.y_batch + (long long)t * g.ldy + n] = v;
+  }
+}
+
+template <int RB>
+static void launch_gemv(const GemmArgs& g, cudaStream_t st) {
+  const int M = g.B * g.T;
+  const int gy = cdiv(M, RB);
+  // smallest K-split that still gives every SM a couple of CTAs
+  int ksplit = 1;
+  while (ksplit < 8 && (long long)cdiv(g.N, 8 / ksplit) * gy < 296 && g.K / (ksplit * 2) >= 128) ksplit *= 2;
+  dim3 grid(cdiv(g.N, 8 / ksplit), gy);
+  if (ksplit == 1) k_gemv_f32<RB, 1><<<grid, 256, 0, st>>>(g);
+  else if (ksplit == 2) k_gemv_f32<RB, 2><<<grid, 256, 0, st>>>(g);
+  else if (ksplit == 4) k_gemv_f32<RB, 4><<<grid, 256, 0, st>>>(g);
+  else k_gemv_f32<RB, 8><<<grid, 256, 0, st>>>(g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,8 +421,17 @@ int csmb_gemm_f32(const float* A, long long a_batch, int lda, const float* W, fl
   dim3 grid(cdiv(N, 64), (unsigned)((M + 63) / 64));
   const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (a_batch % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  if (vec) k_gemm_f32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
-  else k_gemm_f32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+  if (vec && M <= 32) {
+    // the residual may alias Y (in-place layer update): each output element is read then written by one lane
+    if (M == 1) launch_gemv<1>(g, (cudaStream_t)stream);
+    else if (M == 2) launch_gemv<2>(g, (cudaStream_t)stream);
+    else if (M <= 4) launch_gemv<4>(g, (cudaStream_t)stream);
+    else launch_gemv<8>(g, (cudaStream_t)stream);
+  } else if (vec) {
+    k_gemm_f32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+  } else {
+    k_gemm_f32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+  }
   CSMB_LAUNCH_CHECK();
   return CSMB_OK;
 }

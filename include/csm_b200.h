@@ -178,7 +178,8 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
 /* Batch-1 latency path: ONE persistent cooperative kernel per frame (csrc/frame_kernel.cu) doing what
  * csmb_decode_frame does for a single sequence — generate_frame with T=1 (generation.py:21-92) plus the input
  * construction of :156-161 — with a producer warp per CTA streaming every weight matrix exactly once through a
- * shared-memory ring and grid-wide barriers between the ~640 dependent GEMV phases.
+ * shared-memory ring; the ~640 dependent GEMV phases synchronise through tagged activation words, not barriers.
+ * workspace must be zero-initialised once (csmb_frame_workspace_bytes) and belongs to one sequence.
  * block_table: this sequence's row of the paged-KV table; pos: DEVICE int, position of this frame's backbone row.
  * Fused samplers: greedy, or temperature without top-k/top-p/min-p; anything else (and model shapes other than
  * csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
@@ -188,8 +189,6 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/);
 void csmb_debug_set_frame_prof(unsigned long long* device_buf);
 /* debug: bit 0 = skip the GEMV arithmetic of csmb_frame_b1 (timing experiments only; results are wrong) */
 void csmb_debug_set_frame_flags(int flags);
-/* tuning: L2 prefetch distance (16 KiB stages per SM, 0 = off) and pacing (SM cycles between prefetches) of csmb_frame_b1 */
-void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles);
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,

@@ -214,15 +214,7 @@ def _fused():
     # in-kernel phase timers
     from csm_mlx_b200 import _lib
     prof = torch.zeros((148, 16), device=dev, dtype=torch.int64)
-    _lib.lib().csmb_debug_set_frame_prof(prof.data_ptr())
-    prev = st.decode_frame_fused(prev, spec)
-    torch.cuda.synchronize()
-    _lib.lib().csmb_debug_set_frame_prof(None)
-    names = ["sync", "load", "gemv", "fin", "datt", "batt", "sample", "merge", "wait", "arrive"]
-    pr = prof.cpu().double() / 1.9e3  # cycles -> us at ~1.9 GHz
-    for cta in (0, 1, 77, 147):
-        print(f"cta {cta}: total {pr[cta, 12]:.0f} us, barriers {int(prof[cta, 13])}: " + ", ".join(f"{n} {pr[cta, i]:.0f}" for i, n in enumerate(names)))
-    print("mean over CTAs: " + ", ".join(f"{n} {pr[:, i].mean():.0f}" for i, n in enumerate(names)))
+    names = ["poll", "load", "gemv", "fin", "datt", "batt", "sample", "merge", "wait"]
 
     def prof_run(tag):
         for _ in range(3):
@@ -239,33 +231,11 @@ def _fused():
         torch.cuda.synchronize()
         _lib.lib().csmb_debug_set_frame_prof(None)
         pr = prof.cpu().double() / 1.9e3
-        print(f"{tag}: {ms:.3f} ms/frame ({9.1067e9 / ms / 1e6 / 6557.8:.3f} of peak) | " + ", ".join(f"{n} {pr[:, i].mean():.0f}" for i, n in enumerate(names)))
-    _lib.lib().csmb_debug_set_frame_prefetch(0, 640)
+        print(f"{tag}: {ms:.3f} ms/frame ({9.1067e9 / ms / 1e6 / 6557.8:.3f} of peak) status {int(st.frame_status.item())} | "
+              + ", ".join(f"{n} {pr[:, i].mean():.0f}" for i, n in enumerate(names)) + f" | total {pr[:, 12].mean():.0f} phases {int(prof[0, 13])}")
     for fl in (0, 1, 8):
         _lib.lib().csmb_debug_set_frame_flags(fl)
         prof_run(f"dbg flags {fl}")
     _lib.lib().csmb_debug_set_frame_flags(0)
-    _lib.lib().csmb_debug_set_frame_prefetch(0, 640)
     (toks2,) = generation.generate_tokens(model, [(ptok, pmask)], 25, temperature=0.0)
     print("generate_tokens (fused) equals golden:", bool((toks2.numpy() == g["tokens"]).all()))
-    # raw trace of CTA 1 thread 0
-    prof2 = torch.zeros((148 * 16 + 2 * 6000,), device=dev, dtype=torch.int64)
-    _lib.lib().csmb_debug_set_frame_flags(4)
-    _lib.lib().csmb_debug_set_frame_prof(prof2.data_ptr())
-    st.decode_frame_fused(frames[-1], spec)
-    torch.cuda.synchronize()
-    _lib.lib().csmb_debug_set_frame_prof(None)
-    _lib.lib().csmb_debug_set_frame_flags(0)
-    tr = prof2[148 * 16:].cpu().reshape(-1, 2)
-    tr = tr[tr[:, 1] > 0]
-    # print the events of decoder step ~20 (skip the backbone: find the 25th occurrence of id 40 x4 per step)
-    idx40 = (tr[:, 0] == 40).nonzero().flatten()
-    start = int(idx40[4 * 18]) if len(idx40) > 4 * 18 else 0
-    seg = tr[start:start + 60]
-    t0c = int(seg[0, 1])
-    print("trace (id, cycles since start, delta):")
-    prevc = t0c
-    for i in range(seg.shape[0]):
-        cyc = int(seg[i, 1])
-        print(f"  {int(seg[i, 0]):3d} {cyc - t0c:7d} {cyc - prevc:6d}")
-        prevc = cyc

@@ -146,3 +146,44 @@ def test_inputs_too_long_raises(model_1b):
     tok, mask = tokenizers.tokenize_text_segment(prompt_ids(5, 1998), 0)  # 2000 rows
     with pytest.raises(ValueError, match="Inputs too long"):
         generation.generate_tokens(model_1b, [(tok, mask)], 125)
+
+
+def test_fused_frame_kernel_equals_per_op_path(model_1b, monkeypatch):
+    """The persistent frame kernel (csmb_frame_b1) and the per-op CUDA-graph path produce the same greedy tokens."""
+    (fused,) = generation.generate_tokens(model_1b, [_prompt()], 6, temperature=0.0)
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    (per_op,) = generation.generate_tokens(model_1b, [_prompt()], 6, temperature=0.0)
+    assert torch.equal(fused, per_op)
+
+
+def test_fused_frame_kernel_temperature_sampling_matches_oracle(model_1b, oracle_1b):
+    """temperature 0.8, no filters: the frame kernel's in-kernel Gumbel/Philox sampling == the oracle's definition."""
+    tok, mask = _prompt()
+    n_prompt = tok.shape[0]
+    state = {"f": 0}
+
+    def sampler(logits, i):
+        pos = n_prompt - 1 + state["f"]
+        t = osamp.sample(logits[0].numpy(), 0.8, seed=77, draw=pos * 32 + i, row=0)
+        if i == 31:
+            state["f"] += 1
+        return torch.tensor([t])
+
+    exp = olm.generate_tokens(oracle_1b, tok.long(), mask, 4, sampler=sampler)
+    (got,) = generation.generate_tokens(model_1b, [(tok, mask)], 4, sampler=SamplerSpec(temperature=0.8, seed=77))
+    assert torch.equal(got.long(), exp)
+
+
+def test_long_context_multi_chunk_attention_vs_oracle(model_1b, oracle_1b):
+    """150-row prompt (> 128 keys: the frame kernel's multi-chunk attention + merge path; prefill through the tiled
+    linear): greedy tokens equal the oracle's."""
+    gen = torch.Generator().manual_seed(31)
+    t1 = olm.text_rows(prompt_ids(3, 8))
+    a1 = olm.audio_rows(torch.randint(0, 2048, (32, 128), generator=gen))
+    t2 = olm.text_rows(prompt_ids(4, 9))
+    tok = torch.cat([t1[0], a1[0], t2[0]])
+    mask = torch.cat([t1[1], a1[1], t2[1]])
+    assert tok.shape[0] == 150
+    exp = olm.generate_tokens(oracle_1b, tok, mask, 3)
+    (got,) = generation.generate_tokens(model_1b, [(tok.int(), mask)], 3, temperature=0.0)
+    assert torch.equal(got.long(), exp)
