@@ -66,6 +66,8 @@ _SIGS = {
     "csmb_embed_audio": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_rmsnorm": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
     "csmb_linear": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "csmb_linear_tc_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "csmb_linear_tc": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _I, _P]),
     "csmb_swiglu": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "csmb_rope_kv_append": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "csmb_attention": (C.c_int, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

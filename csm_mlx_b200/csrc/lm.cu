@@ -21,10 +21,17 @@ struct Workspace {
   int32_t *dec_seq, *dec_pos;              // [rows] decoder row maps (rebuilt per step)
   int32_t *dec_bt;                         // [batch][dec_pages]
   int32_t *c0_tmp;                         // [batch]
+  void* tc;                                // scratch of the tensor-core linear (bf16 hi/lo split, split-K partials)
+  size_t tc_bytes;
   size_t bytes;
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr int TC_MIN_ROWS = 16;  // from this many rows on, linears run on the tensor cores (gemm_tc.cu)
+
+struct Workspace;
+static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
+               int accumulate, cudaStream_t st);
 
 static Workspace carve(const csmb_model& m, int max_rows, void* base) {
   const csmb_llama &b = m.backbone, &d = m.decoder;
@@ -62,8 +69,29 @@ static Workspace carve(const csmb_model& m, int max_rows, void* base) {
   w.dec_pos = (int32_t*)take(R * 4);
   w.dec_bt = (int32_t*)take(R * (size_t)dec_pages * 4);
   w.c0_tmp = (int32_t*)take(R * 4);
+  // tensor-core linear scratch: the largest requirement over this model's (N, K) shapes at max_rows rows
+  size_t tcb = 0;
+  if (max_rows >= TC_MIN_ROWS) {
+    const int shapes[][2] = {{qkv_b, b.d_model}, {b.d_model, b.n_heads * b.head_dim}, {2 * b.d_ff, b.d_model}, {b.d_model, b.d_ff},
+                             {qkv_d, d.d_model}, {d.d_model, d.n_heads * d.head_dim}, {2 * d.d_ff, d.d_model}, {d.d_model, d.d_ff},
+                             {m.audio_vocab, b.d_model}, {m.audio_vocab, d.d_model}, {d.d_model, b.d_model}};
+    for (auto& sh : shapes)
+      if (sh[1] % 64 == 0) {
+        const size_t need = linear_tc_workspace_bytes(max_rows, sh[0], sh[1]);
+        tcb = need > tcb ? need : tcb;
+      }
+  }
+  w.tc = take(tcb);
+  w.tc_bytes = tcb;
   w.bytes = off;
   return w;
+}
+
+static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
+               int accumulate, cudaStream_t st) {
+  if (R >= TC_MIN_ROWS && K % 64 == 0 && w.tc != nullptr && w.tc_bytes >= linear_tc_workspace_bytes(R, N, K))
+    return launch_linear_tc(x, ldx, W, y, ldy, R, N, K, accumulate, w.tc, w.tc_bytes, st);
+  return launch_linear(x, ldx, W, y, ldy, R, N, K, accumulate, st);
 }
 
 // ---- small index kernels ------------------------------------------------------------------------
@@ -107,17 +135,17 @@ static int llama_layers(const csmb_llama& L, float* x, const Workspace& w, float
   for (int l = 0; l < L.n_layers; ++l) {
     float* pool = kv_pool + (size_t)l * kv_layer_stride;
     if ((rc = launch_rmsnorm(x, d, L.norm_in[l], w.xn, d, R, d, L.eps, nullptr, st))) return rc;
-    if ((rc = launch_linear(w.xn, d, L.wqkv[l], w.qkv, nqkv, R, nqkv, d, 0, st))) return rc;
+    if ((rc = lin(w, w.xn, d, L.wqkv[l], w.qkv, nqkv, R, nqkv, d, 0, st))) return rc;
     if ((rc = launch_rope_kv_append(w.qkv, L.rope, pool, block_table, max_pages, row_seq, row_pos, R, H, Hkv, hd, st)))
       return rc;
     if ((rc = launch_attention(w.qkv, nqkv, pool, block_table, max_pages, row_seq, row_pos, w.attn, R, H, Hkv, hd,
                                max_pos, st)))
       return rc;
-    if ((rc = launch_linear(w.attn, H * hd, L.wo[l], x, d, R, d, H * hd, 1, st))) return rc;
+    if ((rc = lin(w, w.attn, H * hd, L.wo[l], x, d, R, d, H * hd, 1, st))) return rc;
     if ((rc = launch_rmsnorm(x, d, L.norm_post[l], w.xn, d, R, d, L.eps, nullptr, st))) return rc;
-    if ((rc = launch_linear(w.xn, d, L.wgu[l], w.gu, 2 * F, R, 2 * F, d, 0, st))) return rc;
+    if ((rc = lin(w, w.xn, d, L.wgu[l], w.gu, 2 * F, R, 2 * F, d, 0, st))) return rc;
     if ((rc = launch_swiglu(w.gu, w.act, R, F, st))) return rc;
-    if ((rc = launch_linear(w.act, F, L.wdown[l], x, d, R, d, F, 1, st))) return rc;
+    if ((rc = lin(w, w.act, F, L.wdown[l], x, d, R, d, F, 1, st))) return rc;
   }
   return CSMB_OK;
 }
@@ -147,7 +175,7 @@ static int backbone_forward(const csmb_model& m, const csmb_batch& b, const Work
   if ((rc = launch_rmsnorm(w.x, L.d_model, L.norm_final, h_last, L.d_model, n_last, L.d_model, L.eps, last_rows, st)))
     return rc;
   if (c0_logits)
-    if ((rc = launch_linear(h_last, L.d_model, m.c0_head, c0_logits, m.audio_vocab, n_last, m.audio_vocab,
+    if ((rc = lin(w, h_last, L.d_model, m.c0_head, c0_logits, m.audio_vocab, n_last, m.audio_vocab,
                             L.d_model, 0, st)))
       return rc;
   return CSMB_OK;
@@ -177,7 +205,7 @@ static int depth_decode(const csmb_model& m, const csmb_batch& b, const Workspac
     k_dec_rows<<<cdiv(B * 2 > B * dec_pages ? B * 2 : B * dec_pages, 128), 128, 0, st>>>(
         w.dec_seq, w.dec_pos, w.dec_bt, B, rps, i == 1 ? 0 : i, dec_pages);
     CSMB_LAUNCH_CHECK();
-    if ((rc = launch_linear(w.din, db, m.projection, w.dx, dd, R, dd, db, 0, st))) return rc;
+    if ((rc = lin(w, w.din, db, m.projection, w.dx, dd, R, dd, db, 0, st))) return rc;
     if ((rc = llama_layers(L, w.dx, w, b.dec_kv_pool, b.dec_kv_layer_stride, w.dec_bt, dec_pages, w.dec_seq,
                            w.dec_pos, R, dec_pages * CSMB_PAGE, st)))
       return rc;
@@ -187,7 +215,7 @@ static int depth_decode(const csmb_model& m, const csmb_batch& b, const Workspac
     if ((rc = launch_rmsnorm(last, ldlast, L.norm_final, w.hn, dd, B, dd, L.eps, nullptr, st))) return rc;
     float* lg = logits_out ? logits_out + (size_t)i * V : w.logits;
     const int ldl = logits_out ? ncb * V : V;
-    if ((rc = launch_linear(w.hn, dd, m.audio_head_t + (size_t)(i - 1) * V * dd, lg, ldl, B, V, dd, 0, st))) return rc;
+    if ((rc = lin(w, w.hn, dd, m.audio_head_t + (size_t)(i - 1) * V * dd, lg, ldl, B, V, dd, 0, st))) return rc;
     if ((rc = launch_sample(lg, ldl, frame + i, ncb, B, V, sampler, draw_base + (uint64_t)i, pos, (uint32_t)ncb,
                             forced ? forced + i : nullptr, ncb, st)))
       return rc;

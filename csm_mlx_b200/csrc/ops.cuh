@@ -27,4 +27,9 @@ int launch_sample(const float* logits, int ldl, int32_t* out, int out_stride, in
                   const csmb_sampler& s, uint64_t draw_base, const int32_t* row_pos, uint32_t draw_pos_mul,
                   const int32_t* forced, int forced_stride, cudaStream_t st);
 
+// tcgen05 / TMEM / TMA linear for R >= 9 rows, K % 64 == 0 (gemm_tc.cu).  workspace: linear_tc_workspace_bytes(R, N, K), zeroed once.
+size_t linear_tc_workspace_bytes(int R, int N, int K);
+int launch_linear_tc(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K, int accumulate,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace csmb

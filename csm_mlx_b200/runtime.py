@@ -70,7 +70,7 @@ class LMState:
         if rows <= self._ws_rows:
             return
         nbytes = _lib.lib().csmb_lm_workspace_bytes(C.byref(self.model.desc()), rows)
-        self.workspace = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
+        self.workspace = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # zeroed: sticky error flag inside
         self._ws_rows = rows
 
     def _batch_desc(self) -> _lib.Batch:

@@ -70,6 +70,16 @@ int csmb_rmsnorm(const float* x, int ldx, const float* w, float* y, int ldy, int
 int csmb_linear(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
                 int accumulate, int device, void* stream);
 
+/* Tensor-core variant of csmb_linear for many rows (prefill, batched decode): tcgen05.mma (kind::f16, fp32 TMEM
+ * accumulators) fed by TMA; the weight tile is the UMMA A operand (M = 128 rows), the token rows are N (<= 256 per
+ * tile); X is split into bf16 hi + lo on the fly and both halves are accumulated, so results match fp32 math on the
+ * bf16 weights to ~1e-5.  Small-N shapes are split along K over up to 16 CTAs per tile (fp32 partials, fixed-order
+ * reduction).  Requires K % 64 == 0; workspace = csmb_linear_tc_workspace_bytes(R, N, K) bytes, 256-byte aligned, zeroed
+ * once by its owner (first int = sticky error flag set if an internal bounded wait timed out). */
+size_t csmb_linear_tc_workspace_bytes(int R, int N, int K);
+int csmb_linear_tc(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K, int accumulate,
+                   void* workspace, size_t workspace_bytes, int device, void* stream);
+
 /* SwiGLU of mlx_lm MLP: out[r][f] = silu(gu[r][f]) * gu[r][F+f]   (gu = fused gate|up output). */
 int csmb_swiglu(const float* gu, float* out, int R, int F, int device, void* stream);
 

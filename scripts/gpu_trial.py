@@ -239,3 +239,30 @@ def _fused():
     _lib.lib().csmb_debug_set_frame_flags(0)
     (toks2,) = generation.generate_tokens(model, [(ptok, pmask)], 25, temperature=0.0)
     print("generate_tokens (fused) equals golden:", bool((toks2.numpy() == g["tokens"]).all()))
+
+
+@section("batch")
+def _batch():
+    from tests.workloads import prompt_ids
+    for B in (16, 64):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        st = LMState(model, B, max_len=64)
+        t1 = time.time()
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        spec = SamplerSpec()
+        frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+        torch.cuda.synchronize()
+        print(f"B={B} prefill+first frame {1e3 * (time.time() - t1):.1f} ms")
+        prev = frame
+        for _ in range(3):
+            prev = st.decode_frame_graphed(prev, spec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            prev = st.decode_frame_graphed(prev, spec)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"B={B} decode frame (graph): {ms:.2f} ms -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s, {9.1067e9 / ms / 1e6 / 6557.8:.3f} of HBM roofline")

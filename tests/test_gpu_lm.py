@@ -187,3 +187,13 @@ def test_long_context_multi_chunk_attention_vs_oracle(model_1b, oracle_1b):
     exp = olm.generate_tokens(oracle_1b, tok, mask, 3)
     (got,) = generation.generate_tokens(model_1b, [(tok.int(), mask)], 3, temperature=0.0)
     assert torch.equal(got.long(), exp)
+
+
+def test_batch16_tensor_core_path_matches_single(model_1b):
+    """16 utterances in lock-step: every linear runs on the tcgen05 path (rows >= 16); each must equal the
+    utterance generated alone through the batch-1 kernels."""
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(40 + i, 8 + (i % 5)), i % 3) for i in range(16)]
+    batched = generation.generate_tokens(model_1b, prompts, 3, temperature=0.0)
+    for i in (0, 7, 15):
+        (single,) = generation.generate_tokens(model_1b, [prompts[i]], 3, temperature=0.0)
+        assert torch.equal(single, batched[i]), i

@@ -177,3 +177,20 @@ def test_sample_matches_oracle_philox(device, spec):
         exp = [osamp.sample(lg[r].numpy(), spec[0], seed=spec[5], draw=draw, row=r, top_k=spec[1], top_p=spec[2],
                             min_p=spec[3], min_keep=spec[4]) for r in range(4)]
         assert got == exp
+
+
+@pytest.mark.parametrize("R,N,K", [(16, 3072, 2048), (64, 16384, 2048), (64, 2048, 8192), (10, 2051, 2048),
+                                   (150, 3072, 2048), (300, 2048, 2048), (33, 2051, 1024), (128, 1024, 1024)])
+def test_linear_tensor_core(device, R, N, K):
+    """tcgen05 linear (bf16 hi+lo split of the activations): within 2e-5 relative of fp64 math on the bf16 weights."""
+    g = torch.Generator().manual_seed(R + N + K)
+    x = torch.randn(R, K, generator=g).to(device)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(torch.bfloat16).to(device)
+    y = torch.full((R, N), 0.5, device=device)
+    nbytes = _lib.lib().csmb_linear_tc_workspace_bytes(R, N, K)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    _lib.check(_lib.lib().csmb_linear_tc(x.data_ptr(), K, w.data_ptr(), y.data_ptr(), N, R, N, K, 1, ws.data_ptr(), nbytes, 0,
+                                         _st(device)))
+    ref = x.double() @ w.double().t() + 0.5
+    assert int(ws[:4].view(torch.int32).item()) == 0  # no internal wait timed out
+    assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())) * 4
