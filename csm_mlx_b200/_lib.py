@@ -79,7 +79,7 @@ _SIGS = {
                                     _P, _P, _P, _I, _I, _I, _P]),
     "csmb_decode_frame": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
                                     C.c_uint64, _I, _P]),
-    "csmb_frame_workspace_bytes": (C.c_size_t, [C.POINTER(Model)]),
+    "csmb_frame_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I]),
     "csmb_debug_set_frame_prof": (None, [_P]),
     "csmb_debug_set_frame_flags": (None, [_I]),
     "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P,

@@ -198,6 +198,19 @@ __device__ __forceinline__ bool poll_continue(Ctx& c, unsigned& spins, int code)
   return true;
 }
 __device__ __forceinline__ unsigned cur_tag(const Ctx& c) { return (c.launch << 12) | (c.phase & 0xfffu); }
+// Stage 1 of every tagged read: lane 0 of the warp polls ONE word (with a short back-off) and the other 31 lanes sleep
+// at the warp barrier; only then does the whole warp load and verify everything it needs.  Without this, 256 threads
+// x several loads per poll round from each of the 148 CTAs hammer the very L2 lines the producers are storing to.
+__device__ __forceinline__ void probe_wait(Ctx& c, const uint2* word, unsigned tag) {
+  if (c.lane == 0 && !c.aborted) {
+    unsigned spins = 0;
+    while (ll_ld(word).y != tag) {
+      __nanosleep(40);
+      if (!poll_continue(c, spins, 150)) break;
+    }
+  }
+  __syncwarp();
+}
 // consumer-side sync (shared-memory results visible to all consumer warps)
 __device__ __forceinline__ void csync() { named_bar_sync(2, NCT); }
 
@@ -215,74 +228,80 @@ __device__ __forceinline__ int n_stages(const Range& r) {
 }
 
 // ------------------------------------------------------------------------------------------------ consumer GEMV
-// Partial dot products of R activation rows with every unit of the range.  Two ring stages are processed per
-// iteration, both unconditionally (a missing second stage just produces an unused value) so that their LDS -> FMA ->
-// shuffle chains interleave; two accumulators per (unit, row) halve the dependent-FMA chain.  The lane reduction
-// stops after three shuffle steps and leaves 4 partials per unit: part[(r*MAXU + u)*4 + 0..3].
+// Partial dot products of R activation rows with every unit of the range.  GS ring stages are processed per iteration,
+// all unconditionally (a missing stage just produces an unused value) so that their LDS -> FMA -> shuffle chains
+// interleave and the per-iteration bookkeeping (mbarrier waits / arrives, loop control) is amortised; two accumulators
+// per (unit, row) halve the dependent-FMA chain.  The lane reduction stops after three shuffle steps and leaves 4
+// partials per unit: part[(r*MAXU + u)*4 + 0..3].
 template <int R>
 __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float* part) {
   if (c.p->dbg & 8) return;  // timing experiment: no streaming at all (pure latency chain)
+  constexpr int GS = 2;  // 4 was measured slower: longer waits and fewer free ring slots for the producer
   const int KS = r.K / UNIT;
   const int units = r.rows * KS;
   const int nst = n_stages(r);
   const bool math = !(c.p->dbg & 1);
   const size_t woff = (size_t)c.warp * (UNIT * 2) + c.lane * 16;
-  for (int s = 0; s < nst; s += 2) {
-    const bool two = s + 1 < nst;
-    const int slot0 = c.q % NSTAGES, slot1 = (c.q + 1) % NSTAGES;
-    const uint32_t par0 = (c.q / NSTAGES) & 1, par1 = ((c.q + 1) / NSTAGES) & 1;
+  for (int s = 0; s < nst; s += GS) {
+    const int ns = min(GS, nst - s);
     mark(c, T_GEMV);
-    mbar_wait(c, &c.ring.full[slot0], par0, 2);
-    if (two) mbar_wait(c, &c.ring.full[slot1], par1, 2);
-    mark(c, T_WAIT);
-    const int u0 = s * NCW + c.warp, u1 = u0 + NCW;
-    float a0[R][2], a1[R][2];
 #pragma unroll
-    for (int i = 0; i < R; ++i) a0[i][0] = a0[i][1] = a1[i][0] = a1[i][1] = 0.f;
+    for (int g = 0; g < GS; ++g)
+      if (g < ns) mbar_wait(c, &c.ring.full[(c.q + g) % NSTAGES], ((c.q + g) / NSTAGES) & 1, 2);
+    mark(c, T_WAIT);
+    float acc[GS][R][2];
+#pragma unroll
+    for (int g = 0; g < GS; ++g)
+#pragma unroll
+      for (int i = 0; i < R; ++i) acc[g][i][0] = acc[g][i][1] = 0.f;
     if (math && !c.aborted) {
-      const unsigned char* b0 = c.ring.data + (size_t)slot0 * STAGE_BYTES + woff;
-      const unsigned char* b1 = c.ring.data + (size_t)slot1 * STAGE_BYTES + woff;
+      const unsigned char* b[GS];
+#pragma unroll
+      for (int g = 0; g < GS; ++g) b[g] = c.ring.data + (size_t)((c.q + g) % NSTAGES) * STAGE_BYTES + woff;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        const uint4 w0 = *reinterpret_cast<const uint4*>(b0 + ch * 512);
-        const uint4 w1 = *reinterpret_cast<const uint4*>(b1 + ch * 512);
-        const float f0[8] = {bf16lo(w0.x), bf16hi(w0.x), bf16lo(w0.y), bf16hi(w0.y), bf16lo(w0.z), bf16hi(w0.z), bf16lo(w0.w), bf16hi(w0.w)};
-        const float f1[8] = {bf16lo(w1.x), bf16hi(w1.x), bf16lo(w1.y), bf16hi(w1.y), bf16lo(w1.z), bf16hi(w1.z), bf16lo(w1.w), bf16hi(w1.w)};
+        uint4 w[GS];
 #pragma unroll
-        for (int i = 0; i < R; ++i)
+        for (int g = 0; g < GS; ++g) w[g] = *reinterpret_cast<const uint4*>(b[g] + ch * 512);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            a0[i][e & 1] = fmaf(f0[e], xr[i][ch * 8 + e], a0[i][e & 1]);
-            a1[i][e & 1] = fmaf(f1[e], xr[i][ch * 8 + e], a1[i][e & 1]);
-          }
+        for (int g = 0; g < GS; ++g) {
+          const float f[8] = {bf16lo(w[g].x), bf16hi(w[g].x), bf16lo(w[g].y), bf16hi(w[g].y),
+                              bf16lo(w[g].z), bf16hi(w[g].z), bf16lo(w[g].w), bf16hi(w[g].w)};
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[g][i][e & 1] = fmaf(f[e], xr[i][ch * 8 + e], acc[g][i][e & 1]);
+        }
       }
     }
-    float s0[R], s1[R];
+    float sum[GS][R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      s0[i] = a0[i][0] + a0[i][1];
-      s1[i] = a1[i][0] + a1[i][1];
-    }
+    for (int g = 0; g < GS; ++g)
+#pragma unroll
+      for (int i = 0; i < R; ++i) sum[g][i] = acc[g][i][0] + acc[g][i][1];
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1)
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
-        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-      }
+      for (int g = 0; g < GS; ++g)
+#pragma unroll
+        for (int i = 0; i < R; ++i) sum[g][i] += __shfl_xor_sync(0xffffffffu, sum[g][i], o);
     if (c.lane < 4) {
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        if (u0 < units) part[((size_t)i * MAXU + u0) * 4 + c.lane] = s0[i];
-        if (two && u1 < units) part[((size_t)i * MAXU + u1) * 4 + c.lane] = s1[i];
+      for (int g = 0; g < GS; ++g) {
+        const int u = (s + g) * NCW + c.warp;
+        if (g < ns && u < units) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) part[((size_t)i * MAXU + u) * 4 + c.lane] = sum[g][i];
+        }
       }
     }
     __syncwarp();
     if (c.lane == 0) {
-      mbar_arrive(&c.ring.empty[slot0]);
-      if (two) mbar_arrive(&c.ring.empty[slot1]);
+#pragma unroll
+      for (int g = 0; g < GS; ++g)
+        if (g < ns) mbar_arrive(&c.ring.empty[(c.q + g) % NSTAGES]);
     }
-    c.q += two ? 2 : 1;
+    c.q += ns;
   }
 }
 
@@ -305,6 +324,7 @@ template <int NL>
 __device__ __forceinline__ void gather_ll(Ctx& c, const uint2* src, unsigned tag, float* dst) {
   uint4 v[NL];
   unsigned spins = 0;
+  probe_wait(c, src + (size_t)(NL - 1) * (NCT * 2) + c.warp * 64 + 63, tag);
   while (true) {
 #pragma unroll
     for (int j = 0; j < NL; ++j) v[j] = ll_ld2(src + (size_t)j * (NCT * 2) + c.tid * 2);
@@ -380,6 +400,7 @@ __device__ __forceinline__ void load_act_slice(Ctx& c, const uint2* act, int F, 
     const uint2* base = act + (size_t)i * F + c.warp * UNIT + c.lane * 8;
     uint4 v[16];
     unsigned spins = 0;
+    probe_wait(c, act + (size_t)i * F + c.warp * UNIT + UNIT - 1, tag);
     while (true) {
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
@@ -452,6 +473,7 @@ __device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, un
   const FrameParams& p = *c.p;
   uint2 v[9];
   unsigned spins = 0;
+  probe_wait(c, logits + min(V - 1, c.warp * (V / NCW) + V / NCW - 1), tag);
   while (true) {
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -519,6 +541,7 @@ __device__ void decoder_attention(Ctx& c, float* kvl, int pos0, const uint2* qkv
   {
     uint4 t[R][6];
     unsigned spins = 0;
+    probe_wait(c, qkv + (size_t)(R - 1) * ldq + (H + HKV + kvh) * HD + HD - 1, tag);
     while (true) {
 #pragma unroll
       for (int i = 0; i < R; ++i) {
@@ -632,6 +655,7 @@ __device__ void backbone_attention_item(Ctx& c, int layer, int kvh, int chunk, i
   {
     uint4 t[3];
     unsigned spins = 0;
+    probe_wait(c, qkv + (H + HKV + kvh) * HD + HD - 1, tag_in);
     while (true) {
       t[0] = ll_ld2(qkv + hq * HD + c.lane * 2);
       t[1] = ll_ld2(qkv + (H + kvh) * HD + c.lane * 2);
@@ -776,6 +800,7 @@ __device__ void merged_attention_slice(Ctx& c, int nchunks, unsigned tag, float 
     const uint2* src = p.attn_part + (size_t)s * WORDS;
     uint2 v[9];
     unsigned spins = 0;
+    probe_wait(c, src + 8 * NCT + c.warp * 32 + 31, tag);
     while (true) {
 #pragma unroll
       for (int j = 0; j < 9; ++j) v[j] = ll_ld(src + j * NCT + c.tid);
@@ -1140,9 +1165,11 @@ static size_t frame_ws_words(const csmb_model* m) {
   return w;
 }
 
-size_t csmb_frame_workspace_bytes(const csmb_model* m) {
+size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
   if (!m) return 0;
-  const size_t dec_kv = (size_t)384 * m->decoder.n_layers * 32 * KROW * sizeof(float);  // private copy per CTA (<= 384 SMs)
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 384;
+  const size_t dec_kv = (size_t)sms * m->decoder.n_layers * 32 * KROW * sizeof(float);  // private copy per CTA
   return frame_ws_words(m) * sizeof(uint2) + (size_t)m->backbone.d_model * sizeof(float) + dec_kv + 256 + 16384;
 }
 
@@ -1161,7 +1188,7 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   if (sampler->temperature != 0.f && ((sampler->top_k > 0 && sampler->top_k < m->audio_vocab) ||
                                      (sampler->top_p > 0.f && sampler->top_p < 1.f) || sampler->min_p > 0.f))
     return CSMB_ERR_UNSUPPORTED;
-  CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m));
+  CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m, device));
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 0;
   CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

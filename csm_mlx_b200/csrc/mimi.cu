@@ -197,23 +197,40 @@ static void launch_gemv(const GemmArgs& g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over the last dim (with bias), one warp per row.
+// LayerNorm over the last dim (with bias), one warp per row; the row (d <= 1024, d % 128 == 0) stays in registers.
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, long long x_batch,
                                                    const float* __restrict__ w, const float* __restrict__ b,
                                                    float* __restrict__ y, int R, int T, int d, float eps) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
   const float* xr = x + (long long)(r / T) * x_batch + (long long)(r % T) * d;
+  float4 v[8];
+  const int nv = d / 128;
   float s = 0.f;
-  for (int c = lane; c < d; c += 32) s += xr[c];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      v[j] = *reinterpret_cast<const float4*>(xr + j * 128 + lane * 4);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
   const float mean = warp_sum(s) / (float)d;
-  float v = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const float t = xr[c] - mean;
-    v += t * t;
-  }
-  const float rstd = rsqrtf(warp_sum(v) / (float)d + eps);
-  for (int c = lane; c < d; c += 32) y[(size_t)r * d + c] = (xr[c] - mean) * rstd * w[c] + b[c];
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const float a0 = v[j].x - mean, a1 = v[j].y - mean, a2 = v[j].z - mean, a3 = v[j].w - mean;
+      q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const float4 g = *reinterpret_cast<const float4*>(w + j * 128 + lane * 4);
+      const float4 bb = *reinterpret_cast<const float4*>(b + j * 128 + lane * 4);
+      *reinterpret_cast<float4*>(y + (size_t)r * d + j * 128 + lane * 4) =
+          make_float4((v[j].x - mean) * rstd * g.x + bb.x, (v[j].y - mean) * rstd * g.y + bb.y,
+                      (v[j].z - mean) * rstd * g.z + bb.z, (v[j].w - mean) * rstd * g.w + bb.w);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,11 +302,22 @@ __global__ void __launch_bounds__(128) k_mimi_attention(const float* __restrict_
   sum = warp_sum(sum);
   __syncwarp();
   float a0 = 0.f, a1 = 0.f;
-  for (int j = 0; j < S; ++j) {
-    const float* vp = cb + (size_t)((first + j) % cap) * 2 * H * 64 + H * 64 + h * 64;
-    const float p = sc[j];
-    a0 = fmaf(p, vp[lane], a0);
-    a1 = fmaf(p, vp[lane + 32], a1);
+  for (int j0 = 0; j0 < S; j0 += 8) {  // eight independent loads in flight (the keys are L2-resident, not L1)
+    float v0[8], v1[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = min(j0 + u, S - 1);
+      const float* vp = cb + (size_t)((first + j) % cap) * 2 * H * 64 + H * 64 + h * 64;
+      v0[u] = vp[lane];
+      v1[u] = vp[lane + 32];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (j0 + u < S) {
+        const float p = sc[j0 + u];
+        a0 = fmaf(p, v0[u], a0);
+        a1 = fmaf(p, v1[u], a1);
+      }
   }
   const float inv = 1.f / sum;
   float* o = out + (size_t)bt * H * 64 + h * 64;
@@ -442,6 +470,7 @@ int csmb_layernorm(const float* x, long long x_batch, const float* w, const floa
   CSMB_ENTER(device);
   const int R = B * T;
   if (R == 0) return CSMB_OK;
+  CSMB_REQUIRE(d % 128 == 0 && d <= 1024 && x_batch % 4 == 0);
   k_layernorm<<<cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(x, x_batch, w, b, y, R, T, d, eps);
   CSMB_LAUNCH_CHECK();
   return CSMB_OK;

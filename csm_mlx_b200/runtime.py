@@ -207,7 +207,7 @@ class LMState:
     def decode_frame_fused(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
         """One whole frame in the persistent kernel (csmb_frame_b1).  Returns a fresh (1, n_codebooks) tensor."""
         if getattr(self, "_fws", None) is None:
-            nbytes = _lib.lib().csmb_frame_workspace_bytes(C.byref(self.model.desc()))
+            nbytes = _lib.lib().csmb_frame_workspace_bytes(C.byref(self.model.desc()), self.dev_idx)
             self._fws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)
             self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)
         self._check_room()

@@ -189,12 +189,13 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
  * csmb_decode_frame does for a single sequence — generate_frame with T=1 (generation.py:21-92) plus the input
  * construction of :156-161 — with a producer warp per CTA streaming every weight matrix exactly once through a
  * shared-memory ring; the ~640 dependent GEMV phases synchronise through tagged activation words, not barriers.
- * workspace must be zero-initialised once (csmb_frame_workspace_bytes) and belongs to one sequence.
+ * workspace must be zero-initialised once (csmb_frame_workspace_bytes; ~40 MB on B200: one private decoder-KV
+ * copy per SM) and belongs to one sequence.
  * block_table: this sequence's row of the paged-KV table; pos: DEVICE int, position of this frame's backbone row.
  * Fused samplers: greedy, or temperature without top-k/top-p/min-p; anything else (and model shapes other than
  * csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
  * code if an internal wait timed out (all waits are bounded). */
-size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/);
+size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/, int device);
 /* debug: device buffer [n_sms][16] u64 that later csmb_frame_b1 launches fill with per-CTA phase timers (ns); null = off */
 void csmb_debug_set_frame_prof(unsigned long long* device_buf);
 /* debug: bit 0 = skip the GEMV arithmetic of csmb_frame_b1 (timing experiments only; results are wrong) */
