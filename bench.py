@@ -135,6 +135,80 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- other configs
+def other_configs(model, mimi, dev):
+    """Informational, single GPU, short runs: BASELINE.json configs[2] (context), [3] (batch 64), [4] (codec)."""
+    from csm_mlx_b200 import Segment, generation, tokenizers
+    from csm_mlx_b200.runtime import LMState, SamplerSpec
+    from tests.workloads import prompt_ids, synthetic_audio
+
+    out = {}
+    spec = SamplerSpec(temperature=0.0)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n=1):
+        torch.cuda.synchronize(dev)
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(n):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n, r
+
+    # configs[3]: 64 independent utterances in lock-step on one GPU (request batching; tcgen05 linears)
+    B = 64
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+    st = LMState(model, B, max_len=64)
+    t_pre, _ = timed(lambda: st.prefill([p[0] for p in prompts], [p[1] for p in prompts]))
+    frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+    st.sample_c0(frame, spec)
+    st.depth_decode(frame, spec)
+    state = {"f": frame}
+    for _ in range(3):
+        state["f"] = st.decode_frame_graphed(state["f"], spec)
+
+    def step():
+        state["f"] = st.decode_frame_graphed(state["f"], spec)
+    t_step, _ = timed(step, 10)
+    out["batch64_one_gpu"] = {"audio_s_per_s": B * FRAME_S / (t_step / 1e3), "ms_per_frame_step": t_step, "prefill_ms": t_pre,
+                              "roofline_frac": lm_algorithmic_bytes(12, 20) / (t_step / 1e3) / 1e9 / 6557.8,
+                              "note": "LM frames only (CUDA graph of per-op kernels, tcgen05 linears); 64 frames per step"}
+    del st
+    # configs[2]: 2-segment context (2 x 5 s synthetic audio -> Mimi encode) + new text -> 164-row prefill -> frames
+    tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+    try:
+        clips = [synthetic_audio(11, 5.0), synthetic_audio(12, 5.0)]
+        t_enc, _ = timed(lambda: [mimi.encode(c[None, None].to(dev)) for c in clips])
+        segs = [Segment(i, "context sentence number %d" % i, clips[i]) for i in range(2)]
+        prompt = generation._build_prompt(model, "and now the answer", 0, segs)
+        st = LMState(model, 1, max_len=int(prompt[0].shape[0]) + 40)
+        t_pre, _ = timed(lambda: st.prefill([prompt[0]], [prompt[1]]))
+        frame = torch.zeros((1, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(frame, spec)
+        st.depth_decode(frame, spec)
+        state = {"f": frame}
+
+        def step1():
+            state["f"] = st.decode_frame_fused(state["f"], spec)
+        for _ in range(3):
+            step1()
+        t_f, _ = timed(step1, 20)
+        st.check_status()
+        out["context_2x5s"] = {"prompt_rows": int(prompt[0].shape[0]), "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
+                               "ms_per_frame": t_f, "note": "frame kernel with 2-chunk attention (S > 128)"}
+    finally:
+        tokenizers.set_text_tokenizer(None)
+    # configs[4] scaled down: 4 clips x 60 s through the codec (encode -> codes -> decode)
+    clips = torch.stack([synthetic_audio(100 + i, 60.0) for i in range(4)])[:, None].to(dev)
+    mimi.encode(clips[:1, :, :48000])
+    t_e, codes = timed(lambda: mimi.encode(clips))
+    t_d, audio = timed(lambda: mimi.decode(codes))
+    out["mimi_codec_4x60s"] = {"encode_audio_s_per_s": 240.0 / (t_e / 1e3), "decode_audio_s_per_s": 240.0 / (t_d / 1e3),
+                               "frames": int(codes.shape[2]), "note": "fp32 CUDA-core strided-row GEMMs, one GPU"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
@@ -298,6 +372,10 @@ def run_ours(args):
                "sample": f"prefill(10 rows) + {nfr} greedy frames + Mimi streaming decode, oracle PyTorch-CPU fp32 "
                          f"({tc:.2f} s)"}
 
+    other = None
+    if world == 1 and not args.no_extras:
+        other = other_configs(model, mimi, dev)
+
     lats_ms = sorted(1e3 * x for x in lats)
     pct = lambda p: lats_ms[min(len(lats_ms) - 1, int(p * len(lats_ms)))] if lats_ms else None
     d2h = frames * (1920 * 4 + ncb * 4)
@@ -325,6 +403,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_frame": alg, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
         "cpu_baseline": cpu,
         "tokens_checksum": int(sum(int(t.long().sum()) for t in all_tokens)) if all_tokens else None,
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -339,6 +418,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational measurements of the other BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;  // row tiles on x: 60 s x batch at 24 kHz exceeds gridDim.y
   const int M = g.B * g.T;
   // loader mapping: thread -> (row lr, k-quad lk)
   const int lr = tid >> 2, lk = (tid & 3) * 4;
@@ -446,7 +446,7 @@ int csmb_gemm_f32(const float* A, long long a_batch, int lda, const float* W, fl
   if (T == 0) return CSMB_OK;
   GemmArgs g{A, a_batch, lda, W, Y, y_batch, ldy, bias, scale, residual, r_batch, ldr, T, N, K, B, act_in, act_out};
   const long long M = (long long)B * T;
-  dim3 grid(cdiv(N, 64), (unsigned)((M + 63) / 64));
+  dim3 grid((unsigned)((M + 63) / 64), cdiv(N, 64));
   const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (a_batch % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (vec && M <= 32) {

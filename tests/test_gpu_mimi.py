@@ -86,3 +86,17 @@ def test_encode_batch_and_roundtrip_consistency(mimi_gpu, mimi_weights, device):
     assert (got == ref).float().mean() > 0.995
     # decode(encode(x)) on the GPU equals the oracle's decode of the same codes
     assert snr_db(omimi.decode(got, mimi_weights), mimi_gpu.decode(got.to(device)).cpu()) > 80
+
+
+def test_long_batch_codec_roundtrip_shapes(mimi_gpu, device):
+    """configs[4] in miniature: 2 clips x 60 s (1.44 M samples each: more row tiles than gridDim.y allows) encode and
+    decode; self-consistency: decoding the codes of the first 2 s equals decoding the same frames alone (causal codec)."""
+    clips = torch.stack([synthetic_audio(100 + i, 60.0) for i in range(2)])[:, None].to(device)
+    codes = mimi_gpu.encode(clips)
+    assert codes.shape == (2, 32, 750)
+    short = mimi_gpu.encode(clips[:, :, : 48000])
+    assert (codes[:, :, :25] == short).float().mean() > 0.995  # causal encoder: a prefix encodes to the same codes
+    audio = mimi_gpu.decode(codes)
+    assert audio.shape == (2, 1, 750 * 1920)
+    head = mimi_gpu.decode(codes[:, :, :25].contiguous())
+    assert snr_db(head.cpu(), audio[:, :, : 25 * 1920].cpu()) > 80
