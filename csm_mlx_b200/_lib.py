@@ -82,6 +82,7 @@ _SIGS = {
     "csmb_frame_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I]),
     "csmb_debug_set_frame_prof": (None, [_P]),
     "csmb_debug_set_frame_flags": (None, [_I]),
+    "csmb_debug_set_frame_prefetch": (None, [_I, _I]),
     "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P,
                                 C.c_size_t, _P, _I, _P]),
     "csmb_gemm_f32": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

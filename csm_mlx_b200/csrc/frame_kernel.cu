@@ -64,6 +64,7 @@ struct FrameParams {
   unsigned* nonce;             // launch counter in the workspace: read by every CTA at start, bumped by CTA 0 at the
                                // end, so consecutive launches (also CUDA-graph replays) never share tags
   int* abort_flag;
+  int pf_max, pf_interval;     // producer: L2 prefetch distance (16 KiB stages, 0 = off) and pacing (SM cycles)
   int dbg;                     // debug switches (0 in production): 1 = skip GEMV math, 8 = no weight streaming
   unsigned long long* prof;    // optional [gridDim][16] phase timers in SM cycles (debug); null in production
   // sampling
@@ -876,24 +877,89 @@ __device__ bool sched_range(const FrameParams& p, int idx, int cta, int G, Range
   return true;
 }
 
-// Producer (one thread per CTA): copies the schedule, stage by stage, into the ring as slots free up.
+struct Cursor {
+  int idx, stage, nst;
+  Range r;
+  bool valid;
+};
+__device__ __forceinline__ void cursor_load(const FrameParams& p, Cursor& k, int cta, int G) {
+  k.valid = sched_range(p, k.idx, cta, G, k.r);
+  k.stage = 0;
+  k.nst = k.valid ? n_stages(k.r) : 0;
+}
+__device__ __forceinline__ void cursor_chunk(const Cursor& k, const char*& src, uint32_t& bytes) {
+  const size_t total = (size_t)k.r.rows * k.r.K * 2, off = (size_t)k.stage * STAGE_BYTES;
+  src = reinterpret_cast<const char*>(k.r.p) + off;
+  bytes = (uint32_t)((total - off) < (size_t)STAGE_BYTES ? (total - off) : (size_t)STAGE_BYTES);
+}
+__device__ __forceinline__ void cursor_advance(const FrameParams& p, Cursor& k, int cta, int G) {
+  if (++k.stage >= k.nst) {
+    k.idx++;
+    cursor_load(p, k, cta, G);
+  }
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Producer (one thread per CTA).  The RING cursor copies the schedule, stage by stage, into shared memory as slots
+// free up.  While the ring is full (the consumers are in a latency phase) a second PREFETCH cursor runs ahead of it and
+// pulls future stages HBM -> L2 (cp.async.bulk.prefetch.L2), one stage per pf_interval cycles (this SM's fair share
+// of the HBM rate) and at most pf_max stages ahead, so HBM keeps streaming through the latency phases and the ring
+// later refills from L2.  Every byte still leaves HBM once.  pf_max = 0 disables the prefetch cursor.
 __device__ void producer_main(Ctx& c) {
   const FrameParams& p = *c.p;
   if (p.dbg & 8) return;
-  Range r;
-  for (int idx = 0; sched_range(p, idx, c.cta, c.G, r) && !c.aborted; ++idx) {
-    const size_t bytes = (size_t)r.rows * r.K * 2;
-    const char* src = reinterpret_cast<const char*>(r.p);
-    for (size_t off = 0; off < bytes; off += STAGE_BYTES, ++c.q) {
-      const int slot = c.q % NSTAGES;
-      const uint32_t par = (c.q / NSTAGES) & 1;
-      mbar_wait(c, &c.ring.empty[slot], par ^ 1, 1);
-      if (c.aborted) continue;
-      const uint32_t n = (uint32_t)((bytes - off) < (size_t)STAGE_BYTES ? (bytes - off) : (size_t)STAGE_BYTES);
-      mbar_arrive_expect_tx(&c.ring.full[slot], n);
-      bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src + off, n, &c.ring.full[slot], c.policy);
+  Cursor rc, pc;
+  rc.idx = 0;
+  cursor_load(p, rc, c.cta, c.G);
+  pc = rc;
+  uint32_t pq = 0;  // global stage number of the prefetch cursor (>= c.q)
+  const int pf_max = p.pf_max, pf_interval = p.pf_interval;
+  long long last_pf = clock64();
+  unsigned n_pf = 0;
+  while (rc.valid && !c.aborted) {
+    const int slot = c.q % NSTAGES;
+    const uint32_t par = (c.q / NSTAGES) & 1;
+    unsigned idle = 0;
+    while (!mbar_test(&c.ring.empty[slot], par ^ 1)) {
+      if (pf_max > 0 && pc.valid && pq < c.q + (uint32_t)pf_max && clock64() - last_pf >= pf_interval) {
+        if (pq >= c.q + NSTAGES) {  // stages inside the ring's own reach are fetched by the ring copies anyway
+          const char* src;
+          uint32_t n;
+          cursor_chunk(pc, src, n);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
+          last_pf = clock64();
+          ++n_pf;
+        }
+        cursor_advance(p, pc, c.cta, c.G);
+        ++pq;
+      } else {
+        if (++idle > SPIN_LIMIT * 8u) raise_abort(c, 1);
+        if ((idle & 4095) == 0 && check_abort(c)) break;
+      }
+      if (c.aborted) break;
+    }
+    if (c.aborted) break;
+    const char* src;
+    uint32_t n;
+    cursor_chunk(rc, src, n);
+    mbar_arrive_expect_tx(&c.ring.full[slot], n);
+    bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src, n, &c.ring.full[slot], c.policy);
+    cursor_advance(p, rc, c.cta, c.G);
+    ++c.q;
+    if (pq < c.q) {  // keep the prefetch cursor at or ahead of the ring cursor
+      pc = rc;
+      pq = c.q;
     }
   }
+  if (p.prof != nullptr) p.prof[(size_t)c.cta * 16 + 14] = n_pf;
 }
 
 // one depth-decoder step with R rows (R = 2 for the first step: positions 0 and 1)
@@ -1144,12 +1210,14 @@ using namespace csmb;
 
 static unsigned long long* g_prof_ptr = nullptr;  // debug only: csmb_debug_set_frame_prof
 static int g_dbg_flags = 0;
+static int g_pf_max = 0, g_pf_interval = 700;
 
 extern "C" {
 
 /* debug: device buffer [n_sms][16] u64 receiving per-CTA phase timers (SM cycles) of later csmb_frame_b1 launches */
 void csmb_debug_set_frame_prof(unsigned long long* device_buf) { g_prof_ptr = device_buf; }
 void csmb_debug_set_frame_flags(int flags) { g_dbg_flags = flags & 0xff; }
+void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles) { g_pf_max = max_stages; g_pf_interval = interval_cycles; }
 
 static size_t frame_ws_words(const csmb_model* m) {
   const csmb_llama &B = m->backbone, &D = m->decoder;
@@ -1235,6 +1303,8 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   p.draw_base = draw_base;
   p.prof = g_prof_ptr;
   p.dbg = g_dbg_flags;
+  p.pf_max = g_pf_max;
+  p.pf_interval = g_pf_interval;
 
   static const size_t dyn_smem = (size_t)NSTAGES * STAGE_BYTES + KVS_BYTES;  // ring + decoder KV staging
   CSMB_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));

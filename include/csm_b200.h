@@ -200,6 +200,8 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/, int device);
 void csmb_debug_set_frame_prof(unsigned long long* device_buf);
 /* debug: bit 0 = skip the GEMV arithmetic of csmb_frame_b1 (timing experiments only; results are wrong) */
 void csmb_debug_set_frame_flags(int flags);
+/* tuning: L2 prefetch distance (16 KiB stages per SM, 0 = off) and pacing (SM cycles between prefetches) of csmb_frame_b1 */
+void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles);
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,

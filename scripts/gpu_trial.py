@@ -237,6 +237,11 @@ def _fused():
         _lib.lib().csmb_debug_set_frame_flags(fl)
         prof_run(f"dbg flags {fl}")
     _lib.lib().csmb_debug_set_frame_flags(0)
+    for (pm, pi) in ((16, 700), (24, 700), (32, 700), (24, 350), (24, 1400), (48, 500)):
+        _lib.lib().csmb_debug_set_frame_prefetch(pm, pi)
+        prof_run(f"prefetch {pm} stages / {pi} cyc")
+        print("   prefetches issued per CTA:", float(prof[:, 14].double().mean()))
+    _lib.lib().csmb_debug_set_frame_prefetch(0, 700)
     (toks2,) = generation.generate_tokens(model, [(ptok, pmask)], 25, temperature=0.0)
     print("generate_tokens (fused) equals golden:", bool((toks2.numpy() == g["tokens"]).all()))
 
