@@ -248,6 +248,7 @@ def run_ours(args):
 
     st = LMState(model, 1, max_len=tok.shape[0] + frames + 1)
     codec = mimi.new_decode_stream(1)
+    lane = generation._CodecLane(codec, dev)   # the product's own overlap of codec(t) with LM(t+1)
     fused = st.fused_supported(spec) and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"
     next_frame = (lambda fr: st.decode_frame_fused(fr, spec)) if fused else (lambda fr: st.decode_frame_graphed(fr, spec))
 
@@ -261,13 +262,19 @@ def run_ours(args):
         c0 = lib.csmb_debug_launch_count()
         e0.record()
         st.run_prefill(staged)
-        st.sample_c0(frame, spec)
-        st.depth_decode(frame, spec)
+        if fused:
+            frame = st.first_frame_fused(spec)
+        else:
+            st.sample_c0(frame, spec)
+            st.depth_decode(frame, spec)
         for f in range(frames):
-            tokens_dev[f].copy_(frame[0])
-            audio_dev[f].copy_(codec.step(frame.reshape(1, ncb, 1)).reshape(-1))
+            audio = lane.step(frame)
+            with torch.cuda.stream(lane.stream):
+                tokens_dev[f].copy_(frame[0])
+                audio_dev[f].copy_(audio.reshape(-1))
             if f + 1 < frames:
                 frame = next_frame(frame)
+        lane.join()
         e1.record()
         torch.cuda.synchronize(dev)
         launches["eager"] = lib.csmb_debug_launch_count() - c0

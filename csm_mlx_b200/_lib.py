@@ -83,8 +83,11 @@ _SIGS = {
     "csmb_debug_set_frame_prof": (None, [_P]),
     "csmb_debug_set_frame_flags": (None, [_I]),
     "csmb_debug_set_frame_prefetch": (None, [_I, _I]),
+    "csmb_set_frame_ctas": (None, [_I]),
     "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P,
                                 C.c_size_t, _P, _I, _P]),
+    "csmb_frame_b1_depth": (C.c_int, [C.POINTER(Model), _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P, C.c_size_t, _P,
+                                      _I, _P]),
     "csmb_gemm_f32": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_layernorm": (C.c_int, [_P, _LL, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
     "csmb_mimi_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

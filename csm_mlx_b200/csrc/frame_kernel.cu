@@ -35,7 +35,7 @@ constexpr int NTHREADS = (NCW + 1) * 32;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGES = 8;
 constexpr int UNIT = 1024;              // weights per (warp, stage) unit
-constexpr int MAXU = 128;               // max units per range per CTA (csm_1b: <= 112)
+constexpr int MAXU = 192;               // max units per range per CTA (csm_1b: 112 on 148 CTAs, 176 on 96)
 constexpr int MAX_SPLIT = 16;           // backbone attention chunks (128 keys each) per head
 constexpr int PSTRIDE = 72;             // words per attention partial: acc[64], m, l, pad (32 heads x 72 = 9 x 256)
 constexpr int KROW = 512;               // floats per decoder-KV position: K (2 x 128) then V (2 x 128)
@@ -52,6 +52,7 @@ struct FrameParams {
   const int32_t* pos_ptr;      // position of this frame's backbone row
   int32_t* frame_out;          // [ncb]
   float* h_last;               // [d_b] (plain; output only)
+  const float* h_in;           // depth-only launch: the backbone's normalised last hidden row (prefill output); else null
   float* dec_kv;               // [CTA][Ld][32 pos][KROW]: every CTA keeps its own copy of the frame's decoder KV
   // cross-CTA activations: tagged words {value bits, tag}
   uint2 *xa, *xb;              // backbone residual stream ping-pong [d_b]
@@ -917,7 +918,7 @@ __device__ void producer_main(Ctx& c) {
   const FrameParams& p = *c.p;
   if (p.dbg & 8) return;
   Cursor rc, pc;
-  rc.idx = 0;
+  rc.idx = p.h_in ? p.m.backbone.n_layers * 5 : 0;  // depth-only launches start at the c0 head
   cursor_load(p, rc, c.cta, c.G);
   pc = rc;
   uint32_t pq = 0;  // global stage number of the prefetch cursor (>= c.q)
@@ -1046,7 +1047,7 @@ __device__ void consumer_main(Ctx& c) {
   // ---- phase 0: input embedding x = sum_k audio_emb[prev[k] + k*V]   (generation.py:156-161 + models.py:82-92),
   // computed by CTA 0 and published as tagged words
   unsigned tag_x = cur_tag(c);
-  if (c.cta == 0) {
+  if (c.cta == 0 && p.h_in == nullptr) {
     for (int k = c.tid * 8; k < db; k += NCT * 8) {
       float acc[8];
 #pragma unroll
@@ -1070,7 +1071,7 @@ __device__ void consumer_main(Ctx& c) {
   const int nchunks = (S + 127) / 128;  // <= MAX_SPLIT for S <= 2048
   constexpr int NLB = 2048 / (NCT * 2);
   NormW nw = prefetch_norm<2>(c, B.norm_in[0]);
-  for (int l = 0; l < B.n_layers; ++l) {
+  for (int l = 0; l < (p.h_in ? 0 : B.n_layers); ++l) {
     gather_ll<NLB>(c, x, tag_x, c.sattn);
     mark(c, T_POLL);
     csync();
@@ -1111,10 +1112,17 @@ __device__ void consumer_main(Ctx& c) {
     c.phase++;
   }
   // ---- final norm -> h_last (decoder input row 0) ; codebook0 head ; sample c0
-  gather_ll<NLB>(c, x, tag_x, c.sattn);
-  mark(c, T_POLL);
-  csync();
-  norm_from_smem<1, 2>(c, c.sattn, nw, B.eps, x1r);
+  if (p.h_in) {  // depth-only launch (first frame after a prefill): the row is given, already normalised
+    for (int k = c.tid * 4; k < db; k += NCT * 4)
+      *reinterpret_cast<float4*>(c.sattn + k) = __ldg(reinterpret_cast<const float4*>(p.h_in + k));
+    csync();
+    slice_from_smem<1>(c, c.sattn, db, x1r);
+  } else {
+    gather_ll<NLB>(c, x, tag_x, c.sattn);
+    mark(c, T_POLL);
+    csync();
+    norm_from_smem<1, 2>(c, c.sattn, nw, B.eps, x1r);
+  }
   if (c.cta == 0 && c.warp < db / UNIT) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -1130,7 +1138,8 @@ __device__ void consumer_main(Ctx& c) {
   unsigned tag_lg = cur_tag(c);
   phase_linear<1>(c, p.m.c0_head, V, db, x1r, p.logits, V, nullptr, 0);
   c.phase++;
-  const unsigned long long draw0 = p.draw_base + (unsigned long long)pos * (unsigned)ncb;
+  // draws are indexed by the position of the row whose hidden state is sampled from (the last prompt row when depth-only)
+  const unsigned long long draw0 = p.draw_base + (unsigned long long)(p.h_in ? pos - 1 : pos) * (unsigned)ncb;
   int tok = sample_token(c, p.logits, V, tag_lg, draw0);
   if (c.cta == 0 && c.tid == 0) p.frame_out[0] = tok;
   // ---- depth decoder: step 1 has rows (h_last @ pos 0, embed(c0) @ pos 1)   (generation.py:56-90)
@@ -1211,6 +1220,7 @@ using namespace csmb;
 static unsigned long long* g_prof_ptr = nullptr;  // debug only: csmb_debug_set_frame_prof
 static int g_dbg_flags = 0;
 static int g_pf_max = 0, g_pf_interval = 700;
+static int g_frame_ctas = 0;  // 0 = automatic (see launch_frame)
 
 extern "C" {
 
@@ -1218,6 +1228,7 @@ extern "C" {
 void csmb_debug_set_frame_prof(unsigned long long* device_buf) { g_prof_ptr = device_buf; }
 void csmb_debug_set_frame_flags(int flags) { g_dbg_flags = flags & 0xff; }
 void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles) { g_pf_max = max_stages; g_pf_interval = interval_cycles; }
+void csmb_set_frame_ctas(int n) { g_frame_ctas = n > 0 ? n : 0; }
 
 static size_t frame_ws_words(const csmb_model* m) {
   const csmb_llama &B = m->backbone, &D = m->decoder;
@@ -1241,12 +1252,13 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
   return frame_ws_words(m) * sizeof(uint2) + (size_t)m->backbone.d_model * sizeof(float) + dec_kv + 256 + 16384;
 }
 
-int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
-                  const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
-                  uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
-                  void* stream) {
+static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
+                        const int32_t* prev_frame, const float* h_in, const int32_t* pos, int32_t* frame,
+                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
+                        int32_t* status, int device, void* stream) {
   CSMB_ENTER(device);
-  CSMB_REQUIRE(m && kv_pool && block_table && prev_frame && pos && frame && sampler && workspace);
+  CSMB_REQUIRE(m && pos && frame && sampler && workspace);
+  CSMB_REQUIRE(h_in || (kv_pool && block_table && prev_frame));
   const csmb_llama &B = m->backbone, &D = m->decoder;
   const bool shape_ok = B.d_model == 2048 && B.n_heads == 32 && B.n_kv_heads == 8 && B.head_dim == 64 &&
                         D.d_model == 1024 && D.n_heads == 8 && D.n_kv_heads == 2 && D.head_dim == 128 &&
@@ -1260,7 +1272,7 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 0;
   CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  CSMB_REQUIRE(sms <= 384);
+  CSMB_REQUIRE(sms >= 128 && sms <= 384);
 
   FrameParams p;
   p.m = *m;
@@ -1268,6 +1280,7 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   p.kv_layer_stride = kv_layer_stride;
   p.block_table = block_table;
   p.prev_frame = prev_frame;
+  p.h_in = h_in;
   p.pos_ptr = pos;
   p.frame_out = frame;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
@@ -1310,10 +1323,48 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
   CSMB_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   CSMB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(base), 0, 64, st));  // abort flag only; the nonce persists
   void* args[] = {&p};
-  CSMB_CUDA(cudaLaunchCooperativeKernel((void*)k_frame, dim3(sms), dim3(NTHREADS), args, dyn_smem, st));
+  // fewest CTAs for which every linear's per-CTA slice fits the partial-sum buffer (MAXU units) and its rows fit one
+  // finalising thread each (rows * 2 <= NCT)
+  auto fits = [&](int G) {
+    auto ok = [&](int N, int K) { const int rows = (N + G - 1) / G; return rows * (K / UNIT) <= MAXU && rows * 2 <= NCT; };
+    return ok((int)nqkv_b, B.d_model) && ok(B.d_model, B.n_heads * B.head_dim) && ok(B.d_ff, B.d_model) &&
+           ok(B.d_model, B.d_ff) && ok(m->audio_vocab, B.d_model) && ok(D.d_model, B.d_model) && ok((int)nqkv_d, D.d_model) &&
+           ok(D.d_model, D.n_heads * D.head_dim) && ok(D.d_ff, D.d_model) && ok(D.d_model, D.d_ff) && ok(m->audio_vocab, D.d_model);
+  };
+  // default grid: the largest CTA count <= SMs that divides every matrix's row count, so that all slices are equal and
+  // whole ring stages (csm_1b on 148 SMs: 128 CTAs, measured 3% faster than 148 uneven slices); the SMs left over
+  // run the codec's streaming step of the previous frame concurrently (second stream).
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  int grid = sms;
+  if (g_frame_ctas > 0) {
+    grid = g_frame_ctas < sms ? g_frame_ctas : sms;
+  } else {
+    const int g = gcd(gcd(gcd(B.d_model, B.d_ff), gcd(D.d_model, D.d_ff)), gcd((int)nqkv_b, (int)nqkv_d));
+    for (int c = sms; c >= (sms * 3) / 4; --c)
+      if (g % c == 0) { grid = c; break; }
+  }
+  while (grid < sms && !fits(grid)) ++grid;
+  CSMB_REQUIRE(fits(grid));
+  CSMB_CUDA(cudaLaunchCooperativeKernel((void*)k_frame, dim3(grid), dim3(NTHREADS), args, dyn_smem, st));
   count_launch();
   if (status) CSMB_CUDA(cudaMemcpyAsync(status, p.abort_flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return CSMB_OK;
+}
+
+int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
+                  const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
+                  uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
+                  void* stream) {
+  return launch_frame(m, kv_pool, kv_layer_stride, block_table, prev_frame, nullptr, pos, frame, sampler, draw_base,
+                      workspace, workspace_bytes, status, device, stream);
+}
+
+int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t* pos, int32_t* frame,
+                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
+                        int32_t* status, int device, void* stream) {
+  if (!h_last) return CSMB_ERR_INVALID;
+  return launch_frame(m, nullptr, 0, nullptr, nullptr, h_last, pos, frame, sampler, draw_base, workspace,
+                      workspace_bytes, status, device, stream);
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ struct Workspace {
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-constexpr int TC_MIN_ROWS = 16;  // from this many rows on, linears run on the tensor cores (gemm_tc.cu)
+constexpr int TC_MIN_ROWS = 9;   // from this many rows on, linears run on the tensor cores (gemm_tc.cu); <= 8: GEMV kernels
 
 struct Workspace;
 static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,

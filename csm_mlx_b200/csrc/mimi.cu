@@ -62,8 +62,10 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  // software pipeline: the global loads of tile k0+BK are in flight while tile k0 is multiplied out of shared memory
+  auto load_tile = [&](int k0, float4& av, float4& bv) {
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
     const int k = k0 + lk;
     if (VEC) {
       if (arow && k < g.K) av = *reinterpret_cast<const float4*>(arow + k);
@@ -85,10 +87,15 @@ __global__ void __launch_bounds__(256) k_gemm_f32(GemmArgs g) {
     if (g.act_in == 1) {
       av.x = elu1(av.x); av.y = elu1(av.y); av.z = elu1(av.z); av.w = elu1(av.w);
     }
+  };
+  float4 av, bv;
+  load_tile(0, av, bv);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
     __syncthreads();
     As[lk][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
     Bs[lk][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
     __syncthreads();
+    if (k0 + BK < g.K) load_tile(k0 + BK, av, bv);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

@@ -109,7 +109,7 @@ class _Session:
         self.model, self.spec, self.host_sampler, self.procs = model, spec, host_sampler, logits_processors
         B = len(prompts)
         longest = max(int(p[0].shape[0]) for p in prompts)
-        self.state = LMState(model, B, max_len=longest + max_audio_frames + 1)
+        self.state = LMState.acquire(model, B, max_len=longest + max_audio_frames + 1)
         self.prompts = prompts
         self.c0_history: Optional[list] = [] if logits_processors else None
         self.prev: Optional[torch.Tensor] = None
@@ -119,10 +119,14 @@ class _Session:
     def step(self) -> torch.Tensor:
         st, model = self.state, self.model
         frame = torch.zeros((self.B, model.n_audio_codebooks), device=model.device, dtype=torch.int32)
+        plain = self.host_sampler is None and not self.procs
         if self.prev is None:
             st.prefill([p[0] for p in self.prompts], [p[1] for p in self.prompts])
-            _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
-        elif self.host_sampler is None and not self.procs:
+            if plain and self.fused and st.fused_supported(self.spec):
+                frame = st.first_frame_fused(self.spec)
+            else:
+                _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
+        elif plain:
             if self.fused and st.fused_supported(self.spec):
                 frame = st.decode_frame_fused(self.prev, self.spec)
             else:
@@ -132,6 +136,13 @@ class _Session:
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
         self.prev = frame
         return frame
+
+    def close(self) -> None:
+        """Raises if the persistent kernel reported an abort; otherwise returns the state to the model's pool."""
+        st, self.state = self.state, None
+        if st is not None:
+            st.check_status()
+            st.release()
 
 
 def _build_prompt(model: CSM, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -178,6 +189,37 @@ class _HostMirror:
         return self.bufs[slot]
 
 
+class _CodecLane:
+    """The codec's streaming step (generation.py:251) on its own CUDA stream: frame t is decoded to audio while
+    the LM already computes frame t+1 on the caller's stream.  The frame kernel is launched on ``lm_ctas`` CTAs
+    (a few SMs fewer than the GPU has) so the codec's small kernels always have somewhere to run.
+    ``CSMB_DISABLE_OVERLAP=1`` keeps everything on the caller's stream."""
+
+    def __init__(self, codec, device: torch.device):
+        self.codec, self.device = codec, device
+        self.overlap = os.environ.get("CSMB_DISABLE_OVERLAP", "0") != "1"
+        self.main = torch.cuda.current_stream(device)
+        self.stream = torch.cuda.Stream(device) if self.overlap else self.main
+        self._ready = torch.cuda.Event()
+
+    def step(self, frame: torch.Tensor) -> torch.Tensor:
+        """frame (B, K) int32 produced on the caller's stream -> (B, 1, 1920) audio valid on ``self.stream``.
+        Enter ``torch.cuda.stream(lane.stream)`` for any follow-up work on the result."""
+        B, K = frame.shape
+        if not self.overlap:
+            return self.codec.step(frame.reshape(B, K, 1))
+        self._ready.record(self.main)
+        self.stream.wait_event(self._ready)
+        frame.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            return self.codec.step(frame.reshape(B, K, 1))
+
+    def join(self) -> None:
+        """Order the caller's stream after everything enqueued on the lane (before buffers are released)."""
+        if self.overlap:
+            self.main.wait_stream(self.stream)
+
+
 def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tensor]], max_audio_frames: int, *,
                     temperature: float = 0.8, sampler=None, logits_processors=None, seed: Optional[int] = None
                     ) -> List[torch.Tensor]:
@@ -214,7 +256,7 @@ def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tens
         pending = slot
     if pending is not None:
         drain(pending)
-    sess.state.check_status()
+    sess.close()
     return [torch.stack(f) if f else torch.zeros((0, ncb), dtype=torch.int32) for f in out]
 
 
@@ -272,22 +314,27 @@ def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, c
     spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
     sess = _Session(model, [prompt], max_audio_frames, spec, host_sampler, logits_processors)
     ncb = model.n_audio_codebooks
-    codec = get_audio_tokenizer(ncb).new_decode_stream(batch=1)
+    mimi = get_audio_tokenizer(ncb)
+    lane = _CodecLane(mimi.acquire_decode_stream(batch=1), model.device)
     mirror = _HostMirror([((1, ncb), torch.int32), ((1, 1, 1920), torch.float32)], model.device)
     pending: Optional[int] = None
-    for _ in range(max_audio_frames):
-        frame = sess.step()
-        audio = codec.step(frame.reshape(1, ncb, 1))
-        slot = mirror.push([frame, audio])
+    try:
+        for _ in range(max_audio_frames):
+            frame = sess.step()
+            audio = lane.step(frame)
+            with torch.cuda.stream(lane.stream):
+                slot = mirror.push([frame, audio])
+            if pending is not None:
+                host_frame, host_audio = mirror.wait(pending)
+                if not bool(host_frame.any()):
+                    return  # eos: the speculative frame just enqueued is discarded
+                yield host_audio.reshape(-1).clone()
+            pending = slot
         if pending is not None:
             host_frame, host_audio = mirror.wait(pending)
-            if not bool(host_frame.any()):
-                sess.state.check_status()
-                return  # eos: the speculative frame just enqueued is discarded
-            yield host_audio.reshape(-1).clone()
-        pending = slot
-    if pending is not None:
-        host_frame, host_audio = mirror.wait(pending)
-        if bool(host_frame.any()):
-            yield host_audio.reshape(-1).clone()
-    sess.state.check_status()
+            if bool(host_frame.any()):
+                yield host_audio.reshape(-1).clone()
+    finally:
+        lane.join()
+        mimi.release_decode_stream(lane.codec)
+        sess.close()

@@ -214,6 +214,21 @@ class Mimi:
         self._require()
         return MimiDecodeStream(self, batch, max_frames=frames_per_step, offline=False, use_graph=use_graph)
 
+    def acquire_decode_stream(self, batch: int = 1) -> "MimiDecodeStream":
+        """A start-of-stream decoder state from the pool (its captured CUDA graph is kept between utterances)."""
+        pool = self.__dict__.setdefault("_stream_pool", [])
+        for i, st in enumerate(pool):
+            if st.m is self and st.B == batch and st.F == 1:
+                pool.pop(i)
+                st.reset()
+                return st
+        return self.new_decode_stream(batch)
+
+    def release_decode_stream(self, st: "MimiDecodeStream") -> None:
+        pool = self.__dict__.setdefault("_stream_pool", [])
+        if len(pool) < 4 and all(x is not st for x in pool):
+            pool.append(st)
+
     def reset_state(self) -> None:
         """generation.py:224-225,258."""
         self._default_stream = None

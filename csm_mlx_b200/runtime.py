@@ -8,6 +8,7 @@ creates one ``LMState`` and drops it at the end.  All arithmetic happens in libc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -64,6 +65,26 @@ class LMState:
         self.h_last = torch.empty((batch, b.hidden_size), device=self.device, dtype=torch.float32)
         self.c0_logits = torch.empty((batch, model.n_audio_vocab), device=self.device, dtype=torch.float32)
         self._seq_iota = torch.arange(batch, device=self.device, dtype=torch.int32)
+
+    # ------------------------------------------------------------------ reuse across utterances
+    @classmethod
+    def acquire(cls, model: CSM, batch: int, max_len: int = MAX_SEQ_LEN) -> "LMState":
+        """A rewound state from the model's pool (KV pages, workspaces and captured graphs are kept between
+        utterances), or a new one whose reservation is rounded up to 256 positions so later requests fit."""
+        need = min(int(max_len), MAX_SEQ_LEN)
+        pool = model.__dict__.setdefault("_lm_pool", [])
+        for i, st in enumerate(pool):
+            if st.model is model and st.batch == batch and st.max_len >= need:
+                pool.pop(i)
+                st.reset()
+                return st
+        return cls(model, batch, min(MAX_SEQ_LEN, -(-need // 256) * 256))
+
+    def release(self) -> None:
+        """Hand the state back for the next utterance (the caller's stream must be ordered after its last use)."""
+        pool = self.model.__dict__.setdefault("_lm_pool", [])
+        if len(pool) < 4 and self.kv_pool.numel() * 4 <= (1 << 30) and all(st is not self for st in pool):
+            pool.append(self)
 
     # ------------------------------------------------------------------ plumbing
     def _ensure_workspace(self, rows: int) -> None:
@@ -204,12 +225,28 @@ class LMState:
                                                  or sampler.min_p > 0)
         return self.batch == 1 and shape and plain and 3 <= self.model.n_audio_codebooks <= 32
 
-    def decode_frame_fused(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
-        """One whole frame in the persistent kernel (csmb_frame_b1).  Returns a fresh (1, n_codebooks) tensor."""
+    def _frame_workspace(self) -> None:
         if getattr(self, "_fws", None) is None:
             nbytes = _lib.lib().csmb_frame_workspace_bytes(C.byref(self.model.desc()), self.dev_idx)
             self._fws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)
             self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)
+            if os.environ.get("CSMB_FRAME_CTAS"):
+                _lib.lib().csmb_set_frame_ctas(int(os.environ["CSMB_FRAME_CTAS"]))
+
+    def first_frame_fused(self, sampler: SamplerSpec) -> torch.Tensor:
+        """The frame that follows a prefill (codebook-0 head + sampling + depth loop on ``h_last``) in one launch of
+        the persistent kernel (csmb_frame_b1_depth).  Returns a fresh (1, n_codebooks) tensor."""
+        self._frame_workspace()
+        frame = torch.empty((1, self.model.n_audio_codebooks), device=self.device, dtype=torch.int32)
+        s = sampler.to_c()
+        _lib.check(_lib.lib().csmb_frame_b1_depth(
+            C.byref(self.model.desc()), self.h_last.data_ptr(), self.pos.data_ptr(), frame.data_ptr(), C.byref(s), 0,
+            self._fws.data_ptr(), self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
+        return frame
+
+    def decode_frame_fused(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
+        """One whole frame in the persistent kernel (csmb_frame_b1).  Returns a fresh (1, n_codebooks) tensor."""
+        self._frame_workspace()
         self._check_room()
         frame = torch.empty((1, self.model.n_audio_codebooks), device=self.device, dtype=torch.int32)
         s = sampler.to_c()

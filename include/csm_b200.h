@@ -202,10 +202,21 @@ void csmb_debug_set_frame_prof(unsigned long long* device_buf);
 void csmb_debug_set_frame_flags(int flags);
 /* tuning: L2 prefetch distance (16 KiB stages per SM, 0 = off) and pacing (SM cycles between prefetches) of csmb_frame_b1 */
 void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles);
+/* tuning: CTAs of later csmb_frame_b1 launches; 0 = automatic: the largest count <= SMs that splits every weight matrix
+   into equal row slices (128 for csm_1b on a 148-SM B200).  The SMs left over let the codec's streaming step of the
+   previous frame run beside the frame kernel on a second stream (generation.py:251 moved off the critical path). */
+void csmb_set_frame_ctas(int n);
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
                   void* stream);
+/* The same kernel without its backbone part, for the first frame after a prompt (generation.py:139-146 with the
+ * whole prompt as `tokens`): h_last = csmb_backbone_forward's normalised last hidden row [d_backbone] of this sequence,
+ * pos = DEVICE int holding the sequence length (the sampled row is pos-1, which also indexes the random draws exactly
+ * like csmb_sample + csmb_depth_decode do).  Codebook-0 head, sampling and the 31 depth steps run in one launch. */
+int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t* pos, int32_t* frame,
+                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
+                        int32_t* status, int device, void* stream);
 
 /* ---------------------------------------------------------------- Mimi codec ------------------- */
 /* moshi_mlx Mimi.encode / decode / decode_step (csm_mlx/tokenizers.py:14-21,70,150; generation.py:224-225,

@@ -271,3 +271,32 @@ def _batch():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         print(f"B={B} decode frame (graph): {ms:.2f} ms -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s, {9.1067e9 / ms / 1e6 / 6557.8:.3f} of HBM roofline")
+
+
+@section("setup")
+def _setup():
+    """Where does the first-chunk time of stream_generate go?"""
+    mimi = Mimi(32, device=dev).load_pytorch_weights(random_mimi_weights())
+    tokenizers.set_audio_tokenizer(mimi)
+    spec = SamplerSpec(temperature=0.0)
+
+    def tick(label, fn):
+        torch.cuda.synchronize(); t1 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+        print(f"  {label}: {1e3 * (time.perf_counter() - t1):.2f} ms", flush=True)
+        return r
+
+    for rep in range(3):
+        print("rep", rep)
+        sess = tick("session (LMState alloc)", lambda: generation._Session(model, [(ptok, pmask)], 125, spec, None, None))
+        codec = tick("codec stream alloc", lambda: mimi.new_decode_stream(1))
+        f0 = tick("first step (prefill + frame 0 per-op)", sess.step)
+        f1 = tick("second step (fused; workspace alloc)", sess.step)
+        f2 = tick("third step", sess.step)
+        tick("codec step 0 (eager warm)", lambda: codec.step(f0.reshape(1, 32, 1)))
+        tick("codec step 1 (capture + replay)", lambda: codec.step(f1.reshape(1, 32, 1)))
+        tick("codec step 2 (replay)", lambda: codec.step(f2.reshape(1, 32, 1)))
+    for rep in range(3):
+        t1 = time.perf_counter(); lat = []; last = t1
+        for ch in generation.stream_generate(model, ids, 0, [], max_audio_length_ms=2000, temperature=0.0):
+            now = time.perf_counter(); lat.append(1e3 * (now - last)); last = now
+        print("stream_generate chunk gaps ms:", [round(x, 2) for x in lat[:6]], "total", round(1e3 * (last - t1), 1))

@@ -90,3 +90,27 @@ def test_generate_batch(model_1b, mimi_gpu):
     assert len(audios) == 3 and all(a.shape == (3 * 1920,) for a in audios)
     single = generate(model_1b, texts[1], 1, [], max_audio_length_ms=240, temperature=0.0)
     assert snr_db(single, audios[1]) > 80
+
+
+def test_pooled_state_and_codec_reuse_is_deterministic(model_1b, mimi_gpu, monkeypatch):
+    """Back-to-back utterances reuse the pooled LM state / codec stream (KV pages, workspaces, captured graphs):
+    a different utterance in between must not leak into the next one, with and without the codec on its own stream."""
+    ids_a, ids_b = cfg1_prompt_ids(), [128000, 11, 22, 33, 44, 128001]
+    first = torch.cat(list(stream_generate(model_1b, ids_a, 0, [], max_audio_length_ms=800, temperature=0.0)))
+    other = torch.cat(list(stream_generate(model_1b, ids_b, 3, [], max_audio_length_ms=400, temperature=0.0)))
+    again = torch.cat(list(stream_generate(model_1b, ids_a, 0, [], max_audio_length_ms=800, temperature=0.0)))
+    assert first.shape == (10 * 1920,) and other.shape == (5 * 1920,)
+    assert torch.equal(first, again)
+    assert len(model_1b.__dict__.get("_lm_pool", [])) >= 1 and len(mimi_gpu.__dict__.get("_stream_pool", [])) >= 1
+    monkeypatch.setenv("CSMB_DISABLE_OVERLAP", "1")
+    serial = torch.cat(list(stream_generate(model_1b, ids_a, 0, [], max_audio_length_ms=800, temperature=0.0)))
+    assert torch.equal(first, serial)
+
+
+def test_abandoned_stream_releases_resources(model_1b, mimi_gpu):
+    """A consumer that stops iterating early (generator closed) still orders the codec stream and returns the state."""
+    gen = stream_generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=2000, temperature=0.0)
+    head = [next(gen) for _ in range(3)]
+    gen.close()
+    full = list(stream_generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=400, temperature=0.0))
+    assert all(torch.equal(a, b) for a, b in zip(head, full))
