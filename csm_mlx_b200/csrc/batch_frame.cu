@@ -1,0 +1,679 @@
+// Fused batched decode frame (sm_100a): what csmb_decode_frame computes for B sequences in lock-step — generate_frame
+// with T = 1 (csm_mlx/generation.py:21-92) plus the next-input construction (:156-161) — as a chain of ~1 250 kernels
+// per frame instead of ~3 700:
+//
+//   * every Linear is ONE tcgen05 launch (k_gemm_part): 128 weight rows x all token rows per CTA tile, fp32 TMEM
+//     accumulators, TMA-fed 128B-swizzled stages, split along K so that ~148 CTAs stream the matrix; it reads the
+//     activations as bf16 hi + lo planes (x = hi + lo to 2^-17) that its PRODUCER kernel already wrote, and leaves
+//     fp32 split-K partials [S][R][N];
+//   * everything between two Linears is ONE kernel that starts by summing those partials in fixed order:
+//       k_resid_norm_split    partial sum + residual add + RMSNorm + hi/lo split
+//       k_attn_decode_fused   partial sum + RoPE + paged KV append + GQA attention + hi/lo split
+//       k_swiglu_split        partial sum + SwiGLU + hi/lo split
+//       k_sample_embed        partial sum (logits) + sampling + next codebook embedding gather (+ hi/lo split)
+//       k_frame_embed_norm    previous frame -> summed audio embeddings + first RMSNorm + hi/lo split
+//   * all launches are chained with programmatic dependent launch: a GEMM CTA sets up its barriers / TMEM and already
+//     streams its first weight stages (weights do not depend on the previous kernel) while its producer kernel is
+//     still running; only the activation loads wait (griddepcontrol.wait).
+//
+// Arithmetic is that of the per-op path (fp32 accumulation, fixed summation orders): parity tests compare both with
+// the batch-1 kernels and the oracle token for token.
+#include <math.h>
+
+#include <utility>
+
+#include "tc.cuh"
+
+namespace csmb {
+
+constexpr int BF_MAX_STAGES = 6;
+constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
+
+static int g_bf_min_kblocks = 4;   // split-K: at least this many 64-wide K blocks per CTA
+static int g_bf_pdl = 1;           // programmatic dependent launch on/off (debug)
+static int g_bf_max_ctas = 148;
+
+// ---------------------------------------------------------------------------------------------- GEMM
+struct GpArgs {
+  float* part;  // [S][R][N] fp32 partials
+  int R, N, K, RN, nstages, S;
+  int* err;
+};
+
+// dynamic smem: [stage][ W 128x64 | Xhi RNx64 | Xlo RNx64 ] bf16, 1024-byte aligned tiles
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
+            const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[BF_MAX_STAGES], empty[BF_MAX_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TC_BM, r0 = blockIdx.y * a.RN;
+  const int RN = a.RN;
+  const uint32_t w_bytes = TC_BM * TC_BK * 2, x_bytes = (uint32_t)RN * TC_BK * 2;
+  const uint32_t x_off = w_bytes, stage_bytes = (w_bytes + 2 * x_bytes + 1023u) & ~1023u;
+  const int nk_total = a.K / TC_BK, NS = a.nstages;
+  const int kb0 = (int)(((long long)nk_total * blockIdx.z) / a.S), kb1 = (int)(((long long)nk_total * (blockIdx.z + 1)) / a.S);
+  const int nk = kb1 - kb0;
+  uint32_t ncols = 32;
+  while ((int)ncols < RN) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < BF_MAX_STAGES; ++i) {
+      tc_mbar_init(&full[i], 1);
+      tc_mbar_init(&empty[i], 1);
+    }
+    tc_mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      // weights do not depend on the previous kernel: fill the pipeline with them before waiting for it
+      const int pre = nk < NS ? nk : NS;
+      for (int kb = 0; kb < pre; ++kb) {
+        tc_mbar_expect_tx(&full[kb], w_bytes + 2 * x_bytes);
+        tma_load_2d(smem + (size_t)kb * stage_bytes, &map_w, (kb0 + kb) * TC_BK, n0, &full[kb]);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) {
+        unsigned char* st = smem + (size_t)kb * stage_bytes;
+        tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[kb]);
+        tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[kb]);
+      }
+      for (int kb = pre; kb < nk; ++kb) {
+        const int s = kb % NS;
+        const uint32_t par = (kb / NS) & 1;
+        if (!tc_mbar_wait(&empty[s], par ^ 1, a.err)) break;
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        tc_mbar_expect_tx(&full[s], w_bytes + 2 * x_bytes);
+        tma_load_2d(st, &map_w, (kb0 + kb) * TC_BK, n0, &full[s]);
+        tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[s]);
+        tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(RN);
+      bool ok = true;
+      for (int kb = 0; kb < nk && ok; ++kb) {
+        const int s = kb % NS;
+        const uint32_t par = (kb / NS) & 1;
+        ok = tc_mbar_wait(&full[s], par, a.err);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = s32(smem + (size_t)s * stage_bytes);
+        const uint64_t da = umma_desc(sa), dhi = umma_desc(sa + x_off), dlo = umma_desc(sa + x_off + x_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);
+          umma_f16(tmem_base, da + koff, dhi + koff, idesc, (kb | k) != 0);
+          umma_f16(tmem_base, da + koff, dlo + koff, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(&acc_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 -> TMEM lane quarters (warp % 4) =====
+    pdl_wait();  // `part` may still be read by the previous kernel of the stream
+    const int quarter = warp & 3;
+    const bool ok = tc_mbar_wait(&acc_full, 0, a.err);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int n = n0 + quarter * 32 + lane;
+    if (ok) {
+      float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
+      for (int c0 = 0; c0 < RN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        if (n < a.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int r = r0 + c0 + j;
+            if (c0 + j < RN && r < a.R) dst0[(size_t)r * a.N] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+static int bf_pick_split_k(int R, int N, int K, int min_kblocks, int max_ctas) {
+  const int tiles = cdiv(N, TC_BM) * (R <= 256 ? 1 : cdiv(R, 128));
+  const int nk = K / TC_BK;
+  int S = max_ctas / tiles;
+  const int cap = nk / (min_kblocks > 0 ? min_kblocks : 1);
+  S = S < cap ? S : cap;
+  return S < 1 ? 1 : S;
+}
+static int bf_pick_split(int R, int N, int K) { return bf_pick_split_k(R, N, K, g_bf_min_kblocks, g_bf_max_ctas); }
+// knob-independent bound used for sizing the partials buffer
+constexpr int BF_SIZING_MIN_KBLOCKS = 1, BF_SIZING_MAX_CTAS = 296;
+
+// ---------------------------------------------------------------------------------------------- fused element kernels
+struct PartIn {
+  const float* p;  // partials [S][R][ld]
+  int S;
+  size_t stride;   // R * ld
+  int ld;
+};
+__device__ __forceinline__ float part_sum1(const PartIn& pi, size_t off) {
+  float v = 0.f;
+  for (int z = 0; z < pi.S; ++z) v += pi.p[(size_t)z * pi.stride + off];
+  return v;
+}
+__device__ __forceinline__ float2 part_sum2(const PartIn& pi, size_t off) {
+  float2 v = make_float2(0.f, 0.f);
+  for (int z = 0; z < pi.S; ++z) {
+    const float2 t = *reinterpret_cast<const float2*>(pi.p + (size_t)z * pi.stride + off);
+    v.x += t.x;
+    v.y += t.y;
+  }
+  return v;
+}
+__device__ __forceinline__ float4 part_sum4(const PartIn& pi, size_t off) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < pi.S; ++z) {
+    const float4 t = *reinterpret_cast<const float4*>(pi.p + (size_t)z * pi.stride + off);
+    v.x += t.x;
+    v.y += t.y;
+    v.z += t.z;
+    v.w += t.w;
+  }
+  return v;
+}
+// sum over a 256-thread block, broadcast to every thread (red: 8 floats of shared memory)
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  __syncthreads();
+  return tot;
+}
+
+// x[b][:] = sum_k audio_emb[prev[b][k] + k*V][:]   (generation.py:156-161 + models.py:82-92 + generation.py:32-36),
+// then RMSNorm(w) -> hi/lo.  One block per sequence; d == 2048 (8 channels per thread).
+__global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restrict__ prev, const uint16_t* __restrict__ audio_emb,
+                                                          int ncb, int V, int d, float* __restrict__ x,
+                                                          const float* __restrict__ w, float eps,
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, c = threadIdx.x * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int s = 0; s < ncb; ++s) {
+    int t = prev[(size_t)b * ncb + s];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    const uint4 q = *reinterpret_cast<const uint4*>(audio_emb + ((size_t)t + (size_t)s * V) * d + c);
+    acc[0] += bf16lo(q.x); acc[1] += bf16hi(q.x); acc[2] += bf16lo(q.y); acc[3] += bf16hi(q.y);
+    acc[4] += bf16lo(q.z); acc[5] += bf16hi(q.z); acc[6] += bf16lo(q.w); acc[7] += bf16hi(q.w);
+  }
+  float4* xo = reinterpret_cast<float4*>(x + (size_t)b * d + c);
+  xo[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  xo[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ss += acc[e] * acc[e];
+  const float scale = rsqrtf(block_sum256(ss, red) / (float)d + eps);
+  const float4 g0 = *reinterpret_cast<const float4*>(w + c), g1 = *reinterpret_cast<const float4*>(w + c + 4);
+  store_split4(hi + (size_t)b * d + c, lo + (size_t)b * d + c, acc[0] * scale * g0.x, acc[1] * scale * g0.y,
+               acc[2] * scale * g0.z, acc[3] * scale * g0.w);
+  store_split4(hi + (size_t)b * d + c + 4, lo + (size_t)b * d + c + 4, acc[4] * scale * g1.x, acc[5] * scale * g1.y,
+               acc[6] * scale * g1.z, acc[7] * scale * g1.w);
+}
+
+// Row rin = blockIdx.x * row_mul + row_add of the residual stream:  mode 1: x = sum(part);  mode 2: x += sum(part);
+// mode 0: x unchanged.  Then y = RMSNorm(x) * w -> hi/lo row blockIdx.x (and fp32 y32 if given).  d = NV * 1024.
+template <int NV>
+__global__ void __launch_bounds__(256) k_resid_norm_split(float* __restrict__ x, int ldx, PartIn part, int mode,
+                                                          const float* __restrict__ w, float eps,
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                          float* __restrict__ y32, int row_mul, int row_add) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int d = NV * 1024;
+  const int rin = blockIdx.x * row_mul + row_add, rout = blockIdx.x;
+  float4 v[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = threadIdx.x * 4 + j * 1024;
+    float* xp = x + (size_t)rin * ldx + c;
+    float4 s;
+    if (mode == 0) {
+      s = *reinterpret_cast<const float4*>(xp);
+    } else {
+      s = part_sum4(part, (size_t)rin * part.ld + c);
+      if (mode == 2) {
+        const float4 o = *reinterpret_cast<const float4*>(xp);
+        s = make_float4(o.x + s.x, o.y + s.y, o.z + s.z, o.w + s.w);
+      }
+      *reinterpret_cast<float4*>(xp) = s;
+    }
+    v[j] = s;
+    ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+  }
+  const float scale = rsqrtf(block_sum256(ss, red) / (float)d + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = threadIdx.x * 4 + j * 1024;
+    const float4 g = *reinterpret_cast<const float4*>(w + c);
+    const float4 y = make_float4(v[j].x * scale * g.x, v[j].y * scale * g.y, v[j].z * scale * g.z, v[j].w * scale * g.w);
+    store_split4(hi + (size_t)rout * d + c, lo + (size_t)rout * d + c, y.x, y.y, y.z, y.w);
+    if (y32) *reinterpret_cast<float4*>(y32 + (size_t)rout * d + c) = y;
+  }
+}
+
+// One block per (sequence b, kv head): for each of the sequence's rps new rows (positions pos .. pos+rps-1) sum the qkv
+// partials, rotate q and k (attention.py:119-177), append k/v to the paged cache (:236-237) and attend over positions
+// 0..pos (attention.py:242-249); warp g = query head kvh*G + g.  Output rows [b*rps + i][H*HD] as hi/lo.
+template <int HD>
+__global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const float* __restrict__ rope, float* pool,
+                                                           const int32_t* __restrict__ block_table, int max_pages,
+                                                           const int32_t* __restrict__ pos_arr, int pos0, int rps, int H,
+                                                           int Hkv, uint16_t* __restrict__ out_hi,
+                                                           uint16_t* __restrict__ out_lo, int max_pos) {
+  extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
+  const int G = H / Hkv, h = kvh * G + warp;
+  constexpr int half = HD / 2;
+  float* sq = smem + (size_t)warp * (HD + max_pos);
+  float* sc = sq + HD;
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
+  const float scale = rsqrtf((float)HD);
+  for (int i = 0; i < rps; ++i) {
+    const int r = b * rps + i;
+    const int pos = (pos_arr ? pos_arr[b] : pos0) + i;
+    const size_t roff = (size_t)r * qkv.ld;
+    const float* rc = rope + (size_t)pos * half * 2;
+    {
+      const int lp = pos / CSMB_PAGE;
+      const int page = block_table ? block_table[(size_t)b * max_pages + lp] : b * max_pages + lp;
+      float* kdst = pool + (size_t)page * page_stride + head_off + (size_t)(pos % CSMB_PAGE) * HD;
+      float* vdst = kdst + (size_t)Hkv * CSMB_PAGE * HD;
+      for (int p = threadIdx.x; p < half; p += blockDim.x) {
+        const float2 k = part_sum2(qkv, roff + (size_t)(H + kvh) * HD + 2 * p);
+        const float2 cs = *reinterpret_cast<const float2*>(rc + 2 * p);
+        *reinterpret_cast<float2*>(kdst + 2 * p) = make_float2(k.x * cs.x - k.y * cs.y, k.y * cs.x + k.x * cs.y);
+      }
+      for (int c = threadIdx.x * 2; c < HD; c += blockDim.x * 2)
+        *reinterpret_cast<float2*>(vdst + c) = part_sum2(qkv, roff + (size_t)(H + Hkv + kvh) * HD + c);
+    }
+    for (int p = lane; p < half; p += 32) {
+      const float2 q = part_sum2(qkv, roff + (size_t)h * HD + 2 * p);
+      const float2 cs = *reinterpret_cast<const float2*>(rc + 2 * p);
+      sq[2 * p] = q.x * cs.x - q.y * cs.y;
+      sq[2 * p + 1] = q.y * cs.x + q.x * cs.y;
+    }
+    __syncthreads();  // this block's k/v rows are in the cache, sq is complete
+    const int S = pos + 1;
+    const int32_t* bt = block_table ? block_table + (size_t)b * max_pages : nullptr;
+    float m = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
+      const float* kp = pool + (size_t)page * page_stride + head_off + (size_t)(j % CSMB_PAGE) * HD;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+        dot = fmaf(kv.x, sq[c], dot);
+        dot = fmaf(kv.y, sq[c + 1], dot);
+        dot = fmaf(kv.z, sq[c + 2], dot);
+        dot = fmaf(kv.w, sq[c + 3], dot);
+      }
+      dot *= scale;
+      sc[j] = dot;
+      m = fmaxf(m, dot);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(sc[j] - m);
+      sc[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    constexpr int PER = HD / 32;
+    float acc[PER];
+#pragma unroll
+    for (int ii = 0; ii < PER; ++ii) acc[ii] = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
+      const float* vp = pool + (size_t)page * page_stride + (size_t)Hkv * CSMB_PAGE * HD + head_off + (size_t)(j % CSMB_PAGE) * HD;
+      const float p = sc[j];
+#pragma unroll
+      for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(p, vp[lane + 32 * ii], acc[ii]);
+    }
+    const size_t o = (size_t)r * H * HD + (size_t)h * HD;
+#pragma unroll
+    for (int ii = 0; ii < PER; ++ii) {
+      uint16_t hh, ll;
+      split_bf16(acc[ii] * inv, hh, ll);
+      out_hi[o + lane + 32 * ii] = hh;
+      out_lo[o + lane + 32 * ii] = ll;
+    }
+    __syncthreads();  // sq / sc are reused by the next row
+  }
+}
+
+// act[r][f] = silu(gate) * up from the fused gate|up partials (mlx_lm MLP) -> hi/lo [R][F]
+__global__ void __launch_bounds__(256) k_swiglu_split(PartIn gu, int F, size_t total4, uint16_t* __restrict__ hi,
+                                                      uint16_t* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const size_t i = i4 * 4, r = i / F, f = i % F;
+  const float4 g = part_sum4(gu, r * gu.ld + f), u = part_sum4(gu, r * gu.ld + F + f);
+  store_split4(hi + i, lo + i, (g.x / (1.f + expf(-g.x))) * u.x, (g.y / (1.f + expf(-g.y))) * u.y,
+               (g.z / (1.f + expf(-g.z))) * u.z, (g.w / (1.f + expf(-g.w))) * u.w);
+}
+
+struct BfSample {
+  float inv_temp;  // 0 => greedy
+  uint32_t seed_lo, seed_hi;
+  uint64_t draw_base;
+  uint32_t draw_pos_mul;
+};
+
+// One block per sequence: logits = sum of the head's partials; token = argmax / Gumbel-max (generation.py:51-54,
+// 81-84; same draw indexing as csmb_sample); frame[b][cb] = token; then the next depth step's input row
+// embed_audio(cb, token) (generation.py:86-89) as hi (the embedding is bf16: lo = 0) at row b*out_mul + out_mul-1,
+// and, for the first depth step (out_mul == 2), row 2b = h_last[b] (generation.py:56-64).
+__global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample a, const int32_t* __restrict__ row_pos,
+                                                      int cb, int32_t* __restrict__ frame, int ncb,
+                                                      const uint16_t* __restrict__ audio_emb, int d, int embed,
+                                                      const float* __restrict__ h_last, uint16_t* __restrict__ hi,
+                                                      uint16_t* __restrict__ lo, int out_mul) {
+  extern __shared__ float sl[];
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < V; i += 256) sl[i] = part_sum1(lg, (size_t)b * lg.ld + i);
+  __syncthreads();
+  int tok;
+  if (a.inv_temp == 0.f) {
+    tok = block_argmax(V, [&](int i) { return sl[i]; }, red_v, red_i);
+  } else {
+    const uint64_t draw = a.draw_base + (uint64_t)(row_pos ? row_pos[b] : 0) * a.draw_pos_mul;
+    const uint32_t dlo = (uint32_t)draw, dhi = (uint32_t)(draw >> 32);
+    tok = block_argmax(
+        V, [&](int i) { return sl[i] * a.inv_temp + gumbel_for(i, dlo, dhi, (uint32_t)b, a.seed_lo, a.seed_hi); }, red_v,
+        red_i);
+  }
+  if (threadIdx.x == 0) frame[(size_t)b * ncb + cb] = tok;
+  if (!embed) return;
+  const int t = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const uint16_t* src = audio_emb + ((size_t)t + (size_t)cb * V) * d;
+  const size_t re = (size_t)(b * out_mul + out_mul - 1) * d;
+  for (int c = threadIdx.x * 8; c < d; c += 256 * 8) {
+    *reinterpret_cast<uint4*>(hi + re + c) = *reinterpret_cast<const uint4*>(src + c);
+    *reinterpret_cast<uint4*>(lo + re + c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (h_last != nullptr && out_mul == 2) {
+    const size_t rh = (size_t)(b * 2) * d;
+    for (int c = threadIdx.x * 4; c < d; c += 256 * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(h_last + (size_t)b * d + c);
+      store_split4(hi + rh + c, lo + rh + c, v.x, v.y, v.z, v.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <typename... KArgs, typename... Args>
+static cudaError_t bf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_bf_pdl ? 1 : 0;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+struct FastWs {
+  int* err;
+  float *x, *dx, *h_last, *part;
+  uint16_t *hi, *lo;
+  size_t part_floats, bytes;
+};
+
+static size_t bf_part_floats(int R, int N, int K) {
+  return (size_t)bf_pick_split_k(R, N, K, BF_SIZING_MIN_KBLOCKS, BF_SIZING_MAX_CTAS) * R * N;
+}
+
+static FastWs bf_carve(const csmb_model& m, int B, void* base) {
+  const csmb_llama &b = m.backbone, &d = m.decoder;
+  const int qkv_b = (b.n_heads + 2 * b.n_kv_heads) * b.head_dim, qkv_d = (d.n_heads + 2 * d.n_kv_heads) * d.head_dim;
+  const size_t R2 = (size_t)2 * B;
+  size_t kmax = (size_t)(b.d_ff > d.d_ff ? b.d_ff : d.d_ff);
+  kmax = kmax > (size_t)b.d_model ? kmax : (size_t)b.d_model;
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return r;
+  };
+  FastWs w;
+  w.err = (int*)take(256);
+  w.x = (float*)take((size_t)B * b.d_model * 4);
+  w.dx = (float*)take(R2 * d.d_model * 4);
+  w.h_last = (float*)take((size_t)B * b.d_model * 4);
+  w.hi = (uint16_t*)take(R2 * kmax * 2);
+  w.lo = (uint16_t*)take(R2 * kmax * 2);
+  size_t pf = 0;
+  auto need = [&](int R, int N, int K) {
+    const size_t f = bf_part_floats(R, N, K);
+    pf = f > pf ? f : pf;
+  };
+  need(B, qkv_b, b.d_model); need(B, b.d_model, b.n_heads * b.head_dim); need(B, 2 * b.d_ff, b.d_model); need(B, b.d_model, b.d_ff);
+  need(B, m.audio_vocab, b.d_model); need(B, m.audio_vocab, d.d_model);
+  for (int R : {B, 2 * B}) {
+    need(R, d.d_model, b.d_model); need(R, qkv_d, d.d_model); need(R, d.d_model, d.n_heads * d.head_dim);
+    need(R, 2 * d.d_ff, d.d_model); need(R, d.d_model, d.d_ff);
+  }
+  w.part_floats = pf;  // sized for the most generous split the tuning knobs allow
+  w.part = (float*)take(w.part_floats * 4);
+  w.bytes = off;
+  return w;
+}
+
+static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st) {
+  CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  const int S = bf_pick_split(R, N, K);
+  CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
+  const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
+  CUtensorMap mw, mhi, mlo;
+  if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
+    return CSMB_ERR_UNSUPPORTED;
+  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
+  int nstages = (int)(BF_SMEM_BUDGET / stage);
+  nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
+  CSMB_REQUIRE(nstages >= 2);
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err};
+  const size_t smem = stage * nstages + 1024;
+  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+  dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
+  CSMB_CUDA(bf_launch(k_gemm_part, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  *out = PartIn{w.part, S, (size_t)R * N, N};
+  return CSMB_OK;
+}
+
+static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, const float* nw, float eps, float* y32, int rows,
+                   int row_mul, int row_add, cudaStream_t st) {
+  if (d == 1024)
+    CSMB_CUDA(bf_launch(k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+  else if (d == 2048)
+    CSMB_CUDA(bf_launch(k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+  else
+    return CSMB_ERR_UNSUPPORTED;
+  return CSMB_OK;
+}
+
+static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool, const int32_t* block_table, int max_pages,
+                   const int32_t* pos_arr, int pos0, int rps, int B, cudaStream_t st) {
+  const int G = L.n_heads / L.n_kv_heads, max_pos = max_pages * CSMB_PAGE;
+  const size_t smem = (size_t)G * (L.head_dim + max_pos) * sizeof(float);
+  CSMB_REQUIRE(smem <= 48 * 1024 && G >= 1 && G <= 8);
+  const dim3 grid(B * L.n_kv_heads), block(32 * G);
+  if (L.head_dim == 64)
+    CSMB_CUDA(bf_launch(k_attn_decode_fused<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                        rps, L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
+  else if (L.head_dim == 128)
+    CSMB_CUDA(bf_launch(k_attn_decode_fused<128>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                        rps, L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
+  else
+    return CSMB_ERR_UNSUPPORTED;
+  return CSMB_OK;
+}
+
+// one Llama stack over R = B*rps rows whose first normalised input is already in w.hi / w.lo.  `final_norm`, the
+// weight of the norm after the last layer, is applied to rows b*rps + rps-1 only (R -> B rows).
+static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool, size_t layer_stride,
+                     const int32_t* block_table, int max_pages, const int32_t* pos_arr, int pos0, int rps, int B,
+                     float* y32_final, cudaStream_t st) {
+  const int d = L.d_model, F = L.d_ff, R = B * rps;
+  const int nqkv = (L.n_heads + 2 * L.n_kv_heads) * L.head_dim;
+  int rc;
+  PartIn part;
+  for (int l = 0; l < L.n_layers; ++l) {
+    if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st))) return rc;
+    if ((rc = bf_attn(w, L, part, pool + (size_t)l * layer_stride, block_table, max_pages, pos_arr, pos0, rps, B, st))) return rc;
+    if ((rc = bf_gemm(w, L.wo[l], R, d, L.n_heads * L.head_dim, &part, st))) return rc;
+    if ((rc = bf_norm(w, x, d, part, 2, L.norm_post[l], L.eps, nullptr, R, 1, 0, st))) return rc;
+    if ((rc = bf_gemm(w, L.wgu[l], R, 2 * F, d, &part, st))) return rc;
+    {
+      const size_t total4 = (size_t)R * F / 4;
+      CSMB_CUDA(bf_launch(k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi, w.lo));
+    }
+    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st))) return rc;
+    if (l + 1 < L.n_layers) {
+      if ((rc = bf_norm(w, x, d, part, 2, L.norm_in[l + 1], L.eps, nullptr, R, 1, 0, st))) return rc;
+    } else {
+      if ((rc = bf_norm(w, x, d, part, 2, L.norm_final, L.eps, y32_final, B, rps, rps - 1, st))) return rc;
+    }
+  }
+  return CSMB_OK;
+}
+
+static bool bf_supported(const csmb_model& m, const csmb_sampler& s) {
+  const csmb_llama &b = m.backbone, &d = m.decoder;
+  auto llama_ok = [](const csmb_llama& L) {
+    return (L.d_model == 1024 || L.d_model == 2048) && (L.head_dim == 64 || L.head_dim == 128) && L.n_kv_heads > 0 &&
+           L.n_heads % L.n_kv_heads == 0 && L.n_heads / L.n_kv_heads <= 8 && L.d_ff % 64 == 0 && L.d_ff % 4 == 0 &&
+           L.n_heads * L.head_dim == L.d_model;
+  };
+  const bool filtered = s.temperature != 0.f && ((s.top_k > 0 && s.top_k < m.audio_vocab) || (s.top_p > 0.f && s.top_p < 1.f) || s.min_p > 0.f);
+  return llama_ok(b) && llama_ok(d) && b.d_model == 2048 && m.audio_vocab <= 8192 && m.n_codebooks >= 2 && !filtered &&
+         s.temperature >= 0.f;
+}
+
+}  // namespace csmb
+
+using namespace csmb;
+
+extern "C" {
+
+void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas) {
+  if (min_kblocks >= BF_SIZING_MIN_KBLOCKS) g_bf_min_kblocks = min_kblocks;
+  if (pdl >= 0) g_bf_pdl = pdl ? 1 : 0;
+  if (max_ctas > 0) g_bf_max_ctas = max_ctas < BF_SIZING_MAX_CTAS ? max_ctas : BF_SIZING_MAX_CTAS;
+}
+
+size_t csmb_decode_frame_fast_workspace_bytes(const csmb_model* m, int batch) {
+  if (!m || batch <= 0) return 0;
+  return bf_carve(*m, batch, nullptr).bytes;
+}
+
+int csmb_decode_frame_fast_supported(const csmb_model* m, const csmb_sampler* sampler) {
+  return (m && sampler && bf_supported(*m, *sampler)) ? 1 : 0;
+}
+
+int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* prev_frame, const int32_t* pos,
+                           int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
+                           size_t workspace_bytes, int device, void* stream) {
+  CSMB_ENTER(device);
+  CSMB_REQUIRE(m && bt && prev_frame && pos && frame && sampler && workspace && bt->batch > 0);
+  CSMB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  if (!bf_supported(*m, *sampler)) return CSMB_ERR_UNSUPPORTED;
+  const csmb_llama &Bk = m->backbone, &D = m->decoder;
+  const int B = bt->batch, db = Bk.d_model, dd = D.d_model, V = m->audio_vocab, ncb = m->n_codebooks;
+  FastWs w = bf_carve(*m, B, workspace);
+  CSMB_REQUIRE(workspace_bytes >= w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dec_pages = cdiv(ncb, CSMB_PAGE);
+  BfSample sa;
+  sa.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
+  sa.seed_lo = (uint32_t)sampler->seed;
+  sa.seed_hi = (uint32_t)(sampler->seed >> 32);
+  sa.draw_pos_mul = (uint32_t)ncb;
+  int rc;
+  PartIn part;
+  const size_t lg_smem = (size_t)V * sizeof(float);
+
+  // ---- backbone step (generation.py:34-42 with T = 1)
+  CSMB_CUDA(bf_launch(k_frame_embed_norm, dim3(B), dim3(256), 0, st, prev_frame, m->audio_emb, ncb, V, db, w.x, Bk.norm_in[0],
+                      Bk.eps, w.hi, w.lo));
+  if ((rc = bf_layers(w, Bk, w.x, bt->kv_pool, bt->kv_layer_stride, bt->block_table, bt->max_pages, pos, 0, 1, B, w.h_last, st)))
+    return rc;
+  if ((rc = bf_gemm(w, m->c0_head, B, V, db, &part, st))) return rc;
+  sa.draw_base = draw_base;
+  CSMB_CUDA(bf_launch(k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, 0, frame, ncb, m->audio_emb, db, 1,
+                      (const float*)w.h_last, w.hi, w.lo, 2));
+  // ---- depth decoder (generation.py:56-90)
+  for (int i = 1; i < ncb; ++i) {
+    const int rps = (i == 1) ? 2 : 1, R = B * rps;
+    if ((rc = bf_gemm(w, m->projection, R, dd, db, &part, st))) return rc;
+    if ((rc = bf_norm(w, w.dx, dd, part, 1, D.norm_in[0], D.eps, nullptr, R, 1, 0, st))) return rc;
+    if ((rc = bf_layers(w, D, w.dx, bt->dec_kv_pool, bt->dec_kv_layer_stride, nullptr, dec_pages, nullptr, i == 1 ? 0 : i, rps, B,
+                        nullptr, st)))
+      return rc;
+    if ((rc = bf_gemm(w, m->audio_head_t + (size_t)(i - 1) * V * dd, B, V, dd, &part, st))) return rc;
+    sa.draw_base = draw_base + (uint64_t)i;
+    CSMB_CUDA(bf_launch(k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, i, frame, ncb, m->audio_emb, db,
+                        i + 1 < ncb ? 1 : 0, (const float*)nullptr, w.hi, w.lo, 1));
+  }
+  return CSMB_OK;
+}
+
+}  // extern "C"

@@ -15,24 +15,13 @@
 // residual add, coalesced stores: for a fixed token row the 32 lanes of a warp write 32 consecutive features).
 // Reference ops replaced: every nn.Linear of the path at T > 1 / B > 8 (attention.py:216-218,253; mlx_lm MLP;
 // generation.py:42,75,79).
-#include <cuda.h>
-
-#include "ops.cuh"
+#include "tc.cuh"
 
 namespace csmb {
 
-constexpr int TC_BM = 128;      // weight rows per tile (UMMA M)
-constexpr int TC_BK = 64;       // K per stage = one 128-byte swizzle row of bf16
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
-constexpr unsigned TC_SPIN = 1u << 24;
 
 // ---- bf16 hi/lo split of the activations -----------------------------------------------------------------
-__device__ __forceinline__ uint16_t f32_to_bf16_rn(float f) {
-  uint32_t u = __float_as_uint(f);
-  u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even (inputs are finite)
-  return (uint16_t)(u >> 16);
-}
 __global__ void __launch_bounds__(256) k_split_bf16(const float* __restrict__ x, int ldx, uint16_t* __restrict__ hi,
                                                     uint16_t* __restrict__ lo, int K, size_t total) {
   const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -48,73 +37,6 @@ __global__ void __launch_bounds__(256) k_split_bf16(const float* __restrict__ x,
   }
   *reinterpret_cast<uint2*>(hi + i) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
   *reinterpret_cast<uint2*>(lo + i) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
-}
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tc_mbar_init(uint64_t* b, uint32_t n) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n));
-}
-__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool tc_mbar_try(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(s32(b)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: returns false on timeout (the kernel then drains without touching memory it does not own)
-__device__ __forceinline__ bool tc_mbar_wait(uint64_t* b, uint32_t parity, int* err) {
-  unsigned spins = 0;
-  while (!tc_mbar_try(b, parity)) {
-    if (++spins > TC_SPIN) {
-      atomicExch(err, 1);
-      return false;
-    }
-    if ((spins & 4095) == 0 && *reinterpret_cast<volatile int*>(err) != 0) return false;
-  }
-  return true;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          s32(dst)),
-      "l"(map), "r"(s32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);        // [0,14)  start address >> 4
-  d |= (uint64_t)1 << 16;                              // [16,30) leading byte offset >> 4 (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                    // [32,46) stride byte offset >> 4: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                              // [46,48) descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                              // [61,64) layout: SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-  uint32_t d = 0;
-  d |= 1u << 4;                      // c_format = F32
-  d |= 1u << 7;                      // a_format = BF16
-  d |= 1u << 10;                     // b_format = BF16
-  d |= (uint32_t)(n >> 3) << 17;     // n_dim
-  d |= (uint32_t)(TC_BM >> 4) << 24; // m_dim
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
-          tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
 
 struct TcArgs {
@@ -213,16 +135,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       for (int c0 = 0; c0 < RN; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-            "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(taddr, v);
         if (n < a.N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -285,7 +198,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 // bf16 [rows][K] row-major, box = box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
-static bool make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+bool tc_make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -320,7 +233,7 @@ int launch_linear_tc(const float* x, int ldx, const uint16_t* W, float* y, int l
   // token rows per tile: all of them if <= 256, else tiles of 128
   int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
   CUtensorMap mw, mhi, mlo;
-  if (!make_map(&mw, W, N, K, TC_BM) || !make_map(&mhi, hi, R, K, RN) || !make_map(&mlo, lo, R, K, RN)) return CSMB_ERR_UNSUPPORTED;
+  if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, hi, R, K, RN) || !tc_make_map(&mlo, lo, R, K, RN)) return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)((200 * 1024) / stage);
   nstages = nstages > TC_STAGES ? TC_STAGES : nstages;

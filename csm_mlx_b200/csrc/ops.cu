@@ -450,34 +450,6 @@ struct SampleArgs {
   uint32_t draw_pos_mul;
 };
 
-__device__ __forceinline__ float gumbel_for(int idx, uint32_t draw_lo, uint32_t draw_hi, uint32_t seq,
-                                            uint32_t k0, uint32_t k1) {
-  uint32_t c[4] = {(uint32_t)(idx >> 2), draw_lo, draw_hi, seq};
-  philox4x32_10(c, k0, k1);
-  const float u = u01(c[idx & 3]);
-  return -logf(-logf(u));
-}
-
-// block-wide argmax over score(i), 256 threads; result broadcast to every thread.
-template <typename F>
-__device__ int block_argmax(int V, F score, float* red_v, int* red_i) {
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += 256) argmax_combine(bv, bi, score(i), i);
-  warp_argmax(bv, bi);
-  if ((threadIdx.x & 31) == 0) {
-    red_v[threadIdx.x >> 5] = bv;
-    red_i[threadIdx.x >> 5] = bi;
-  }
-  __syncthreads();
-  bv = red_v[0];
-  bi = red_i[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) argmax_combine(bv, bi, red_v[w], red_i[w]);
-  __syncthreads();
-  return bi == 0x7fffffff ? 0 : bi;
-}
-
 __global__ void __launch_bounds__(256) k_sample(const float* __restrict__ logits, int ldl,
                                                 int32_t* __restrict__ out, int out_stride, int V, SampleArgs a,
                                                 const int32_t* __restrict__ row_pos,

@@ -183,14 +183,32 @@ class LMState:
             self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx, self._stream()))
         self._advance()
 
+    def fast_supported(self, sampler: SamplerSpec) -> bool:
+        """True if the fused kernel chain of csrc/batch_frame.cu covers this model and sampler (tensor-core linears
+        from 2 sequences up; ``CSMB_DISABLE_FAST=1`` or ``CSMB_FAST_MIN_BATCH`` override)."""
+        if os.environ.get("CSMB_DISABLE_FAST", "0") == "1":
+            return False
+        if self.batch < int(os.environ.get("CSMB_FAST_MIN_BATCH", "2")):
+            return False
+        s = sampler.to_c()
+        return bool(_lib.lib().csmb_decode_frame_fast_supported(C.byref(self.model.desc()), C.byref(s)))
+
     def decode_frame(self, prev_frame: torch.Tensor, frame: torch.Tensor, sampler: SamplerSpec) -> None:
         """Whole frame on device, no host round trip (generation.py:21-92 with T=1)."""
         self._check_room()
         bd = self._batch_desc()
         s = sampler.to_c()
-        _lib.check(_lib.lib().csmb_decode_frame(
-            C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
-            C.byref(s), 0, self.dev_idx, self._stream()))
+        if self.fast_supported(sampler):
+            if getattr(self, "_fast_ws", None) is None:
+                nbytes = _lib.lib().csmb_decode_frame_fast_workspace_bytes(C.byref(self.model.desc()), self.batch)
+                self._fast_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # sticky error flag inside
+            _lib.check(_lib.lib().csmb_decode_frame_fast(
+                C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
+                C.byref(s), 0, self._fast_ws.data_ptr(), self._fast_ws.numel(), self.dev_idx, self._stream()))
+        else:
+            _lib.check(_lib.lib().csmb_decode_frame(
+                C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
+                C.byref(s), 0, self.dev_idx, self._stream()))
         self._advance()
 
     def decode_frame_graphed(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
@@ -263,6 +281,9 @@ class LMState:
         st = getattr(self, "frame_status", None)
         if st is not None and int(st.item()) != 0:
             raise _lib.CsmbError(f"persistent frame kernel aborted (code {int(st.item())})")
+        fw = getattr(self, "_fast_ws", None)
+        if fw is not None and int(fw[:4].view(torch.int32).item()) != 0:
+            raise _lib.CsmbError("fused batched frame: a bounded wait of the tensor-core linear timed out")
 
     def reset(self) -> None:
         """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply

@@ -185,6 +185,25 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
                       const int32_t* pos, int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base,
                       int device, void* stream);
 
+/* Throughput path: the same frame as csmb_decode_frame for `batch` sequences in lock-step, as a fused kernel chain
+ * (csrc/batch_frame.cu): every nn.Linear of the frame (attention.py:216-218,253; mlx_lm MLP; generation.py:42,75,79)
+ * is one tcgen05/TMEM/TMA launch that reads bf16 hi+lo activation planes written by its producer kernel and leaves
+ * fp32 split-K partials; everything between two Linears (partial reduction + residual + RMSNorm, RoPE + KV append +
+ * attention, SwiGLU, sampling + next embedding: generation.py:51-56,81-89, attention.py:226-249) is one kernel.
+ * Launches are chained with programmatic dependent launch, so weight streaming continues across kernel boundaries.
+ * Same argument meaning as csmb_decode_frame (b->workspace is not used); workspace = csmb_decode_frame_fast_workspace_bytes
+ * bytes, 256-byte aligned, zeroed once by its owner (first int = sticky error flag of the bounded waits).
+ * Fused samplers: greedy, or temperature without top-k/top-p/min-p; otherwise (or for unsupported model shapes)
+ * returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  csmb_decode_frame_fast_supported returns 1/0 up front. */
+size_t csmb_decode_frame_fast_workspace_bytes(const csmb_model* m /*host*/, int batch);
+int csmb_decode_frame_fast_supported(const csmb_model* m /*host*/, const csmb_sampler* sampler /*host*/);
+int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
+                           int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
+                           size_t workspace_bytes, int device, void* stream);
+/* tuning: minimum 64-wide K blocks per split-K CTA (>= 1), programmatic dependent launch on/off (-1 = keep),
+   CTA budget per Linear (0 = keep) of later csmb_decode_frame_fast calls */
+void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas);
+
 /* Batch-1 latency path: ONE persistent cooperative kernel per frame (csrc/frame_kernel.cu) doing what
  * csmb_decode_frame does for a single sequence — generate_frame with T=1 (generation.py:21-92) plus the input
  * construction of :156-161 — with a producer warp per CTA streaming every weight matrix exactly once through a

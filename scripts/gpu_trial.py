@@ -273,6 +273,71 @@ def _batch():
         print(f"B={B} decode frame (graph): {ms:.2f} ms -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s, {9.1067e9 / ms / 1e6 / 6557.8:.3f} of HBM roofline")
 
 
+@section("fast")
+def _fast():
+    """Fused batched frame chain (csrc/batch_frame.cu) vs the per-op batched path: tokens and timing."""
+    from csm_mlx_b200 import _lib
+    from tests.workloads import prompt_ids
+    spec = SamplerSpec()
+    for B in (3, 16, 64):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        frames = {}
+        for mode in ("old", "fast"):
+            os.environ["CSMB_DISABLE_FAST"] = "1" if mode == "old" else "0"
+            st = LMState(model, B, max_len=64)
+            st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+            frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+            st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+            out = [frame.clone()]
+            prev = frame
+            for _ in range(3):
+                nxt = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+                st.decode_frame(prev, nxt, spec)
+                out.append(nxt.clone()); prev = nxt
+            torch.cuda.synchronize()
+            st.check_status()
+            frames[mode] = torch.stack(out).cpu()
+            for _ in range(3):
+                prev = st.decode_frame_graphed(prev, spec)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 10
+            e0.record()
+            for _ in range(n):
+                prev = st.decode_frame_graphed(prev, spec)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            print(f"B={B} {mode}: {ms:.2f} ms/frame-step -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s, "
+                  f"{9.1067e9 / ms / 1e6 / 6557.8:.3f} of HBM roofline", flush=True)
+            del st
+        same = torch.equal(frames["old"], frames["fast"])
+        nd = int((frames["old"] != frames["fast"]).sum())
+        print(f"B={B} tokens equal: {same} (differing entries: {nd} of {frames['old'].numel()})", flush=True)
+    os.environ["CSMB_DISABLE_FAST"] = "0"
+    # tuning knobs at B = 64 (graph replay timing)
+    B = 64
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+    for (mk, pdl, ctas) in ((4, 1, 148), (4, 0, 148), (2, 1, 148), (8, 1, 148), (4, 1, 296), (2, 1, 296), (1, 1, 148)):
+        _lib.lib().csmb_debug_set_fast_frame(mk, pdl, ctas)
+        st = LMState(model, B, max_len=64)
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+        prev = frame
+        for _ in range(3):
+            prev = st.decode_frame_graphed(prev, spec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            prev = st.decode_frame_graphed(prev, spec)
+        e1.record(); torch.cuda.synchronize()
+        st.check_status()
+        print(f"B=64 min_kblocks={mk} pdl={pdl} ctas={ctas}: {e0.elapsed_time(e1) / 10:.2f} ms/frame-step", flush=True)
+        del st
+    _lib.lib().csmb_debug_set_fast_frame(4, 1, 148)
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""

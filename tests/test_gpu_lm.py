@@ -197,3 +197,39 @@ def test_batch16_tensor_core_path_matches_single(model_1b):
     for i in (0, 7, 15):
         (single,) = generation.generate_tokens(model_1b, [prompts[i]], 3, temperature=0.0)
         assert torch.equal(single, batched[i]), i
+
+
+def test_batch64_fused_chain_matches_single(model_1b):
+    """BASELINE.json configs[3] shape: 64 utterances in lock-step through the fused kernel chain of
+    csrc/batch_frame.cu (tcgen05 linears on bf16 hi+lo planes, fused partial-sum kernels, programmatic dependent
+    launch); utterances must equal the ones generated alone by the batch-1 persistent kernel."""
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + (i % 9)), i % 4) for i in range(64)]
+    batched = generation.generate_tokens(model_1b, prompts, 4, temperature=0.0)
+    for i in (0, 31, 63):
+        (single,) = generation.generate_tokens(model_1b, [prompts[i]], 4, temperature=0.0)
+        assert torch.equal(single, batched[i]), i
+
+
+@pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.0), SamplerSpec(temperature=0.8, seed=5)])
+def test_fused_chain_equals_per_op_batched_path(model_1b, monkeypatch, spec):
+    """Same batch through csmb_decode_frame_fast and through the per-op csmb_decode_frame (CSMB_DISABLE_FAST=1):
+    identical tokens, greedy and with in-kernel Gumbel/Philox temperature sampling."""
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(60 + i, 6 + i), i % 2) for i in range(5)]
+    fast = generation.generate_tokens(model_1b, prompts, 4, sampler=spec)
+    monkeypatch.setenv("CSMB_DISABLE_FAST", "1")
+    slow = generation.generate_tokens(model_1b, prompts, 4, sampler=spec)
+    for a, b in zip(fast, slow):
+        assert torch.equal(a, b)
+
+
+def test_fused_chain_filtered_sampler_falls_back(model_1b):
+    """top-k is not fused: the batched path must route to the per-op frame (csmb_decode_frame) and still work."""
+    from csm_mlx_b200.runtime import LMState
+
+    st = LMState(model_1b, 3, max_len=32)
+    assert st.fast_supported(SamplerSpec(temperature=0.0))
+    assert st.fast_supported(SamplerSpec(temperature=0.7))
+    assert not st.fast_supported(SamplerSpec(temperature=0.7, top_k=50))
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(70 + i, 7), 0) for i in range(3)]
+    toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, top_k=50, seed=3))
+    assert all(t.shape == (2, 32) for t in toks)
