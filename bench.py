@@ -173,7 +173,7 @@ def other_configs(model, mimi, dev):
     t_step, _ = timed(step, 10)
     out["batch64_one_gpu"] = {"audio_s_per_s": B * FRAME_S / (t_step / 1e3), "ms_per_frame_step": t_step, "prefill_ms": t_pre,
                               "roofline_frac": lm_algorithmic_bytes(12, 20) / (t_step / 1e3) / 1e9 / 6557.8,
-                              "note": "LM frames only (CUDA graph of per-op kernels, tcgen05 linears); 64 frames per step"}
+                              "note": "LM frames only: CUDA graph of the fused kernel chain (csrc/batch_frame.cu: one tcgen05 launch per Linear, fused partial-sum kernels, programmatic dependent launch); 64 frames per step"}
     del st
     # configs[2]: 2-segment context (2 x 5 s synthetic audio -> Mimi encode) + new text -> 164-row prefill -> frames
     tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())

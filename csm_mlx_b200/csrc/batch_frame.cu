@@ -177,28 +177,52 @@ struct PartIn {
   size_t stride;   // R * ld
   int ld;
 };
+// Fixed-order sums over the S split-K partials.  Loads go out in independent batches of 8 through the read-only path
+// (one L2 round trip per batch instead of one per partial: these kernels are pure latency chains).
 __device__ __forceinline__ float part_sum1(const PartIn& pi, size_t off) {
   float v = 0.f;
-  for (int z = 0; z < pi.S; ++z) v += pi.p[(size_t)z * pi.stride + off];
+  for (int z0 = 0; z0 < pi.S; z0 += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = (z0 + u < pi.S) ? __ldg(pi.p + (size_t)(z0 + u) * pi.stride + off) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (z0 + u < pi.S) v += t[u];
+  }
   return v;
 }
 __device__ __forceinline__ float2 part_sum2(const PartIn& pi, size_t off) {
   float2 v = make_float2(0.f, 0.f);
-  for (int z = 0; z < pi.S; ++z) {
-    const float2 t = *reinterpret_cast<const float2*>(pi.p + (size_t)z * pi.stride + off);
-    v.x += t.x;
-    v.y += t.y;
+  for (int z0 = 0; z0 < pi.S; z0 += 8) {
+    float2 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = (z0 + u < pi.S) ? __ldg(reinterpret_cast<const float2*>(pi.p + (size_t)(z0 + u) * pi.stride + off)) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (z0 + u < pi.S) {
+        v.x += t[u].x;
+        v.y += t[u].y;
+      }
   }
   return v;
 }
 __device__ __forceinline__ float4 part_sum4(const PartIn& pi, size_t off) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < pi.S; ++z) {
-    const float4 t = *reinterpret_cast<const float4*>(pi.p + (size_t)z * pi.stride + off);
-    v.x += t.x;
-    v.y += t.y;
-    v.z += t.z;
-    v.w += t.w;
+  for (int z0 = 0; z0 < pi.S; z0 += 8) {
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = (z0 + u < pi.S) ? __ldg(reinterpret_cast<const float4*>(pi.p + (size_t)(z0 + u) * pi.stride + off))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (z0 + u < pi.S) {
+        v.x += t[u].x;
+        v.y += t[u].y;
+        v.z += t[u].z;
+        v.w += t[u].w;
+      }
   }
   return v;
 }
@@ -291,9 +315,10 @@ __global__ void __launch_bounds__(256) k_resid_norm_split(float* __restrict__ x,
   }
 }
 
-// One block per (sequence b, kv head): for each of the sequence's rps new rows (positions pos .. pos+rps-1) sum the qkv
-// partials, rotate q and k (attention.py:119-177), append k/v to the paged cache (:236-237) and attend over positions
-// 0..pos (attention.py:242-249); warp g = query head kvh*G + g.  Output rows [b*rps + i][H*HD] as hi/lo.
+// One block per (sequence b, kv head), warp g = query head kvh*G + g.  Stage 0 (all threads): sum the qkv partials of the
+// sequence's rps new rows (positions pos .. pos+rps-1) for this group's G query heads, its k head and its v head, rotate
+// q and k (attention.py:119-177), keep q in shared memory and append k/v to the paged cache (:236-237).  Then each
+// warp attends over positions 0..pos of its head (attention.py:242-249).  Output rows [b*rps + i][H*HD] as hi/lo.
 template <int HD>
 __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const float* __restrict__ rope, float* pool,
                                                            const int32_t* __restrict__ block_table, int max_pages,
@@ -307,37 +332,37 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
   const int b = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
   const int G = H / Hkv, h = kvh * G + warp;
   constexpr int half = HD / 2;
-  float* sq = smem + (size_t)warp * (HD + max_pos);
-  float* sc = sq + HD;
+  float* sq_all = smem;                                    // [rps][G][HD] rotated queries
+  float* sc = smem + (size_t)rps * G * HD + (size_t)warp * max_pos;  // this warp's scores
   const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
   const float scale = rsqrtf((float)HD);
-  for (int i = 0; i < rps; ++i) {
-    const int r = b * rps + i;
-    const int pos = (pos_arr ? pos_arr[b] : pos0) + i;
-    const size_t roff = (size_t)r * qkv.ld;
-    const float* rc = rope + (size_t)pos * half * 2;
-    {
-      const int lp = pos / CSMB_PAGE;
-      const int page = block_table ? block_table[(size_t)b * max_pages + lp] : b * max_pages + lp;
-      float* kdst = pool + (size_t)page * page_stride + head_off + (size_t)(pos % CSMB_PAGE) * HD;
-      float* vdst = kdst + (size_t)Hkv * CSMB_PAGE * HD;
-      for (int p = threadIdx.x; p < half; p += blockDim.x) {
-        const float2 k = part_sum2(qkv, roff + (size_t)(H + kvh) * HD + 2 * p);
-        const float2 cs = *reinterpret_cast<const float2*>(rc + 2 * p);
-        *reinterpret_cast<float2*>(kdst + 2 * p) = make_float2(k.x * cs.x - k.y * cs.y, k.y * cs.x + k.x * cs.y);
+  const int posb = pos_arr ? pos_arr[b] : pos0;
+  {
+    const int per_row = (G + 2) * half, total = rps * per_row;
+#pragma unroll 2
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int i = idx / per_row, rem = idx % per_row, slot = rem / half, pr = rem % half;
+      const int pos = posb + i;
+      const int col = (slot < G ? (kvh * G + slot) : (slot == G ? H + kvh : H + Hkv + kvh)) * HD + 2 * pr;
+      const float2 v = part_sum2(qkv, (size_t)(b * rps + i) * qkv.ld + col);
+      const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + ((size_t)pos * half + pr) * 2));
+      const float2 rot = make_float2(v.x * cs.x - v.y * cs.y, v.y * cs.x + v.x * cs.y);
+      if (slot < G) {
+        *reinterpret_cast<float2*>(sq_all + ((size_t)i * G + slot) * HD + 2 * pr) = rot;
+      } else {
+        const int lp = pos / CSMB_PAGE;
+        const int page = block_table ? block_table[(size_t)b * max_pages + lp] : b * max_pages + lp;
+        float* kdst = pool + (size_t)page * page_stride + head_off + (size_t)(pos % CSMB_PAGE) * HD;
+        if (slot == G) *reinterpret_cast<float2*>(kdst + 2 * pr) = rot;
+        else *reinterpret_cast<float2*>(kdst + (size_t)Hkv * CSMB_PAGE * HD + 2 * pr) = v;
       }
-      for (int c = threadIdx.x * 2; c < HD; c += blockDim.x * 2)
-        *reinterpret_cast<float2*>(vdst + c) = part_sum2(qkv, roff + (size_t)(H + Hkv + kvh) * HD + c);
     }
-    for (int p = lane; p < half; p += 32) {
-      const float2 q = part_sum2(qkv, roff + (size_t)h * HD + 2 * p);
-      const float2 cs = *reinterpret_cast<const float2*>(rc + 2 * p);
-      sq[2 * p] = q.x * cs.x - q.y * cs.y;
-      sq[2 * p + 1] = q.y * cs.x + q.x * cs.y;
-    }
-    __syncthreads();  // this block's k/v rows are in the cache, sq is complete
-    const int S = pos + 1;
-    const int32_t* bt = block_table ? block_table + (size_t)b * max_pages : nullptr;
+  }
+  __syncthreads();  // this block's k/v rows are in the cache, all queries are in shared memory
+  const int32_t* bt = block_table ? block_table + (size_t)b * max_pages : nullptr;
+  for (int i = 0; i < rps; ++i) {
+    const int r = b * rps + i, pos = posb + i, S = pos + 1;
+    const float* sq = sq_all + ((size_t)i * G + warp) * HD;
     float m = -INFINITY;
     for (int j = lane; j < S; j += 32) {
       const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
@@ -369,12 +394,24 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
     float acc[PER];
 #pragma unroll
     for (int ii = 0; ii < PER; ++ii) acc[ii] = 0.f;
-    for (int j = 0; j < S; ++j) {
-      const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
-      const float* vp = pool + (size_t)page * page_stride + (size_t)Hkv * CSMB_PAGE * HD + head_off + (size_t)(j % CSMB_PAGE) * HD;
-      const float p = sc[j];
+    // keys in groups of 8: the loads of a group are independent and in flight together; accumulation order is j
+    for (int j0 = 0; j0 < S; j0 += 8) {
+      float vv[8][PER];
 #pragma unroll
-      for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(p, vp[lane + 32 * ii], acc[ii]);
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u < S ? j0 + u : S - 1;
+        const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
+        const float* vp = pool + (size_t)page * page_stride + (size_t)Hkv * CSMB_PAGE * HD + head_off + (size_t)(j % CSMB_PAGE) * HD;
+#pragma unroll
+        for (int ii = 0; ii < PER; ++ii) vv[u][ii] = vp[lane + 32 * ii];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j0 + u < S) {
+          const float pj = sc[j0 + u];
+#pragma unroll
+          for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(pj, vv[u][ii], acc[ii]);
+        }
     }
     const size_t o = (size_t)r * H * HD + (size_t)h * HD;
 #pragma unroll
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
       out_hi[o + lane + 32 * ii] = hh;
       out_lo[o + lane + 32 * ii] = ll;
     }
-    __syncthreads();  // sq / sc are reused by the next row
+    __syncwarp();  // sc is reused by this warp's next row
   }
 }
 
@@ -553,7 +590,7 @@ static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, cons
 static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool, const int32_t* block_table, int max_pages,
                    const int32_t* pos_arr, int pos0, int rps, int B, cudaStream_t st) {
   const int G = L.n_heads / L.n_kv_heads, max_pos = max_pages * CSMB_PAGE;
-  const size_t smem = (size_t)G * (L.head_dim + max_pos) * sizeof(float);
+  const size_t smem = ((size_t)rps * G * L.head_dim + (size_t)G * max_pos) * sizeof(float);
   CSMB_REQUIRE(smem <= 48 * 1024 && G >= 1 && G <= 8);
   const dim3 grid(B * L.n_kv_heads), block(32 * G);
   if (L.head_dim == 64)

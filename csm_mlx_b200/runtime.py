@@ -193,12 +193,28 @@ class LMState:
         s = sampler.to_c()
         return bool(_lib.lib().csmb_decode_frame_fast_supported(C.byref(self.model.desc()), C.byref(s)))
 
+    def persist_supported(self, sampler: SamplerSpec) -> bool:
+        """True if the persistent batched frame kernel (csrc/batch_persist.cu) is requested (``CSMB_ENABLE_PERSIST=1``)
+        and covers this model, sampler and batch.  It is token-identical to the kernel chain but measured slower
+        (13.3 vs 9.2 ms per frame-step at 64 sequences, profiles/r01_batched_frame.md), so the chain is the default."""
+        if os.environ.get("CSMB_ENABLE_PERSIST", "0") != "1" or not self.fast_supported(sampler):
+            return False
+        s = sampler.to_c()
+        return bool(_lib.lib().csmb_frame_batch_supported(C.byref(self.model.desc()), C.byref(s), self.batch))
+
     def decode_frame(self, prev_frame: torch.Tensor, frame: torch.Tensor, sampler: SamplerSpec) -> None:
         """Whole frame on device, no host round trip (generation.py:21-92 with T=1)."""
         self._check_room()
         bd = self._batch_desc()
         s = sampler.to_c()
-        if self.fast_supported(sampler):
+        if self.persist_supported(sampler):
+            if getattr(self, "_persist_ws", None) is None:
+                nbytes = _lib.lib().csmb_frame_batch_workspace_bytes(C.byref(self.model.desc()), self.batch, self.dev_idx)
+                self._persist_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # barrier counters + error flag
+            _lib.check(_lib.lib().csmb_frame_batch(
+                C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
+                C.byref(s), 0, self._persist_ws.data_ptr(), self._persist_ws.numel(), self.dev_idx, self._stream()))
+        elif self.fast_supported(sampler):
             if getattr(self, "_fast_ws", None) is None:
                 nbytes = _lib.lib().csmb_decode_frame_fast_workspace_bytes(C.byref(self.model.desc()), self.batch)
                 self._fast_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # sticky error flag inside
@@ -214,7 +230,9 @@ class LMState:
     def decode_frame_graphed(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
         """decode_frame through a CUDA graph captured on first use (fixed buffers; positions live on the device
         and advance inside the graph).  Returns a fresh (B, n_codebooks) int32 tensor."""
-        key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep, sampler.seed)
+        path = "persist" if self.persist_supported(sampler) else ("chain" if self.fast_supported(sampler) else "per-op")
+        key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep, sampler.seed,
+               path)
         if getattr(self, "_graph_key", None) != key:
             ncb = self.model.n_audio_codebooks
             self._g_prev = torch.zeros((self.batch, ncb), device=self.device, dtype=torch.int32)
@@ -284,6 +302,9 @@ class LMState:
         fw = getattr(self, "_fast_ws", None)
         if fw is not None and int(fw[:4].view(torch.int32).item()) != 0:
             raise _lib.CsmbError("fused batched frame: a bounded wait of the tensor-core linear timed out")
+        pw = getattr(self, "_persist_ws", None)
+        if pw is not None and int(pw[256:260].view(torch.int32).item()) != 0:
+            raise _lib.CsmbError(f"persistent batched frame kernel aborted (code {int(pw[256:260].view(torch.int32).item())})")
 
     def reset(self) -> None:
         """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply

@@ -204,6 +204,25 @@ int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* b, const int32
    CTA budget per Linear (0 = keep) of later csmb_decode_frame_fast calls */
 void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas);
 
+/* Throughput path, persistent form (csrc/batch_persist.cu): the frame of csmb_decode_frame for `batch` sequences in ONE
+ * cooperative launch (one CTA per SM): the dataflow of csmb_decode_frame_fast with grid barriers instead of kernel
+ * boundaries, a persistent TMA ring whose producer streams the next Linear's weight tiles through the element-wise
+ * phases and barriers, one TMEM accumulator reused by every Linear, and all tensor maps in the kernel's parameter block.
+ * Replaces per frame: generation.py:21-92 (T = 1) + :156-161.  Same arguments and sampler restrictions as
+ * csmb_decode_frame_fast; batch <= 256.  workspace = csmb_frame_batch_workspace_bytes bytes, 256-byte aligned, zeroed
+ * once by its owner and then owned by this sequence group (it carries the barrier counters between launches; the int
+ * at byte offset 256 is the sticky error flag of the bounded waits). */
+size_t csmb_frame_batch_workspace_bytes(const csmb_model* m /*host*/, int batch, int device);
+int csmb_frame_batch_supported(const csmb_model* m /*host*/, const csmb_sampler* sampler /*host*/, int batch);
+int csmb_frame_batch(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
+                     int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
+                     size_t workspace_bytes, int device, void* stream);
+/* tuning: minimum 64-wide K blocks per split-K work item of later csmb_frame_batch launches */
+void csmb_debug_set_frame_batch(int min_kblocks);
+/* debug: device buffer [n_sms][2][12] u64 receiving the phase timers (SM cycles; threads 0 and 128 of every CTA; categories
+   gemm, prefetch, barrier, attention, norm, swiglu, sample, embed, accumulator wait, epilogue) of later csmb_frame_batch launches; null = off */
+void csmb_debug_set_frame_batch_prof(unsigned long long* device_buf);
+
 /* Batch-1 latency path: ONE persistent cooperative kernel per frame (csrc/frame_kernel.cu) doing what
  * csmb_decode_frame does for a single sequence — generate_frame with T=1 (generation.py:21-92) plus the input
  * construction of :156-161 — with a producer warp per CTA streaming every weight matrix exactly once through a

@@ -338,6 +338,100 @@ def _fast():
     _lib.lib().csmb_debug_set_fast_frame(4, 1, 148)
 
 
+@section("persist")
+def _persist():
+    """Persistent batched frame kernel (csrc/batch_persist.cu) vs the kernel chain: tokens and timing."""
+    from csm_mlx_b200 import _lib
+    from tests.workloads import prompt_ids
+    spec = SamplerSpec()
+    for B in (3, 16, 64):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        frames = {}
+        for mode in ("chain", "persist"):
+            os.environ["CSMB_ENABLE_PERSIST"] = "0" if mode == "chain" else "1"
+            st = LMState(model, B, max_len=64)
+            st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+            frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+            st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+            out = [frame.clone()]
+            prev = frame
+            try:
+                for _ in range(3):
+                    nxt = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+                    st.decode_frame(prev, nxt, spec)
+                    out.append(nxt.clone()); prev = nxt
+                torch.cuda.synchronize()
+                st.check_status()
+            except Exception as e:
+                print(f"B={B} {mode}: FAILED {e}", flush=True)
+                frames[mode] = None
+                continue
+            frames[mode] = torch.stack(out).cpu()
+            for _ in range(3):
+                prev = st.decode_frame_graphed(prev, spec)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 10
+            e0.record()
+            for _ in range(n):
+                prev = st.decode_frame_graphed(prev, spec)
+            e1.record(); torch.cuda.synchronize()
+            st.check_status()
+            ms = e0.elapsed_time(e1) / n
+            print(f"B={B} {mode}: {ms:.2f} ms/frame-step -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s, "
+                  f"{9.1067e9 / ms / 1e6 / 6557.8:.3f} of HBM roofline", flush=True)
+            del st
+        if frames["chain"] is not None and frames["persist"] is not None:
+            nd = int((frames["chain"] != frames["persist"]).sum())
+            print(f"B={B} tokens equal: {nd == 0} (differing entries: {nd} of {frames['chain'].numel()})", flush=True)
+            if nd:
+                d = (frames["chain"] != frames["persist"])
+                print("  first differing (frame, seq, cb):", d.nonzero()[:5].tolist(), flush=True)
+    os.environ["CSMB_ENABLE_PERSIST"] = "1"
+    B = 64
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+    # phase timers
+    prof = torch.zeros((148, 2, 12), device=dev, dtype=torch.int64)
+    st = LMState(model, B, max_len=64)
+    st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+    frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+    st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+    prev = frame
+    for _ in range(2):
+        nxt = torch.zeros((B, 32), device=dev, dtype=torch.int32); st.decode_frame(prev, nxt, spec); prev = nxt
+    _lib.lib().csmb_debug_set_frame_batch_prof(prof.data_ptr())
+    nxt = torch.zeros((B, 32), device=dev, dtype=torch.int32); st.decode_frame(prev, nxt, spec); prev = nxt
+    torch.cuda.synchronize()
+    _lib.lib().csmb_debug_set_frame_batch_prof(None)
+    names = ["gemm", "prefetch", "barrier", "attn", "norm", "swiglu", "sample", "embed", "accwait", "epi", "-", "-"]
+    pr = prof.cpu().double() / 1.965e3  # us at 1965 MHz
+    for th, label in ((0, "thread 0 (producer)"), (1, "thread 128 (epilogue warp)")):
+        print(f"  {label}: mean over CTAs [us/frame]: " + ", ".join(f"{n} {pr[:, th, i].mean():.0f}" for i, n in enumerate(names))
+              + f" | total {pr[:, th].sum(1).mean():.0f}", flush=True)
+        print(f"     CTA0: " + ", ".join(f"{n} {pr[0, th, i]:.0f}" for i, n in enumerate(names)), flush=True)
+        print(f"     CTA147: " + ", ".join(f"{n} {pr[147, th, i]:.0f}" for i, n in enumerate(names)), flush=True)
+    del st
+    for mk in (2, 4):
+        _lib.lib().csmb_debug_set_frame_batch(mk)
+        st = LMState(model, B, max_len=64)
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+        prev = frame
+        for _ in range(3):
+            prev = st.decode_frame_graphed(prev, spec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            prev = st.decode_frame_graphed(prev, spec)
+        e1.record(); torch.cuda.synchronize()
+        st.check_status()
+        print(f"B=64 persist min_kblocks={mk}: {e0.elapsed_time(e1) / 10:.2f} ms/frame-step", flush=True)
+        del st
+    os.environ["CSMB_ENABLE_PERSIST"] = "0"
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""

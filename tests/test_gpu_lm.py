@@ -233,3 +233,20 @@ def test_fused_chain_filtered_sampler_falls_back(model_1b):
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(70 + i, 7), 0) for i in range(3)]
     toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, top_k=50, seed=3))
     assert all(t.shape == (2, 32) for t in toks)
+
+
+def test_persistent_batched_kernel_equals_chain(model_1b, monkeypatch):
+    """csmb_frame_batch (one cooperative launch per frame-step: tcgen05 Linear phases with a persistent TMA ring,
+    grid barriers, in-kernel sampling; opt-in with CSMB_ENABLE_PERSIST=1) produces the tokens of the kernel chain."""
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(80 + i, 7 + i % 6), i % 3) for i in range(20)]
+    chain = generation.generate_tokens(model_1b, prompts, 4, temperature=0.0)
+    monkeypatch.setenv("CSMB_ENABLE_PERSIST", "1")
+    persist = generation.generate_tokens(model_1b, prompts, 4, temperature=0.0)
+    for a, b in zip(chain, persist):
+        assert torch.equal(a, b)
+    spec = SamplerSpec(temperature=0.9, seed=11)
+    sampled_p = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
+    monkeypatch.setenv("CSMB_ENABLE_PERSIST", "0")
+    sampled_c = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
+    for a, b in zip(sampled_c, sampled_p):
+        assert torch.equal(a, b)
