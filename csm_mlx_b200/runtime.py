@@ -93,6 +93,7 @@ class LMState:
         nbytes = _lib.lib().csmb_lm_workspace_bytes(C.byref(self.model.desc()), rows)
         self.workspace = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # zeroed: sticky error flag inside
         self._ws_rows = rows
+        self._graph_key = None  # a graph captured over the per-op path holds pointers into the old workspace
 
     def _batch_desc(self) -> _lib.Batch:
         b = _lib.Batch()

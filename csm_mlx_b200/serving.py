@@ -1,0 +1,263 @@
+"""Continuous batching of independent utterances on one GPU, and a cache of context-segment codes.
+
+The reference generates one utterance at a time (``/root/reference/csm_mlx/generation.py:124,156`` assert batch 1)
+and its streaming demo feeds requests to it from a thread pool, re-tokenising up to six context segments on every
+turn (``run_streaming_csm_mlx.py:102, 830-872, 960-965, 1060-1073``).  SURVEY.md §8e asks for the throughput form of
+the same path: requests sharded over GPUs, and *within a GPU* a fixed set of sequence slots over the paged KV pool
+that requests join and leave between frames.  This module is that host logic; every arithmetic step still runs in
+libcsm_b200.so through ``runtime.LMState`` (prefill / mixed steps on the per-op kernels, steady-state frames on the
+fused kernel chain replayed as a CUDA graph) and ``mimi.Mimi``.
+
+* ``Engine``: ``submit()`` queues a request, ``step()`` generates one frame for every occupied slot and admits queued
+  requests into free slots (their prompt rows are prefilled in the same backbone pass in which the running sequences
+  take their one-row step), ``run()`` drains everything.  EOS (an all-zero frame, generation.py:151-152) and the
+  frame budget are checked on pinned host copies one step late, so the GPU never waits for Python; a finished
+  sequence frees its slot, whose KV pages are simply overwritten by the next occupant.
+* ``ContextCache``: Mimi codes of context audio keyed by content, so a conversation's segments are encoded once
+  (tokenizers.py:61-85 is re-run per turn by the reference).
+
+Greedy results are identical to ``generate`` / ``generate_tokens`` of each request alone (tests/test_gpu_api.py).
+With temperature sampling the random draws are indexed by (seed, position, slot), so they depend on the slot a
+request lands in — like any batched sampler.
+"""
+
+from __future__ import annotations
+
+import hashlib
+from collections import OrderedDict, deque
+from dataclasses import dataclass, field
+from typing import Deque, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .config import MAX_SEQ_LEN
+from .generation import _check_length
+from .models import CSM
+from .runtime import LMState, SamplerSpec
+from .segment import Segment
+from .tokenizers import get_audio_tokenizer, tokenize_audio, tokenize_text_segment
+
+
+class ContextCache:
+    """LRU cache of the (rows, mask) tokenisation of context segments, keyed by speaker, text and audio content."""
+
+    def __init__(self, capacity: int = 64, n_audio_codebooks: int = 32):
+        self.capacity, self.ncb = capacity, n_audio_codebooks
+        self._audio: "OrderedDict[str, Tuple[torch.Tensor, torch.Tensor]]" = OrderedDict()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(audio: torch.Tensor) -> str:
+        a = audio.detach().to("cpu", torch.float32).contiguous()
+        return hashlib.sha1(a.numpy().tobytes()).hexdigest() + f":{a.numel()}"
+
+    def audio_rows(self, audio: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        k = self._key(audio)
+        if k in self._audio:
+            self._audio.move_to_end(k)
+            self.hits += 1
+            return self._audio[k]
+        self.misses += 1
+        rows = tokenize_audio(audio, n_audio_codebooks=self.ncb)
+        self._audio[k] = rows
+        while len(self._audio) > self.capacity:
+            self._audio.popitem(last=False)
+        return rows
+
+    def segment_rows(self, seg: Segment) -> Tuple[torch.Tensor, torch.Tensor]:
+        """tokenize_segment (tokenizers.py:88-102) with the audio half served from the cache."""
+        tt, tm = tokenize_text_segment(seg.text, seg.speaker, n_audio_codebooks=self.ncb)
+        at, am = self.audio_rows(seg.audio)
+        return torch.cat([tt, at], 0), torch.cat([tm, am], 0)
+
+
+@dataclass
+class Request:
+    rid: int
+    tokens: torch.Tensor           # (T, 33) int32 prompt rows
+    mask: torch.Tensor             # (T, 33) bool
+    max_frames: int
+    frames: List[torch.Tensor] = field(default_factory=list)   # (32,) int32 CPU rows, EOS excluded
+    slot: int = -1
+    issued: int = 0                # frames enqueued on the GPU so far
+    done: bool = False
+
+
+def plan_admissions(free_slots: Sequence[int], queue_len: int) -> List[int]:
+    """Slots that take a queued request this step (lowest slot first, FIFO requests)."""
+    return sorted(free_slots)[: max(0, queue_len)]
+
+
+class Engine:
+    """Fixed ``max_batch`` sequence slots over one ``LMState``; see the module docstring."""
+
+    def __init__(self, model: CSM, max_batch: int = 64, max_len: int = MAX_SEQ_LEN, sampler: Optional[SamplerSpec] = None,
+                 context_cache: Optional[ContextCache] = None):
+        self.model, self.B = model, int(max_batch)
+        self.spec = sampler if sampler is not None else SamplerSpec(temperature=0.0)
+        self.state = LMState(model, self.B, max_len=max_len)
+        self.ncb = model.n_audio_codebooks
+        self.cache = context_cache if context_cache is not None else ContextCache(n_audio_codebooks=self.ncb)
+        self.queue: Deque[Request] = deque()
+        self.slots: List[Optional[Request]] = [None] * self.B
+        self.finished: Dict[int, Request] = {}
+        self._next_id = 0
+        self._prev: Optional[torch.Tensor] = None          # device (B, 32) frame of the last step
+        self._pending: Optional[Tuple[int, List[Optional[Request]]]] = None   # (mirror slot, occupants) of the last step
+        self._host = [torch.empty((self.B, self.ncb), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._events = [torch.cuda.Event() for _ in range(2)]
+        self._flip = 0
+        self.steps = self.mixed_steps = 0
+
+    # ------------------------------------------------------------------ requests
+    def build_prompt(self, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """generation.py:108-121 with cached context tokenisation."""
+        toks, masks = [], []
+        for seg in context:
+            t, m = self.cache.segment_rows(seg)
+            toks.append(t)
+            masks.append(m)
+        t, m = tokenize_text_segment(text, speaker, n_audio_codebooks=self.ncb)
+        toks.append(t)
+        masks.append(m)
+        return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0)
+
+    def submit(self, text: Union[str, Sequence[int]], speaker: int, context: Optional[Sequence[Segment]] = None,
+               max_audio_length_ms: float = 90_000) -> int:
+        tok, mask = self.build_prompt(text, speaker, context or [])
+        return self.submit_prompt(tok, mask, int(max_audio_length_ms / 80))
+
+    def submit_prompt(self, tokens: torch.Tensor, mask: torch.Tensor, max_frames: int) -> int:
+        _check_length(self.model, int(tokens.shape[0]), max_frames)           # generation.py:131-137
+        if int(tokens.shape[0]) + max_frames + 1 > self.state.max_len:
+            raise ValueError("request exceeds the KV pages reserved per slot (Engine(max_len=...))")
+        r = Request(self._next_id, tokens.to(torch.int32).cpu(), mask.cpu(), int(max_frames))
+        self._next_id += 1
+        self.queue.append(r)
+        return r.rid
+
+    @property
+    def active(self) -> int:
+        return sum(r is not None for r in self.slots)
+
+    # ------------------------------------------------------------------ one frame for every occupied slot
+    def step(self) -> List[Request]:
+        """Enqueues one frame-step, then retires what the previous step finished.  Returns newly finished requests."""
+        st = self.state
+        newly_done: List[Request] = []
+        free = [b for b, r in enumerate(self.slots) if r is None]
+        admit = plan_admissions(free, len(self.queue))
+        if self.active == 0 and not admit:
+            newly_done += self._drain()
+            return newly_done
+        if admit or self._prev is None:
+            frame = self._mixed_step(admit)
+        else:
+            self._park_idle_slots()
+            frame = st.decode_frame_graphed(self._prev, self.spec)
+        self.steps += 1
+        for r in self.slots:
+            if r is not None:
+                r.issued += 1
+        # publish this step's frame to the host (pinned, asynchronous) and look at the previous one
+        slot = self._flip
+        self._flip ^= 1
+        self._host[slot].copy_(frame, non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(st.device))
+        newly_done += self._drain()
+        self._pending = (slot, list(self.slots))
+        self._prev = frame
+        return newly_done
+
+    def _drain(self) -> List[Request]:
+        done: List[Request] = []
+        if self._pending is None:
+            return done
+        slot, occupants = self._pending
+        self._pending = None
+        self._events[slot].synchronize()
+        host = self._host[slot]
+        for b, r in enumerate(occupants):
+            if r is None or r.done:
+                continue
+            row = host[b]
+            if not bool(row.any()):                      # EOS: generation.py:151-152
+                r.done = True
+            else:
+                r.frames.append(row.clone())
+                if len(r.frames) >= r.max_frames:
+                    r.done = True
+            if r.done:
+                done.append(r)
+                self.finished[r.rid] = r
+                if self.slots[b] is r:
+                    self.slots[b] = None                 # the frame already in flight for this slot is discarded
+        return done
+
+    def _park_idle_slots(self) -> None:
+        """Empty slots keep stepping inside the captured graph; pin them at position 0 so they never leave their pages."""
+        st = self.state
+        idle = [b for b, r in enumerate(self.slots) if r is None]
+        if idle:
+            idx = torch.tensor(idle, dtype=torch.long, device=st.device)
+            st.pos.index_fill_(0, idx, 0)
+            for b in idle:
+                st.pos_host[b] = 0
+
+    def _mixed_step(self, admit: List[int]) -> torch.Tensor:
+        """One backbone pass in which admitted requests prefill their prompts and running sequences take their
+        one-row step (generation.py:34-42 for both T > 1 and T = 1), then c0 + the depth loop for all slots."""
+        st, ncb = self.state, self.ncb
+        self.mixed_steps += 1
+        prev_host = None
+        if self._prev is not None:
+            prev_host = self._prev.to("cpu")             # synchronises; admissions are rare next to frames
+        for b in admit:
+            r = self.queue.popleft()
+            r.slot = b
+            self.slots[b] = r
+            st.pos_host[b] = 0
+        rows, masks = [], []
+        one = torch.cat([torch.ones((1, ncb), dtype=torch.bool), torch.zeros((1, 1), dtype=torch.bool)], 1)
+        for b in range(self.B):
+            r = self.slots[b]
+            if r is not None and b in admit:
+                rows.append(r.tokens)
+                masks.append(r.mask)
+            elif r is not None:
+                rows.append(torch.cat([prev_host[b:b + 1], torch.zeros((1, 1), dtype=torch.int32)], 1))
+                masks.append(one)
+            else:                                          # idle slot: a masked-out dummy row at position 0
+                st.pos_host[b] = 0
+                rows.append(torch.zeros((1, ncb + 1), dtype=torch.int32))
+                masks.append(torch.zeros((1, ncb + 1), dtype=torch.bool))
+        st.prefill(rows, masks)
+        frame = torch.zeros((self.B, ncb), device=st.device, dtype=torch.int32)
+        st.sample_c0(frame, self.spec)
+        st.depth_decode(frame, self.spec)
+        return frame
+
+    # ------------------------------------------------------------------ drivers
+    def run(self) -> Dict[int, Request]:
+        """Steps until the queue and all slots are empty; returns {request id: Request}."""
+        while self.queue or self.active or self._pending is not None:
+            self.step()
+        self.state.check_status()
+        return self.finished
+
+    def tokens(self, rid: int) -> torch.Tensor:
+        r = self.finished[rid]
+        return torch.stack(r.frames) if r.frames else torch.zeros((0, self.ncb), dtype=torch.int32)
+
+    def audio(self, rids: Sequence[int]) -> List[torch.Tensor]:
+        """Mimi decode (tokenizers.py:148-150) of finished requests, batched; 1-D float32 CPU tensors."""
+        mimi = get_audio_tokenizer(self.ncb)
+        toks = [self.tokens(r) for r in rids]
+        fmax = max((int(t.shape[0]) for t in toks), default=0)
+        if fmax == 0:
+            return [torch.zeros((0,), dtype=torch.float32) for _ in toks]
+        codes = torch.zeros((len(toks), self.ncb, fmax), dtype=torch.int32)
+        for i, t in enumerate(toks):
+            codes[i, :, : t.shape[0]] = t.t()
+        audio = mimi.decode(codes.to(self.model.device)).to("cpu")
+        return [audio[i, 0, : 1920 * int(t.shape[0])].clone() for i, t in enumerate(toks)]

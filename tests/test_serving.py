@@ -1,0 +1,92 @@
+"""Continuous batching engine and context cache (csm_mlx_b200/serving.py).
+
+CPU part: the host logic (admission plan, content-keyed context cache).  GPU part: requests of different prompt
+lengths and frame budgets flowing through 4 slots must produce, token for token, what each produces alone through
+generate_tokens (the reference's batch-1 loop, generation.py:139-161) — slot reuse, mixed prefill/decode steps and
+graph-replayed steady-state steps included."""
+import pytest
+import torch
+
+from csm_mlx_b200 import serving, tokenizers
+from tests.workloads import prompt_ids, synthetic_audio
+
+
+def test_plan_admissions():
+    assert serving.plan_admissions([3, 1, 2], 2) == [1, 2]
+    assert serving.plan_admissions([5], 4) == [5]
+    assert serving.plan_admissions([], 3) == []
+    assert serving.plan_admissions([0, 1], 0) == []
+
+
+def test_context_cache_encodes_each_audio_once(monkeypatch):
+    calls = []
+
+    def fake_tokenize_audio(audio, *, n_audio_codebooks=32):
+        calls.append(int(audio.numel()))
+        n = 3
+        tok = torch.zeros((n, n_audio_codebooks + 1), dtype=torch.int32)
+        tok[:, 0] = int(audio.numel())
+        return tok, torch.ones((n, n_audio_codebooks + 1), dtype=torch.bool)
+
+    monkeypatch.setattr(serving, "tokenize_audio", fake_tokenize_audio)
+    cache = serving.ContextCache(capacity=2)
+    a, b, c = torch.ones(100), torch.ones(200), torch.full((100,), 2.0)
+    r1 = cache.audio_rows(a)
+    r2 = cache.audio_rows(a.clone())           # same content, different tensor: a hit
+    assert r1[0] is r2[0] and calls == [100] and (cache.hits, cache.misses) == (1, 1)
+    cache.audio_rows(b)
+    cache.audio_rows(c)                        # same length as a, different content: a miss; evicts a (LRU)
+    assert calls == [100, 200, 100]
+    cache.audio_rows(a)
+    assert calls == [100, 200, 100, 100]
+    from csm_mlx_b200 import Segment
+
+    tok, mask = cache.segment_rows(Segment(1, [128000, 5, 6, 128001], audio=c))
+    assert tok.shape[1] == 33 and tok.shape[0] == 4 + 3 and mask.shape == tok.shape
+    assert calls == [100, 200, 100, 100]       # c was still cached (b was the least recently used)
+
+
+@pytest.mark.gpu
+def test_engine_continuous_batching_matches_single(model_1b, mimi_gpu):
+    from csm_mlx_b200 import generation
+
+    eng = serving.Engine(model_1b, max_batch=4, max_len=128)
+    reqs = [(prompt_ids(100 + i, 6 + 2 * i), i % 3, 3 + (i % 4)) for i in range(9)]   # ragged prompts, budgets 3..6
+    rids = [eng.submit(ids, spk, [], max_audio_length_ms=80 * f) for ids, spk, f in reqs[:6]]
+    for _ in range(4):
+        eng.step()
+    rids += [eng.submit(ids, spk, [], max_audio_length_ms=80 * f) for ids, spk, f in reqs[6:]]   # arrivals mid-flight
+    eng.run()
+    assert eng.active == 0 and not eng.queue
+    assert 0 < eng.mixed_steps < eng.steps          # admissions used mixed steps, steady state the graphed chain
+    for rid, (ids, spk, f) in zip(rids, reqs):
+        (single,) = generation.generate_tokens(model_1b, [tokenizers.tokenize_text_segment(ids, spk)], f, temperature=0.0)
+        assert torch.equal(single, eng.tokens(rid)), rid
+    audio = eng.audio(rids[:2])
+    assert [a.shape for a in audio] == [(1920 * reqs[0][2],), (1920 * reqs[1][2],)]
+
+
+@pytest.mark.gpu
+def test_engine_context_segments_use_the_cache(model_1b, mimi_gpu):
+    from csm_mlx_b200 import Segment, generation
+
+    tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+    try:
+        seg = Segment(0, "a context sentence", synthetic_audio(11, 1.0))
+        eng = serving.Engine(model_1b, max_batch=2, max_len=128)
+        r0 = eng.submit("first answer", 1, [seg], max_audio_length_ms=240)
+        r1 = eng.submit("second answer", 1, [seg], max_audio_length_ms=240)
+        eng.run()
+        assert (eng.cache.hits, eng.cache.misses) == (1, 1)
+        prompt = generation._build_prompt(model_1b, "second answer", 1, [seg])
+        (single,) = generation.generate_tokens(model_1b, [prompt], 3, temperature=0.0)
+        assert torch.equal(single, eng.tokens(r1)) and eng.tokens(r0).shape == (3, 32)
+    finally:
+        tokenizers.set_text_tokenizer(None)
+
+
+@pytest.mark.gpu
+def test_engine_rejects_oversized_requests(model_1b):
+    eng = serving.Engine(model_1b, max_batch=2, max_len=64)
+    with pytest.raises(ValueError):
+        eng.submit(prompt_ids(1, 40), 0, [], max_audio_length_ms=80 * 40)
