@@ -251,13 +251,11 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     for (int g = 0; g < GS; ++g)
       if (g < ns) mbar_wait(c, &c.ring.full[(c.q + g) % NSTAGES], ((c.q + g) / NSTAGES) & 1, 2);
     mark(c, T_WAIT);
-    // (even, odd) accumulator pairs: one packed fp32x2 FMA (FFMA2, sm_100) per bf16 pair — the same two dependent
-    // chains per (unit, row) as scalar FMAs would give, at half the issue slots on the FMA pipe
-    float2 acc[GS][R];
+    float acc[GS][R][2];
 #pragma unroll
     for (int g = 0; g < GS; ++g)
 #pragma unroll
-      for (int i = 0; i < R; ++i) acc[g][i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < R; ++i) acc[g][i][0] = acc[g][i][1] = 0.f;
     if (math && !c.aborted) {
       const unsigned char* b[GS];
 #pragma unroll
@@ -269,13 +267,12 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
         for (int g = 0; g < GS; ++g) w[g] = *reinterpret_cast<const uint4*>(b[g] + ch * 512);
 #pragma unroll
         for (int g = 0; g < GS; ++g) {
-          const float2 f[4] = {make_float2(bf16lo(w[g].x), bf16hi(w[g].x)), make_float2(bf16lo(w[g].y), bf16hi(w[g].y)),
-                               make_float2(bf16lo(w[g].z), bf16hi(w[g].z)), make_float2(bf16lo(w[g].w), bf16hi(w[g].w))};
+          const float f[8] = {bf16lo(w[g].x), bf16hi(w[g].x), bf16lo(w[g].y), bf16hi(w[g].y),
+                              bf16lo(w[g].z), bf16hi(w[g].z), bf16lo(w[g].w), bf16hi(w[g].w)};
 #pragma unroll
           for (int i = 0; i < R; ++i)
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              acc[g][i] = __ffma2_rn(f[e], make_float2(xr[i][ch * 8 + 2 * e], xr[i][ch * 8 + 2 * e + 1]), acc[g][i]);
+            for (int e = 0; e < 8; ++e) acc[g][i][e & 1] = fmaf(f[e], xr[i][ch * 8 + e], acc[g][i][e & 1]);
         }
       }
     }
@@ -283,7 +280,7 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
 #pragma unroll
     for (int g = 0; g < GS; ++g)
 #pragma unroll
-      for (int i = 0; i < R; ++i) sum[g][i] = acc[g][i].x + acc[g][i].y;
+      for (int i = 0; i < R; ++i) sum[g][i] = acc[g][i][0] + acc[g][i][1];
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1)
 #pragma unroll

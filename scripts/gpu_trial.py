@@ -182,7 +182,7 @@ def _time():
 def _fused():
     import numpy as np
     g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cfg1_lm.npz"))
-    st = LMState(model, 1, max_len=256)
+    st = LMState(model, 1, max_len=1024)
     st.prefill([ptok], [pmask])
     spec = SamplerSpec()
     frame = torch.zeros((1, 32), device=dev, dtype=torch.int32)
