@@ -432,6 +432,55 @@ def _persist():
     os.environ["CSMB_ENABLE_PERSIST"] = "0"
 
 
+@section("overlap")
+def _overlap():
+    """Where do the ~0.16 ms per frame between k_frame alone and the streaming loop go?"""
+    mimi = Mimi(32, device=dev).load_pytorch_weights(random_mimi_weights())
+    tokenizers.set_audio_tokenizer(mimi)
+    spec = SamplerSpec()
+    st = LMState(model, 1, max_len=512)
+    codec = mimi.new_decode_stream(1)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    ev = torch.cuda.Event()
+    sink = torch.zeros((1, 1920), device=dev)
+
+    def run(mode, n=100):
+        st.reset(); codec.reset()
+        st.prefill([ptok], [pmask])
+        frame = st.first_frame_fused(spec)
+        for _ in range(3):
+            frame = st.decode_frame_fused(frame, spec)
+            codec.step(frame.reshape(1, 32, 1))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if mode == "lm":
+                pass
+            elif mode == "serial":
+                codec.step(frame.reshape(1, 32, 1))
+            elif mode in ("overlap", "sync-only", "copy-only"):
+                ev.record(main)
+                side.wait_event(ev)
+                frame.record_stream(side)
+                with torch.cuda.stream(side):
+                    if mode == "overlap":
+                        a = codec.step(frame.reshape(1, 32, 1))
+                        sink.copy_(a.reshape(1, -1))
+                    elif mode == "copy-only":
+                        sink[:, :32].copy_(frame.float())
+            frame = st.decode_frame_fused(frame, spec)
+        main.wait_stream(side)
+        e1.record(); torch.cuda.synchronize()
+        print(f"  {mode:10s}: {e0.elapsed_time(e1) / n:.3f} ms/frame", flush=True)
+
+    for rep in range(2):
+        for mode in ("lm", "sync-only", "copy-only", "overlap", "serial"):
+            run(mode)
+    st.check_status()
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""
