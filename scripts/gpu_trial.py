@@ -481,6 +481,27 @@ def _overlap():
     st.check_status()
 
 
+@section("diverge")
+def _diverge():
+    """64 x 125 frames through the engine (fused chain) vs each utterance alone (persistent batch-1 kernel)."""
+    from csm_mlx_b200 import serving
+    from tests.workloads import prompt_ids
+    mimi = Mimi(32, device=dev).load_pytorch_weights(random_mimi_weights())
+    tokenizers.set_audio_tokenizer(mimi)
+    eng = serving.Engine(model, max_batch=64, max_len=160)
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(64)]
+    rids = [eng.submit_prompt(t, m, 125) for t, m in prompts]
+    eng.run()
+    firsts = []
+    for i in range(64):
+        (single,) = generation.generate_tokens(model, [prompts[i]], 125, temperature=0.0)
+        got = eng.tokens(rids[i])
+        neq = (single != got).any(dim=1).nonzero()
+        firsts.append(int(neq[0]) if len(neq) else None)
+    same = sum(f is None for f in firsts)
+    print(f"identical over 125 frames: {same} of 64; first differing frame of the others: {sorted(f for f in firsts if f is not None)}", flush=True)
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""

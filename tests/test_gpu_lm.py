@@ -250,3 +250,18 @@ def test_persistent_batched_kernel_equals_chain(model_1b, monkeypatch):
     sampled_c = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
     for a, b in zip(sampled_c, sampled_p):
         assert torch.equal(a, b)
+
+
+def test_cfg2_full_length_two_implementations_agree(model_1b, monkeypatch):
+    """BASELINE.json configs[1] at full size (125 frames = 10 s): the persistent frame kernel and the per-op CUDA-graph
+    path are independent implementations of the frame; they must agree on all 4 000 tokens, the first 25 frames must
+    equal the oracle's golden tokens, and a second run must reproduce the first bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "cfg1_lm.npz"))
+    (fused,) = generation.generate_tokens(model_1b, [_prompt()], 125, temperature=0.0)
+    (again,) = generation.generate_tokens(model_1b, [_prompt()], 125, temperature=0.0)
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    (per_op,) = generation.generate_tokens(model_1b, [_prompt()], 125, temperature=0.0)
+    assert fused.shape == (125, 32)
+    assert torch.equal(fused, again)
+    assert torch.equal(fused, per_op)
+    assert np.array_equal(fused.numpy()[:25], g["tokens"])

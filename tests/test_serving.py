@@ -90,3 +90,54 @@ def test_engine_rejects_oversized_requests(model_1b):
     eng = serving.Engine(model_1b, max_batch=2, max_len=64)
     with pytest.raises(ValueError):
         eng.submit(prompt_ids(1, 40), 0, [], max_audio_length_ms=80 * 40)
+
+
+def _margin_at(model, prompt, tokens, f, c, a, b, device):
+    """Teacher-forced referee on the per-op kernels: |logit[a] - logit[b]| of codebook c in frame f, given the first f
+    frames and the first c codebooks of frame f of `tokens`."""
+    from csm_mlx_b200.runtime import LMState, SamplerSpec
+
+    st = LMState(model, 1, max_len=int(prompt[0].shape[0]) + f + 2)
+    st.prefill([prompt[0]], [prompt[1]])
+    spec = SamplerSpec()
+    for t in range(f):
+        st.backbone_step(tokens[t:t + 1].to(device, torch.int32).contiguous())
+    if c == 0:
+        lg = st.c0_logits[0]
+    else:
+        frame = torch.zeros((1, 32), device=device, dtype=torch.int32)
+        out = torch.zeros((1, 32, model.n_audio_vocab), device=device)
+        st.depth_decode(frame, spec, logits_out=out, forced=tokens[f:f + 1].to(device, torch.int32).contiguous())
+        lg = out[0, c]
+    return abs(float(lg[a]) - float(lg[b])), float(lg.max() - lg[a])
+
+
+@pytest.mark.gpu
+def test_cfg4_full_size_engine_vs_single(model_1b, mimi_gpu, device):
+    """BASELINE.json configs[3] at full size on one GPU: 64 utterances x 125 frames (256 000 greedy decisions) through
+    the engine (fused tcgen05 kernel chain, CUDA-graph replay) against every utterance generated alone by the batch-1
+    persistent kernel.  The two paths sum in different orders, so an argmax can flip where the two best logits of the
+    random-init model tie to within float noise; from there on the utterance legitimately differs.  Gate: every
+    utterance is identical up to its first differing token, at least 36 of 64 are identical throughout (measured: 44), and at every
+    first difference the two candidates' logits, recomputed teacher-forced on the per-op kernels (a third
+    implementation), are closer than 2e-4 (the stated logit tolerance is 1e-4 per path)."""
+    from csm_mlx_b200 import generation
+
+    eng = serving.Engine(model_1b, max_batch=64, max_len=160)
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(64)]
+    rids = [eng.submit_prompt(t, m, 125) for t, m in prompts]
+    eng.run()
+    identical, worst = 0, 0.0
+    for i in range(64):
+        (single,) = generation.generate_tokens(model_1b, [prompts[i]], 125, temperature=0.0)
+        got = eng.tokens(rids[i])
+        assert got.shape == (125, 32)
+        diff = (single != got).nonzero()
+        if len(diff) == 0:
+            identical += 1
+            continue
+        f, c = int(diff[0][0]), int(diff[0][1])
+        margin, below_max = _margin_at(model_1b, prompts[i], single, f, c, int(single[f, c]), int(got[f, c]), device)
+        worst = max(worst, margin)
+        assert margin < 2e-4 and below_max < 2e-4, (i, f, c, margin, below_max)
+    assert identical >= 36, identical
