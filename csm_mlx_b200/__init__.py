@@ -1,8 +1,8 @@
 """csm_mlx_b200 — B200-native drop-in for the ``csm_mlx`` generation hot path.
 
 Same export list as ``/root/reference/csm_mlx/__init__.py:1-16``.  The training exports (``CSMDataset``,
-``CSMTrainer``, ``TrainArgs``, ``load_adapters``) are outside the generation hot path and raise
-``NotImplementedError`` when used.  ``import csm_mlx`` resolves to a thin alias package of this one.
+``CSMTrainer``, ``TrainArgs``) are outside the generation hot path and raise ``NotImplementedError``
+when used; ``load_adapters`` folds a LoRA / full adapter into the dense weights (``adapters.py``).  ``import csm_mlx`` resolves to a thin alias package of this one.
 """
 
 from .generation import generate, generate_batch, generate_frame, make_cache, stream_generate
@@ -26,8 +26,7 @@ CSMTrainer = _out_of_scope("CSMTrainer")
 TrainArgs = _out_of_scope("TrainArgs")
 
 
-def load_adapters(*a, **k):
-    raise NotImplementedError("load_adapters belongs to the fine-tuning stack, which is outside the generation hot path")
+from .adapters import load_adapters  # noqa: E402  (inference-side half of finetune/utils.py:84-108: adapters are merged)
 
 
 __all__ = [

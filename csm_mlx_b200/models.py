@@ -154,6 +154,7 @@ class CSM:
         else:
             weights = dict(list(file_or_weights))
         weights = {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(_to_numpy(v))) for k, v in weights.items()}
+        weights = normalize_checkpoint_keys(weights)
 
         expected = _expected_shapes(self.args)
         if strict:
@@ -271,6 +272,29 @@ class CSM:
                                              self.n_audio_codebooks, self.n_audio_vocab, dev_idx,
                                              _lib.stream_ptr(self.device)))
         return out.reshape(*tk.shape[:-1], d)
+
+
+_SESAME_RENAMES = (
+    (".attn.q_proj.", ".self_attn.q_proj."), (".attn.k_proj.", ".self_attn.k_proj."), (".attn.v_proj.", ".self_attn.v_proj."),
+    (".attn.output_proj.", ".self_attn.o_proj."), (".mlp.w1.", ".mlp.gate_proj."), (".mlp.w3.", ".mlp.up_proj."),
+    (".mlp.w2.", ".mlp.down_proj."), (".sa_norm.scale", ".input_layernorm.weight"),
+    (".mlp_norm.scale", ".post_attention_layernorm.weight"), (".norm.scale", ".norm.weight"),
+)
+
+
+def normalize_checkpoint_keys(weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Accepts the original ``sesame/csm-1b`` (torchtune) parameter names next to the mlx ones of
+    ``senstella/csm-1b-mlx``: same tensors, same adjacent-pair RoPE row order, different
+    names (``attn.output_proj`` / ``mlp.w1,w3,w2`` / ``sa_norm.scale`` …; a leading ``model.`` is dropped)."""
+    if not any((".attn." in k) or k.endswith(".scale") or k.startswith("model.") or ".mlp.w" in k for k in weights):
+        return weights
+    out = {}
+    for k, v in weights.items():
+        k = k[len("model."):] if k.startswith("model.") else k
+        for a, b in _SESAME_RENAMES:
+            k = k.replace(a, b)
+        out[k] = v
+    return out
 
 
 def _to_numpy(v):

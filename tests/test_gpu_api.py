@@ -114,3 +114,38 @@ def test_abandoned_stream_releases_resources(model_1b, mimi_gpu):
     gen.close()
     full = list(stream_generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=400, temperature=0.0))
     assert all(torch.equal(a, b) for a, b in zip(head, full))
+
+
+def test_load_adapters_folds_lora_into_dense_weights(device, tmp_path):
+    """load_adapters (finetune/utils.py:84-108) on the generation path: the LoRA pair is merged, W' = W + s (A B)^T,
+    and generation runs on the merged weights; a `full` adapter is a non-strict weight load."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from csm_mlx_b200 import CSM, csm_tiny, load_adapters
+    from csm_mlx_b200.random_init import random_csm_weights
+
+    args = csm_tiny()
+    W = random_csm_weights(args, seed=5)
+    m = CSM(args, device=device).load_weights(W)
+    name = "decoder.layers.0.mlp.down_proj"
+    w0 = m.parameters()[name + ".weight"].float().cpu()
+    g = torch.Generator().manual_seed(1)
+    a, b = 0.05 * torch.randn(w0.shape[1], 4, generator=g), 0.05 * torch.randn(4, w0.shape[0], generator=g)
+    d = tmp_path / "adapter"
+    d.mkdir()
+    save_file({name + ".lora_a": a, name + ".lora_b": b}, str(d / "adapters.safetensors"))
+    (d / "adapter_config.json").write_text(json.dumps({"fine_tune_type": "lora", "lora_parameters": {"rank": 4, "scale": 2.0}}))
+    load_adapters(m, str(d))
+    w1 = m.parameters()[name + ".weight"].float().cpu()
+    want = (w0 + 2.0 * (a @ b).t()).to(torch.bfloat16).float()
+    assert torch.equal(w1, want)
+    other = m.parameters()["decoder.layers.0.mlp.up_proj.weight"].float().cpu()
+    assert torch.equal(other, W["decoder.layers.0.mlp.up_proj.weight"].to(torch.bfloat16).float())
+    d2 = tmp_path / "full"
+    d2.mkdir()
+    save_file({"projection.weight": torch.zeros_like(W["projection.weight"])}, str(d2 / "adapters.safetensors"))
+    (d2 / "adapter_config.json").write_text(json.dumps({"fine_tune_type": "full"}))
+    load_adapters(m, str(d2))
+    assert float(m.parameters()["projection.weight"].float().abs().max()) == 0.0

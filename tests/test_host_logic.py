@@ -24,8 +24,8 @@ def test_export_surface_matches_reference():
     from csm_mlx.utils import read_audio, write_audio  # noqa: F401
     with pytest.raises(NotImplementedError):
         csm_mlx.CSMTrainer()
-    with pytest.raises(NotImplementedError):
-        csm_mlx.load_adapters(None, "x")
+    with pytest.raises(FileNotFoundError):
+        csm_mlx.load_adapters(None, "/nonexistent/adapter")
 
 
 def test_model_args_and_param_tree():
@@ -190,3 +190,54 @@ def test_oracle_sampler_filters():
     freq = np.bincount(draws, minlength=5) / 400
     assert abs(freq[0] - 0.5) < 0.1 and abs(freq[1] - 0.2) < 0.08
     assert set(osamp.sample(lg, 1.0, seed=1, draw=d, top_k=2) for d in range(100)) == {0, 1}
+
+
+def test_sesame_checkpoint_key_names_are_accepted():
+    """the original sesame/csm-1b (torchtune) names map onto the mlx names one to one."""
+    from csm_mlx_b200.models import _expected_shapes, normalize_checkpoint_keys
+
+    W = random_csm_weights(csm_tiny(), seed=2)
+    ren = {}
+    for k, v in W.items():
+        k2 = (k.replace(".self_attn.q_proj.", ".attn.q_proj.").replace(".self_attn.k_proj.", ".attn.k_proj.")
+              .replace(".self_attn.v_proj.", ".attn.v_proj.").replace(".self_attn.o_proj.", ".attn.output_proj.")
+              .replace(".mlp.gate_proj.", ".mlp.w1.").replace(".mlp.up_proj.", ".mlp.w3.").replace(".mlp.down_proj.", ".mlp.w2.")
+              .replace(".input_layernorm.weight", ".sa_norm.scale").replace(".post_attention_layernorm.weight", ".mlp_norm.scale")
+              .replace(".norm.weight", ".norm.scale"))
+        ren["model." + k2] = v
+    assert set(ren) != set(W)
+    back = normalize_checkpoint_keys(ren)
+    assert set(back) == set(_expected_shapes(csm_tiny())) == set(W)
+    assert all(back[k] is W[k] for k in W)
+    assert normalize_checkpoint_keys(W) is W
+
+
+def test_merge_lora_math_and_errors():
+    """finetune/utils.py:84-108 folded: W' = W + scale * (lora_a @ lora_b)^T, fp32."""
+    from csm_mlx_b200.adapters import merge_lora
+
+    g = torch.Generator().manual_seed(0)
+    W = {"backbone.layers.0.self_attn.q_proj.weight": torch.randn(12, 8, generator=g), "other.weight": torch.randn(3, 3, generator=g)}
+    a, b = torch.randn(8, 2, generator=g), torch.randn(2, 12, generator=g)
+    out = merge_lora(W, {"backbone.layers.0.self_attn.q_proj.lora_a": a, "backbone.layers.0.self_attn.q_proj.lora_b": b}, 0.5)
+    x = torch.randn(5, 8, generator=g)
+    ref = x @ W["backbone.layers.0.self_attn.q_proj.weight"].t() + 0.5 * ((x @ a) @ b)      # LoRALinear forward
+    assert torch.allclose(x @ out["backbone.layers.0.self_attn.q_proj.weight"].t(), ref, atol=1e-5)
+    assert out["other.weight"] is W["other.weight"]
+    with pytest.raises(ValueError, match="not a Linear"):
+        merge_lora(W, {"nope.lora_a": a, "nope.lora_b": b}, 1.0)
+    with pytest.raises(ValueError, match="shapes"):
+        merge_lora(W, {"backbone.layers.0.self_attn.q_proj.lora_a": a.t().contiguous(), "backbone.layers.0.self_attn.q_proj.lora_b": b}, 1.0)
+
+
+def test_cli_parser_matches_reference_defaults():
+    """cli/generate.py:72-160: option names and defaults of `csm-mlx generate`."""
+    from csm_mlx_b200.cli.generate import build_parser, main
+
+    a = build_parser().parse_args(["Hello from Sesame.", "-o", "out.wav"])
+    assert (a.model, a.weight, a.speaker, a.max_audio_length, a.temperature, a.top_k, a.top_p, a.min_p,
+            a.min_tokens_to_keep, a.adapter) == ("1b", "senstella/csm-1b-mlx", 0, 10000, 0.8, 50, None, None, 1, None)
+    b = build_parser().parse_args(["hi", "--output", "o.wav", "-s", "2", "-l", "2000", "--temp", "0", "-k", "0", "-is", "0", "1",
+                                   "-ia", "a.wav", "b.wav", "-it", "x", "y"])
+    assert b.speaker == 2 and b.input_speakers == [0, 1] and b.input_audios == ["a.wav", "b.wav"] and b.input_texts == ["x", "y"]
+    assert main(["hi", "-o", "o.wav", "-ia", "a.wav"]) == 1      # mismatched context lists: cli/generate.py:157-165
