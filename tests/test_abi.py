@@ -34,3 +34,20 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Sampler) == 32
     assert ctypes.sizeof(_lib.Model) == 2 * ctypes.sizeof(_lib.Llama) + 5 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.Batch) == 8 + 7 * 8
+
+
+def test_header_is_plain_c():
+    """include/csm_b200.h is the boundary a foreign binding compiles against: it must parse as C99 with nothing but
+    <stddef.h> / <stdint.h> (no C++, no CUDA, no torch types)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+
+        pytest.skip("no gcc")
+    src = '#include "csm_b200.h"\nint main(void) { csmb_sampler s; csmb_model m; csmb_batch b; (void)s; (void)m; (void)b; return CSMB_ABI_VERSION - 1; }\n'
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", "-I",
+                        os.path.join(ROOT, "include"), "-"], input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
