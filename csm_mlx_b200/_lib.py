@@ -17,7 +17,7 @@ MAX_LAYERS = 16
 PAGE = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsm_b200.so")
+LIB_PATH = os.environ.get("CSMB_LIB_PATH") or os.path.join(_HERE, "libcsm_b200.so")  # override: A/B builds of the kernels
 
 
 class CsmbError(RuntimeError):

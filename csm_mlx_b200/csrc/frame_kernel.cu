@@ -5,7 +5,7 @@
 // sample, then the 31-step depth-decoder loop with per-step head, sampling and next-embedding gather — without
 // returning to the host.  ~700 dependent GEMV phases per frame make per-kernel launches latency-bound; here
 //   * one PRODUCER thread per CTA walks the statically known weight schedule (its row slice of every matrix, in
-//     order) and streams it HBM -> shared memory with cp.async.bulk (L2 evict-first) into an 8 x 16 KiB ring guarded
+//     order) and streams it HBM -> shared memory with cp.async.bulk (L2 evict-first) into a 4 x 32 KiB ring guarded
 //     by mbarriers; it never waits for activations;
 //   * eight CONSUMER warps per CTA keep their K-slice of the phase's activation vector in registers and reduce
 //     1024-weight units (bf16 -> fp32 by bit shift, fp32 FMA) out of the ring; rows are split evenly across the 148
@@ -32,8 +32,14 @@ namespace csmb {
 constexpr int NCW = 8;                  // consumer warps
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int NTHREADS = (NCW + 1) * 32;
-constexpr int STAGE_BYTES = 16384;
-constexpr int NSTAGES = 8;
+#ifndef CSMB_FRAME_STAGE_KB
+#define CSMB_FRAME_STAGE_KB 32
+#endif
+// ring geometry: 4 x 32 KiB (default; measured 3.30 ms per frame) or 8 x 16 KiB (3.52 ms: twice the mbarrier handshakes
+// and bulk copies per byte)
+constexpr int STAGE_BYTES = CSMB_FRAME_STAGE_KB * 1024;
+constexpr int NSTAGES = 128 * 1024 / STAGE_BYTES;
+constexpr int SUB = STAGE_BYTES / 16384;                 // 16 KiB sub-stages (8 units of 1024 weights) per ring stage
 constexpr int UNIT = 1024;              // weights per (warp, stage) unit
 constexpr int MAXU = 192;               // max units per range per CTA (csm_1b: 112 on 148 CTAs, 176 on 96)
 constexpr int MAX_SPLIT = 16;           // backbone attention chunks (128 keys each) per head
@@ -156,6 +162,7 @@ struct Ctx {
   uint32_t phase;  // activation phase counter (same sequence in every CTA); part of the tag
   uint32_t launch; // tag nonce of this launch (1 .. 2^20-1)
   bool aborted;
+  bool prof_on;    // this thread records phase timers (debug)
   uint64_t policy;
   unsigned long long t_acc[12];
   unsigned long long t_last;
@@ -164,7 +171,7 @@ struct Ctx {
 // phase timers (debug): thread 0 of every CTA accumulates the cycles since the previous mark into category `cat`
 enum { T_POLL = 0, T_LOAD = 1, T_GEMV = 2, T_FIN = 3, T_DATT = 4, T_BATT = 5, T_SAMPLE = 6, T_MERGE = 7, T_WAIT = 8 };
 __device__ __forceinline__ void mark(Ctx& c, int cat) {
-  if (c.p->prof != nullptr && c.tid == 0) {
+  if (c.prof_on) {
     const unsigned long long t = (unsigned long long)clock64();
     c.t_acc[cat] += t - c.t_last;
     c.t_last = t;
@@ -238,17 +245,19 @@ __device__ __forceinline__ int n_stages(const Range& r) {
 template <int R>
 __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float* part) {
   if (c.p->dbg & 8) return;  // timing experiment: no streaming at all (pure latency chain)
-  constexpr int GS = 2;  // 4 was measured slower: longer waits and fewer free ring slots for the producer
+  constexpr int GS = 2;  // 16 KiB sub-stages per iteration; 4 was measured slower: longer waits, fewer free ring slots
+  constexpr int SPI = GS / SUB;  // ring stages per iteration (2 with 16 KiB stages, 1 with 32 KiB stages)
+  static_assert(SUB == 1 || SUB == GS, "stage geometry");
   const int KS = r.K / UNIT;
   const int units = r.rows * KS;
   const int nst = n_stages(r);
   const bool math = !(c.p->dbg & 1);
   const size_t woff = (size_t)c.warp * (UNIT * 2) + c.lane * 16;
-  for (int s = 0; s < nst; s += GS) {
-    const int ns = min(GS, nst - s);
+  for (int s = 0; s < nst; s += SPI) {
+    const int ns = min(SPI, nst - s);
     mark(c, T_GEMV);
 #pragma unroll
-    for (int g = 0; g < GS; ++g)
+    for (int g = 0; g < SPI; ++g)
       if (g < ns) mbar_wait(c, &c.ring.full[(c.q + g) % NSTAGES], ((c.q + g) / NSTAGES) & 1, 2);
     mark(c, T_WAIT);
     float acc[GS][R][2];
@@ -259,7 +268,8 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     if (math && !c.aborted) {
       const unsigned char* b[GS];
 #pragma unroll
-      for (int g = 0; g < GS; ++g) b[g] = c.ring.data + (size_t)((c.q + g) % NSTAGES) * STAGE_BYTES + woff;
+      for (int g = 0; g < GS; ++g)
+        b[g] = c.ring.data + (size_t)((c.q + g / SUB) % NSTAGES) * STAGE_BYTES + (size_t)(g % SUB) * 16384 + woff;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint4 w[GS];
@@ -290,8 +300,8 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     if (c.lane < 4) {
 #pragma unroll
       for (int g = 0; g < GS; ++g) {
-        const int u = (s + g) * NCW + c.warp;
-        if (g < ns && u < units) {
+        const int u = (s * SUB + g) * NCW + c.warp;
+        if (g < ns * SUB && u < units) {
 #pragma unroll
           for (int i = 0; i < R; ++i) part[((size_t)i * MAXU + u) * 4 + c.lane] = sum[g][i];
         }
@@ -300,7 +310,7 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     __syncwarp();
     if (c.lane == 0) {
 #pragma unroll
-      for (int g = 0; g < GS; ++g)
+      for (int g = 0; g < SPI; ++g)
         if (g < ns) mbar_arrive(&c.ring.empty[(c.q + g) % NSTAGES]);
     }
     c.q += ns;
@@ -1186,6 +1196,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
   const unsigned nonce0 = *reinterpret_cast<volatile unsigned*>(p.nonce);
   c.launch = (nonce0 % 0xfffffu) + 1u;
   c.aborted = false;
+  c.prof_on = (p.prof != nullptr) && threadIdx.x == 0;
   for (int i = 0; i < 12; ++i) c.t_acc[i] = 0;
   c.t_last = (p.prof != nullptr) ? (unsigned long long)clock64() : 0ull;
   const unsigned long long t_begin = c.t_last;
