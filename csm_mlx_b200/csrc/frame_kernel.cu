@@ -32,6 +32,9 @@ namespace csmb {
 constexpr int NCW = 8;                  // consumer warps
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int NTHREADS = (NCW + 1) * 32;
+#ifndef CSMB_FRAME_GS
+#define CSMB_FRAME_GS 2
+#endif
 #ifndef CSMB_FRAME_STAGE_KB
 #define CSMB_FRAME_STAGE_KB 32
 #endif
@@ -245,9 +248,9 @@ __device__ __forceinline__ int n_stages(const Range& r) {
 template <int R>
 __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float* part) {
   if (c.p->dbg & 8) return;  // timing experiment: no streaming at all (pure latency chain)
-  constexpr int GS = 2;  // 16 KiB sub-stages per iteration; 4 was measured slower: longer waits, fewer free ring slots
+  constexpr int GS = CSMB_FRAME_GS;  // 16 KiB sub-stages per iteration; 4 was measured slower: longer waits, fewer free ring slots
   constexpr int SPI = GS / SUB;  // ring stages per iteration (2 with 16 KiB stages, 1 with 32 KiB stages)
-  static_assert(SUB == 1 || SUB == GS, "stage geometry");
+  static_assert(GS % SUB == 0, "stage geometry");
   const int KS = r.K / UNIT;
   const int units = r.rows * KS;
   const int nst = n_stages(r);
