@@ -32,6 +32,9 @@ namespace csmb {
 constexpr int NCW = 8;                  // consumer warps
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int NTHREADS = (NCW + 1) * 32;
+#ifndef CSMB_FRAME_NAP
+#define CSMB_FRAME_NAP 40   // ns between probes of a tagged word (0 … 200 ns: within 1 %; two probes in flight: 2-3 % slower)
+#endif
 #ifndef CSMB_FRAME_GS
 #define CSMB_FRAME_GS 2
 #endif
@@ -217,7 +220,7 @@ __device__ __forceinline__ void probe_wait(Ctx& c, const uint2* word, unsigned t
   if (c.lane == 0 && !c.aborted) {
     unsigned spins = 0;
     while (ll_ld(word).y != tag) {
-      __nanosleep(40);
+      __nanosleep(CSMB_FRAME_NAP);
       if (!poll_continue(c, spins, 150)) break;
     }
   }
