@@ -1,8 +1,9 @@
 """Generates tests/golden/*.npz with the CPU oracle (run once, here; the files are committed).
 
-The reference ships no golden vectors and cannot be run in this image (mlx / mlx_lm / moshi_mlx are not
-installable), so these are ORACLE outputs; the oracle itself is pinned against the independent HF
-implementations in tests/test_oracle_vs_hf.py.  Inputs follow SURVEY.md §8d (cfg 1 prompt, seeds).
+The reference ships no golden vectors and cannot be run as shipped in this image (mlx / mlx_lm / moshi_mlx are not
+installable), so these are ORACLE outputs; the oracle itself is pinned against the reference's own modules run over
+an mlx stand-in (scripts/make_reference_golden.py -> tests/golden/reference_cfg1.npz) and, for the third-party
+pieces, against the independent HF implementations in tests/test_oracle_vs_hf.py.  Inputs follow SURVEY.md §8d (cfg 1 prompt, seeds).
 
     python scripts/make_golden.py
 """
