@@ -32,12 +32,14 @@ constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
 static int g_bf_min_kblocks = 4;   // split-K: at least this many 64-wide K blocks per CTA
 static int g_bf_pdl = 1;           // programmatic dependent launch on/off (debug)
 static int g_bf_max_ctas = 148;
+static int g_bf_dbg = 0;
 
 // ---------------------------------------------------------------------------------------------- GEMM
 struct GpArgs {
   float* part;  // [S][R][N] fp32 partials
   int R, N, K, RN, nstages, S;
   int* err;
+  int dbg;  // timing experiments only: bit 0 = no partial stores, bit 1 = no TMEM loads either (results are wrong)
 };
 
 // dynamic smem: [stage][ W 128x64 | Xhi RNx64 | Xlo RNx64 ] bf16, 1024-byte aligned tiles
@@ -140,8 +142,13 @@ k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
       for (int c0 = 0; c0 < RN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        if (n < a.N) {
+        if (a.dbg & 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        }
+        if (n < a.N && !(a.dbg & 1)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int r = r0 + c0 + j;
@@ -567,7 +574,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   int nstages = (int)(BF_SMEM_BUDGET / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, g_bf_dbg};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
@@ -651,6 +658,7 @@ using namespace csmb;
 
 extern "C" {
 
+void csmb_debug_set_fast_frame_flags(int flags) { g_bf_dbg = flags; }
 void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas) {
   if (min_kblocks >= BF_SIZING_MIN_KBLOCKS) g_bf_min_kblocks = min_kblocks;
   if (pdl >= 0) g_bf_pdl = pdl ? 1 : 0;

@@ -502,6 +502,34 @@ def _diverge():
     print(f"identical over 125 frames: {same} of 64; first differing frame of the others: {sorted(f for f in firsts if f is not None)}", flush=True)
 
 
+@section("epi")
+def _epi():
+    """What do the Linear epilogues of the fused chain cost?  (timing only: flags 1/3 produce wrong results)"""
+    from csm_mlx_b200 import _lib
+    from tests.workloads import prompt_ids
+    spec = SamplerSpec()
+    for B in (16, 64):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        for flags in (0, 1, 3, 0):
+            _lib.lib().csmb_debug_set_fast_frame_flags(flags)
+            st = LMState(model, B, max_len=64)
+            st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+            frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+            st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+            prev = frame
+            for _ in range(3):
+                prev = st.decode_frame_graphed(prev, spec)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                prev = st.decode_frame_graphed(prev, spec)
+            e1.record(); torch.cuda.synchronize()
+            print(f"B={B} flags={flags}: {e0.elapsed_time(e1) / 10:.2f} ms/frame-step", flush=True)
+            del st
+    _lib.lib().csmb_debug_set_fast_frame_flags(0)
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""
