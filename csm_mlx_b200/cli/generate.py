@@ -43,6 +43,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--input-audios", "-ia", nargs="*", default=None, help="List of audio files for context")
     p.add_argument("--input-texts", "-it", nargs="*", default=None, help="List of text transcripts for context")
     p.add_argument("--seed", type=int, default=None, help="Sampling seed (this implementation's Philox stream)")
+    p.add_argument("--synthetic-assets", action="store_true",
+                   help="offline smoke runs: seeded random-init CSM / Mimi weights and a stand-in text tokenizer instead "
+                        "of the Hugging Face assets (the output is noise)")
     return p
 
 
@@ -62,7 +65,16 @@ def main(argv: Optional[List[str]] = None) -> int:
     sampler = make_sampler(temp=args.temperature, top_p=args.top_p or 0.0, min_p=args.min_p or 0.0, top_k=args.top_k or -1,
                            min_tokens_to_keep=args.min_tokens_to_keep)           # cli/generate.py:168-174
     csm = CSM(csm_1b())
-    csm.load_weights(_resolve_weight(args.weight))
+    if args.synthetic_assets:
+        from .. import tokenizers
+        from ..mimi import Mimi
+        from ..random_init import random_csm_weights, random_mimi_weights
+
+        csm.load_weights(random_csm_weights())
+        tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+        tokenizers.set_audio_tokenizer(Mimi(32, device=csm.device).load_pytorch_weights(random_mimi_weights()))
+    else:
+        csm.load_weights(_resolve_weight(args.weight))
     if args.adapter is not None:
         load_adapters(csm, args.adapter)
     context = [Segment(speaker, text, None, audio)                                # cli/generate.py:186-189

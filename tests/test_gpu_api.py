@@ -1,4 +1,6 @@
 """End-to-end through the public csm_mlx API on the GPU (README.md:29-55 usage of the reference)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -149,3 +151,25 @@ def test_load_adapters_folds_lora_into_dense_weights(device, tmp_path):
     (d2 / "adapter_config.json").write_text(json.dumps({"fine_tune_type": "full"}))
     load_adapters(m, str(d2))
     assert float(m.parameters()["projection.weight"].float().abs().max()) == 0.0
+
+
+def test_cli_generate_end_to_end(tmp_path):
+    """`csm-mlx generate TEXT -o out.wav` (cli/generate.py:72-202) on synthetic assets, with one context segment read
+    back from a WAV file: a 24 kHz mono file of max_audio_length comes out."""
+    import subprocess
+    import sys
+
+    from csm_mlx_b200.utils import read_audio, write_audio
+    from tests.workloads import synthetic_audio
+
+    ctx = tmp_path / "ctx.wav"
+    write_audio(synthetic_audio(5, 1.0), ctx, 24000)
+    out = tmp_path / "out.wav"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "csm_mlx_b200.cli.generate", "Hello from Sesame.", "-o", str(out), "-l", "400",
+                        "--temp", "0.8", "-k", "50", "--seed", "3", "--synthetic-assets", "-is", "1", "-ia", str(ctx), "-it",
+                        "a context sentence"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Success! Audio saved to" in r.stdout
+    audio = read_audio(out, 24000)
+    assert audio.shape == (5 * 1920,) and bool(torch.isfinite(audio).all())
