@@ -530,6 +530,52 @@ def _epi():
     _lib.lib().csmb_debug_set_fast_frame_flags(0)
 
 
+@section("lanes")
+def _lanes():
+    """Do G independent groups of 64/G sequences, each a CUDA-graph replay of the fused chain on its own stream, beat
+    one group of 64?  (Every kernel of the chain is latency-bound, so concurrent chains might overlap.)"""
+    from tests.workloads import prompt_ids
+    spec = SamplerSpec()
+    for G in (1, 2, 4):
+        B = 64 // G
+        states, prevs, streams = [], [], [torch.cuda.Stream(dev) for _ in range(G)]
+        for gi in range(G):
+            prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + gi * B + i, 8 + i % 9), 0) for i in range(B)]
+            st = LMState(model, B, max_len=64)
+            st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+            frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+            st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+            prev = frame
+            for _ in range(2):
+                prev = st.decode_frame_graphed(prev, spec)
+            states.append(st); prevs.append(prev)
+        torch.cuda.synchronize()
+
+        def step_all():
+            for gi in range(G):
+                with torch.cuda.stream(streams[gi]):
+                    prevs[gi] = states[gi].decode_frame_graphed(prevs[gi], spec)
+
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream(dev))
+        for _ in range(2):
+            step_all()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in streams:
+            s.wait_event(e0)
+        n = 8
+        for _ in range(n):
+            step_all()
+        for s in streams:
+            torch.cuda.current_stream(dev).wait_stream(s)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"G={G} groups x B={B}: {ms:.2f} ms per step of all 64 sequences -> {64 * 0.08 / (ms / 1e3):.0f} audio-s/s", flush=True)
+        del states
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""
