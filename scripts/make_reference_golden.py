@@ -107,6 +107,14 @@ def record(model):
 
 
 def main():
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=25, help="greedy frames of BASELINE configs[0] to generate")
+    ap.add_argument("--check", action="store_true",
+                    help="do not write: compare with the committed fixture (tokens of the generated frames, RoPE tables, "
+                         "prompt / context rows, frame-0 logits, guard text) and exit non-zero on any difference")
+    args = ap.parse_args()
     model = build_model()
     out = {}
     # ---- RoPE tables as the reference builds them (attention.py:57-117), both head sizes of csm_1b
@@ -120,14 +128,15 @@ def main():
     # ---- BASELINE.json configs[0]: "[0]Hello from Sesame.", speaker 0, no context, greedy, 25 frames
     text_tok.table["[0]Hello from Sesame."] = cfg1_prompt_ids()
     rec = record(model)
-    ref_generation.generate(model, "Hello from Sesame.", 0, [], max_audio_length_ms=2000, temperature=0)
-    codes = mimi.decoded[-1]                                  # (1, 32, 25): mx.stack(samples).transpose(1, 2, 0)
+    ref_generation.generate(model, "Hello from Sesame.", 0, [], max_audio_length_ms=80 * args.frames, temperature=0)
+    codes = mimi.decoded[-1]                                  # (1, 32, F): mx.stack(samples).transpose(1, 2, 0)
     tokens = codes[0].t().contiguous()
-    assert tokens.shape == (25, 32), tokens.shape
+    assert tokens.shape == (args.frames, 32), tokens.shape
     out["tokens"] = tokens.numpy().astype(np.int32)
     out["h_last_f0"] = rec["h"][0][0].numpy().astype(np.float32)
     out["logits_f0"] = torch.cat([rec["c0"][0], *rec["ci"][:31]]).numpy().astype(np.float32)         # (32, 2051)
-    out["logits_f24"] = torch.cat([rec["c0"][24], *rec["ci"][24 * 31:25 * 31]]).numpy().astype(np.float32)
+    if args.frames >= 25:
+        out["logits_f24"] = torch.cat([rec["c0"][24], *rec["ci"][24 * 31:25 * 31]]).numpy().astype(np.float32)
     tp, mp = ref_tokenizers.tokenize_text_segment("Hello from Sesame.", 0)
     out["prompt_tokens"] = torch.as_tensor(tp).numpy().astype(np.int32)
     out["prompt_mask"] = torch.as_tensor(mp).numpy().astype(np.int32)
@@ -157,6 +166,17 @@ def main():
     except ValueError as e:
         out["too_long_message"] = np.array(str(e))
 
+    if args.check:
+        ref = np.load(os.path.join(OUT, "reference_cfg1.npz"))
+        bad = []
+        for k, v in out.items():
+            want = ref[k][: args.frames] if k == "tokens" else ref[k]
+            same = (str(v) == str(want)) if v.dtype.kind in "US" else (
+                np.array_equal(v, want) if v.dtype.kind in "iu" else np.allclose(v, want, rtol=0, atol=1e-6))
+            if not same:
+                bad.append(k)
+        print("check against the committed fixture:", "identical" if not bad else f"DIFFERENT: {bad}")
+        raise SystemExit(1 if bad else 0)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "reference_cfg1.npz"), **out)
     print("reference_cfg1.npz:", {k: getattr(v, "shape", None) for k, v in out.items()})

@@ -92,6 +92,22 @@ def test_prompt_rows_rope_tables_and_error_text_vs_reference(ref):
     assert str(e.value) == str(ref["too_long_message"])
 
 
+def test_fixture_is_reproducible_from_the_reference_tree():
+    """Where the reference tree is mounted (the build container), re-run the reference's own modules over the mlx
+    stand-in for 2 frames and compare everything with the committed fixture; skipped on the GPU box, which has no
+    /root/reference."""
+    import subprocess
+    import sys
+
+    if not os.path.isdir("/root/reference/csm_mlx"):
+        pytest.skip("no reference tree here")
+    root = os.path.dirname(GOLDEN.rstrip("/")).rsplit("/tests", 1)[0]
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "make_reference_golden.py"), "--frames", "2", "--check"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "identical" in r.stdout
+
+
 @pytest.mark.gpu
 def test_product_vs_reference_run(ref, model_1b, device):
     """The CUDA path against the reference's own run: 25 greedy frames token-exact, frame-0 hidden state and logits
