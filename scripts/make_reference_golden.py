@@ -62,6 +62,14 @@ class FakeMimi:
         self.decoded.append(torch.as_tensor(codes).clone())
         return mx.zeros((1, 1, 1920 * codes.shape[-1]))
 
+    def reset_state(self):
+        self.resets = getattr(self, "resets", 0) + 1
+
+    def decode_step(self, codes):
+        self.steps = getattr(self, "steps", [])
+        self.steps.append(torch.as_tensor(codes).clone())      # (1, K, 1) per frame
+        return mx.zeros((1, 1, 1920))
+
     def encode(self, audio):
         n = int(audio.shape[-1])
         t = -(-n // 1920)
@@ -71,7 +79,7 @@ class FakeMimi:
 
 text_tok, mimi = FakeTextTokenizer(), FakeMimi()
 ref_tokenizers.get_text_tokenizer = lambda: text_tok
-ref_tokenizers.get_audio_tokenizer = lambda n=32: mimi
+ref_tokenizers.get_audio_tokenizer = lambda n_audio_codebooks=32: mimi
 ref_generation.get_audio_tokenizer = ref_tokenizers.get_audio_tokenizer
 
 
@@ -157,6 +165,25 @@ def main():
     out["ctx_tokens"] = mimi.decoded[-1][0].t().contiguous().numpy().astype(np.int32)                 # (3, 32)
     out["ctx_new_ids"] = np.array(new_ids, dtype=np.int64)
     out["ctx_ids"] = np.array(ctx_ids, dtype=np.int64)
+
+    # ---- stream_generate (generation.py:181-258): one chunk per frame, codes handed to decode_step as (1, K, 1)
+    mimi.steps, mimi.resets = [], 0
+    chunks = list(ref_generation.stream_generate(model, "Hello from Sesame.", 0, [], max_audio_length_ms=240, temperature=0))
+    out["stream_chunks"] = np.array([len(chunks), int(chunks[0].shape[0]), mimi.resets], dtype=np.int64)
+    out["stream_tokens"] = torch.cat([c[0, :, 0][None] for c in mimi.steps]).numpy().astype(np.int32)      # (3, 32)
+
+    # ---- logits processors on codebook 0 with the c0 history (generation.py:44-49, 59-60): a +1e4 bias on token 123
+    seen = []
+
+    def bias(history, logits):
+        seen.append(tuple(torch.as_tensor(history).shape))
+        logits = torch.as_tensor(logits).clone()
+        logits[:, 123] += 1e4
+        return mx.array(logits)
+
+    ref_generation.generate(model, "Hello from Sesame.", 0, [], max_audio_length_ms=160, temperature=0, logits_processors=[bias])
+    out["bias_tokens"] = mimi.decoded[-1][0].t().contiguous().numpy().astype(np.int32)                 # (2, 32)
+    out["bias_history_shapes"] = np.array([list(s) + [0] * (3 - len(s)) for s in seen], dtype=np.int64)
 
     # ---- the guard of generation.py:131-137
     try:

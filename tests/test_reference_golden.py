@@ -92,6 +92,28 @@ def test_prompt_rows_rope_tables_and_error_text_vs_reference(ref):
     assert str(e.value) == str(ref["too_long_message"])
 
 
+def test_logits_processor_run_vs_reference(ref, oracle_1b):
+    """generation.py:44-49, 59-60: a codebook-0 logits processor (+1e4 on token 123) with the c0 history; the oracle
+    reproduces the reference's two frames and sees the same history shapes ((0,) then (1, B, 1))."""
+    seen = []
+
+    def bias(history, logits):
+        seen.append(tuple(history.shape))
+        logits = logits.clone()
+        logits[:, 123] += 1e4
+        return logits
+
+    tok = torch.from_numpy(ref["prompt_tokens"]).long()
+    mask = torch.from_numpy(ref["prompt_mask"]).bool()
+    toks = olm.generate_tokens(oracle_1b, tok, mask, 2, logits_processors=[bias])
+    assert np.array_equal(toks.numpy(), ref["bias_tokens"])
+    want = [tuple(int(x) for x in row[: (1 if i == 0 else 3)]) for i, row in enumerate(ref["bias_history_shapes"])]
+    assert seen == want
+    # stream_generate of the reference: one 1920-sample chunk per frame, the same tokens as generate(), state reset twice
+    assert ref["stream_chunks"].tolist() == [3, 1920, 2]
+    assert np.array_equal(ref["stream_tokens"], ref["tokens"][:3])
+
+
 def test_fixture_is_reproducible_from_the_reference_tree():
     """Where the reference tree is mounted (the build container), re-run the reference's own modules over the mlx
     stand-in for 2 frames and compare everything with the committed fixture; skipped on the GPU box, which has no
@@ -134,3 +156,11 @@ def test_product_vs_reference_run(ref, model_1b, device):
                        tokenizers.tokenize_text_segment(ref["ctx_new_ids"].tolist(), 0)[1]])
     (ctoks,) = generation.generate_tokens(model_1b, [(ctx, cmask)], 3, temperature=0.0)
     assert np.array_equal(ctoks.numpy(), ref["ctx_tokens"])
+
+    def bias(history, logits):
+        logits = logits.clone()
+        logits[:, 123] += 1e4
+        return logits
+
+    (btoks,) = generation.generate_tokens(model_1b, [(tok, mask)], 2, temperature=0.0, logits_processors=[bias])
+    assert np.array_equal(btoks.numpy(), ref["bias_tokens"])
