@@ -82,6 +82,8 @@ struct FrameParams {
   unsigned long long* prof;    // optional [gridDim][16] phase timers in SM cycles (debug); null in production
   // sampling
   float inv_temp;
+  int top_k;                   // 0 = off; else keep the k most likely tokens (ties included), like k_sample_filtered
+  float min_p;                 // 0 = off; else drop tokens whose probability is below min_p x the best one's
   uint32_t seed_lo, seed_hi;
   unsigned long long draw_base;
 };
@@ -505,13 +507,53 @@ __device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, un
     if (!poll_continue(c, spins, 400)) break;
   }
   mark(c, T_POLL);
+  // top-k / min-p (mlx_lm make_sampler as used by cli/generate.py:168-174): the same definition as k_sample_filtered —
+  // e_i = exp(logit_i - max), threshold = max(k-th largest e, min_p), tokens with e_i >= threshold stay.  The k-th
+  // largest e is found exactly by a 31-step bisection on its bit pattern (e >= 0 orders like an unsigned integer).
+  const bool filt = p.inv_temp != 0.f && (p.top_k > 0 || p.min_p > 0.f);
+  float ev[9];
+  float thresh = 0.f;
+  if (filt) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      if (c.tid + j * NCT < V) m = fmaxf(m, __uint_as_float(v[j].x));
+    m = warp_max(m);
+    if (c.lane == 0) c.sred[c.warp] = m;
+    csync();
+    m = c.sred[0];
+#pragma unroll
+    for (int w = 1; w < NCW; ++w) m = fmaxf(m, c.sred[w]);
+    csync();
+#pragma unroll
+    for (int j = 0; j < 9; ++j) ev[j] = (c.tid + j * NCT < V) ? expf(__uint_as_float(v[j].x) - m) : -1.f;
+    unsigned T = 0u;
+    if (p.top_k > 0) {
+      int* cnt = reinterpret_cast<int*>(c.sred + 2 * NCW);
+      for (int bit = 30; bit >= 0; --bit) {
+        const unsigned cand = T | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) n += (ev[j] >= 0.f && __float_as_uint(ev[j]) >= cand) ? 1 : 0;
+        n = __reduce_add_sync(0xffffffffu, n);
+        int* buf = cnt + (bit & 1) * NCW;
+        if (c.lane == 0) buf[c.warp] = n;
+        csync();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) tot += buf[w];
+        if (tot >= p.top_k) T = cand;
+      }
+    }
+    thresh = fmaxf(__uint_as_float(T), p.min_p);
+  }
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   const uint32_t dlo = (uint32_t)draw, dhi = (uint32_t)(draw >> 32);
 #pragma unroll
   for (int j = 0; j < 9; ++j) {
     const int i = c.tid + j * NCT;
-    if (i < V) {
+    if (i < V && !(filt && !(ev[j] >= thresh))) {
       float t = __uint_as_float(v[j].x);
       if (p.inv_temp != 0.f) t = t * p.inv_temp + gumbel_at(i, dlo, dhi, p.seed_lo, p.seed_hi);
       argmax_combine(bv, bi, t, i);
@@ -1282,8 +1324,9 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
                         D.d_ff == 8192 && B.d_ff == 8192 && m->n_codebooks <= 32 && m->n_codebooks >= 3 &&
                         m->audio_vocab <= 9 * NCT;
   if (!shape_ok) return CSMB_ERR_UNSUPPORTED;
-  if (sampler->temperature != 0.f && ((sampler->top_k > 0 && sampler->top_k < m->audio_vocab) ||
-                                     (sampler->top_p > 0.f && sampler->top_p < 1.f) || sampler->min_p > 0.f))
+  // fused samplers: greedy; temperature with optional top-k and / or min-p (min_keep 1).  top-p needs the sorted
+  // cumulative distribution and stays on the per-op path (csmb_decode_frame).
+  if (sampler->temperature != 0.f && ((sampler->top_p > 0.f && sampler->top_p < 1.f) || (sampler->min_p > 0.f && sampler->min_keep > 1)))
     return CSMB_ERR_UNSUPPORTED;
   CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m, device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1328,6 +1371,8 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   CSMB_REQUIRE(reinterpret_cast<uintptr_t>(f) <= reinterpret_cast<uintptr_t>(workspace) + workspace_bytes);
   // tags are 20-bit launch nonces + 12-bit phase numbers; the workspace must start zeroed (tag 0 is never produced)
   p.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
+  p.top_k = (sampler->top_k > 0 && sampler->top_k < m->audio_vocab) ? sampler->top_k : 0;
+  p.min_p = sampler->min_p > 0.f ? sampler->min_p : 0.f;
   p.seed_lo = (uint32_t)sampler->seed;
   p.seed_hi = (uint32_t)(sampler->seed >> 32);
   p.draw_base = draw_base;

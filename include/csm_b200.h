@@ -233,8 +233,8 @@ void csmb_debug_set_frame_batch_prof(unsigned long long* device_buf);
  * workspace must be zero-initialised once (csmb_frame_workspace_bytes; ~40 MB on B200: one private decoder-KV
  * copy per SM) and belongs to one sequence.
  * block_table: this sequence's row of the paged-KV table; pos: DEVICE int, position of this frame's backbone row.
- * Fused samplers: greedy, or temperature without top-k/top-p/min-p; anything else (and model shapes other than
- * csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
+ * Fused samplers: greedy, or temperature with optional top-k and / or min-p (min_keep 1); top-p (and model shapes other
+ * than csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
  * code if an internal wait timed out (all waits are bounded). */
 size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/, int device);
 /* debug: device buffer [n_sms][16] u64 that later csmb_frame_b1 launches fill with per-CTA phase timers (ns); null = off */

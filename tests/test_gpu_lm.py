@@ -265,3 +265,19 @@ def test_cfg2_full_length_two_implementations_agree(model_1b, monkeypatch):
     assert torch.equal(fused, again)
     assert torch.equal(fused, per_op)
     assert np.array_equal(fused.numpy()[:25], g["tokens"])
+
+
+@pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.9, top_k=50, seed=21), SamplerSpec(temperature=0.7, min_p=0.05, seed=22),
+                                  SamplerSpec(temperature=1.1, top_k=8, min_p=0.02, seed=23)])
+def test_fused_frame_kernel_topk_minp_equals_per_op_sampler(model_1b, monkeypatch, spec):
+    """top-k / min-p inside the persistent frame kernel (exact k-th-largest search by bisection on the bit pattern of
+    exp(logit - max)) selects exactly the tokens of the per-op sampler (k_sample_filtered: sorted probabilities), so
+    with the same Philox noise both paths generate the same frames (the README / CLI sampler, cli/generate.py:168-174)."""
+    from csm_mlx_b200.runtime import LMState
+
+    assert LMState(model_1b, 1, max_len=32).fused_supported(spec)
+    assert not LMState(model_1b, 1, max_len=32).fused_supported(SamplerSpec(temperature=0.9, top_p=0.9))
+    (fused,) = generation.generate_tokens(model_1b, [_prompt()], 6, sampler=spec)
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    (per_op,) = generation.generate_tokens(model_1b, [_prompt()], 6, sampler=spec)
+    assert torch.equal(fused, per_op)
