@@ -446,6 +446,8 @@ __global__ void __launch_bounds__(256) k_swiglu_split(PartIn gu, int F, size_t t
 }
 
 struct BfSample {
+  int top_k;       // 0 = off
+  float min_p;     // 0 = off
   float inv_temp;  // 0 => greedy
   uint32_t seed_lo, seed_hi;
   uint64_t draw_base;
@@ -473,11 +475,46 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
   if (a.inv_temp == 0.f) {
     tok = block_argmax(V, [&](int i) { return sl[i]; }, red_v, red_i);
   } else {
+    // top-k / min-p exactly as k_sample_filtered defines them: e_i = exp(logit_i - max), keep e_i >= max(k-th largest e,
+    // min_p); the k-th largest e by a 31-step bisection on its bit pattern (see sample_token in frame_kernel.cu)
+    float thresh = -1.f, m = 0.f;
+    if (a.top_k > 0 || a.min_p > 0.f) {
+      float mx = -INFINITY;
+      for (int i = threadIdx.x; i < V; i += 256) mx = fmaxf(mx, sl[i]);
+      mx = warp_max(mx);
+      if ((threadIdx.x & 31) == 0) red_v[threadIdx.x >> 5] = mx;
+      __syncthreads();
+      m = red_v[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red_v[w]);
+      __syncthreads();
+      unsigned T = 0u;
+      if (a.top_k > 0) {
+        for (int bit = 30; bit >= 0; --bit) {
+          const unsigned cand = T | (1u << bit);
+          int n = 0;
+          for (int i = threadIdx.x; i < V; i += 256) n += (__float_as_uint(expf(sl[i] - m)) >= cand) ? 1 : 0;
+          n = __reduce_add_sync(0xffffffffu, n);
+          if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = n;
+          __syncthreads();
+          int tot = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) tot += red_i[w];
+          __syncthreads();
+          if (tot >= a.top_k) T = cand;
+        }
+      }
+      thresh = fmaxf(__uint_as_float(T), a.min_p);
+    }
     const uint64_t draw = a.draw_base + (uint64_t)(row_pos ? row_pos[b] : 0) * a.draw_pos_mul;
     const uint32_t dlo = (uint32_t)draw, dhi = (uint32_t)(draw >> 32);
     tok = block_argmax(
-        V, [&](int i) { return sl[i] * a.inv_temp + gumbel_for(i, dlo, dhi, (uint32_t)b, a.seed_lo, a.seed_hi); }, red_v,
-        red_i);
+        V,
+        [&](int i) {
+          if (thresh >= 0.f && !(expf(sl[i] - m) >= thresh)) return -INFINITY;
+          return sl[i] * a.inv_temp + gumbel_for(i, dlo, dhi, (uint32_t)b, a.seed_lo, a.seed_hi);
+        },
+        red_v, red_i);
   }
   if (threadIdx.x == 0) frame[(size_t)b * ncb + cb] = tok;
   if (!embed) return;
@@ -647,7 +684,8 @@ static bool bf_supported(const csmb_model& m, const csmb_sampler& s) {
            L.n_heads % L.n_kv_heads == 0 && L.n_heads / L.n_kv_heads <= 8 && L.d_ff % 64 == 0 && L.d_ff % 4 == 0 &&
            L.n_heads * L.head_dim == L.d_model;
   };
-  const bool filtered = s.temperature != 0.f && ((s.top_k > 0 && s.top_k < m.audio_vocab) || (s.top_p > 0.f && s.top_p < 1.f) || s.min_p > 0.f);
+  // fused samplers: greedy; temperature with optional top-k and / or min-p (min_keep 1); top-p stays on the per-op path
+  const bool filtered = s.temperature != 0.f && ((s.top_p > 0.f && s.top_p < 1.f) || (s.min_p > 0.f && s.min_keep > 1));
   return llama_ok(b) && llama_ok(d) && b.d_model == 2048 && m.audio_vocab <= 8192 && m.n_codebooks >= 2 && !filtered &&
          s.temperature >= 0.f;
 }
@@ -689,6 +727,8 @@ int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* bt, const int3
   const int dec_pages = cdiv(ncb, CSMB_PAGE);
   BfSample sa;
   sa.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
+  sa.top_k = (sampler->top_k > 0 && sampler->top_k < V) ? sampler->top_k : 0;
+  sa.min_p = sampler->min_p > 0.f ? sampler->min_p : 0.f;
   sa.seed_lo = (uint32_t)sampler->seed;
   sa.seed_hi = (uint32_t)(sampler->seed >> 32);
   sa.draw_pos_mul = (uint32_t)ncb;

@@ -193,8 +193,8 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
  * Launches are chained with programmatic dependent launch, so weight streaming continues across kernel boundaries.
  * Same argument meaning as csmb_decode_frame (b->workspace is not used); workspace = csmb_decode_frame_fast_workspace_bytes
  * bytes, 256-byte aligned, zeroed once by its owner (first int = sticky error flag of the bounded waits).
- * Fused samplers: greedy, or temperature without top-k/top-p/min-p; otherwise (or for unsupported model shapes)
- * returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  csmb_decode_frame_fast_supported returns 1/0 up front. */
+ * Fused samplers: greedy, or temperature with optional top-k and / or min-p (min_keep 1); top-p (or an unsupported
+ * model shape) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  csmb_decode_frame_fast_supported returns 1/0 up front. */
 size_t csmb_decode_frame_fast_workspace_bytes(const csmb_model* m /*host*/, int batch);
 int csmb_decode_frame_fast_supported(const csmb_model* m /*host*/, const csmb_sampler* sampler /*host*/);
 int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,

@@ -210,7 +210,8 @@ def test_batch64_fused_chain_matches_single(model_1b):
         assert torch.equal(single, batched[i]), i
 
 
-@pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.0), SamplerSpec(temperature=0.8, seed=5)])
+@pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.0), SamplerSpec(temperature=0.8, seed=5),
+                                  SamplerSpec(temperature=0.9, top_k=50, seed=7), SamplerSpec(temperature=0.9, top_k=20, min_p=0.03, seed=8)])
 def test_fused_chain_equals_per_op_batched_path(model_1b, monkeypatch, spec):
     """Same batch through csmb_decode_frame_fast and through the per-op csmb_decode_frame (CSMB_DISABLE_FAST=1):
     identical tokens, greedy and with in-kernel Gumbel/Philox temperature sampling."""
@@ -223,15 +224,16 @@ def test_fused_chain_equals_per_op_batched_path(model_1b, monkeypatch, spec):
 
 
 def test_fused_chain_filtered_sampler_falls_back(model_1b):
-    """top-k is not fused: the batched path must route to the per-op frame (csmb_decode_frame) and still work."""
+    """top-p is not fused: the batched path must route to the per-op frame (csmb_decode_frame) and still work."""
     from csm_mlx_b200.runtime import LMState
 
     st = LMState(model_1b, 3, max_len=32)
     assert st.fast_supported(SamplerSpec(temperature=0.0))
     assert st.fast_supported(SamplerSpec(temperature=0.7))
-    assert not st.fast_supported(SamplerSpec(temperature=0.7, top_k=50))
+    assert st.fast_supported(SamplerSpec(temperature=0.7, top_k=50))
+    assert not st.fast_supported(SamplerSpec(temperature=0.7, top_p=0.9))
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(70 + i, 7), 0) for i in range(3)]
-    toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, top_k=50, seed=3))
+    toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, top_p=0.9, seed=3))
     assert all(t.shape == (2, 32) for t in toks)
 
 
