@@ -283,3 +283,22 @@ def test_fused_frame_kernel_topk_minp_equals_per_op_sampler(model_1b, monkeypatc
     monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
     (per_op,) = generation.generate_tokens(model_1b, [_prompt()], 6, sampler=spec)
     assert torch.equal(fused, per_op)
+
+
+def test_near_maximum_context_fused_equals_per_op(model_1b, monkeypatch):
+    """Edge of the position range (2 048, attention.py:38): a 2 030-row prompt (prefill through the tensor-core linear in
+    row tiles, 127 KV pages) followed by 6 frames up to position 2 036 — the frame kernel's 16-chunk attention + merge
+    against the per-op kernels, token for token; one more frame than the window allows is refused like the reference."""
+    gen = torch.Generator().manual_seed(77)
+    t1 = olm.text_rows(prompt_ids(9, 10))
+    a1 = olm.audio_rows(torch.randint(0, 2048, (32, 2005), generator=gen))
+    t2 = olm.text_rows(prompt_ids(10, 10))
+    tok = torch.cat([t1[0], a1[0], t2[0]]).int()
+    mask = torch.cat([t1[1], a1[1], t2[1]])
+    assert tok.shape[0] == 2030
+    (fused,) = generation.generate_tokens(model_1b, [(tok, mask)], 6, temperature=0.0)
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    (per_op,) = generation.generate_tokens(model_1b, [(tok, mask)], 6, temperature=0.0)
+    assert fused.shape == (6, 32) and torch.equal(fused, per_op)
+    with pytest.raises(ValueError, match="Inputs too long"):
+        generation.generate_tokens(model_1b, [(tok, mask)], 18, temperature=0.0)
