@@ -173,3 +173,12 @@ def test_cli_generate_end_to_end(tmp_path):
     assert "Success! Audio saved to" in r.stdout
     audio = read_audio(out, 24000)
     assert audio.shape == (5 * 1920,) and bool(torch.isfinite(audio).all())
+
+
+def test_zero_length_request_returns_empty_audio(model_1b, mimi_gpu, capsys):
+    """max_audio_length_ms below one frame: no frame is generated, the warning of generation.py:163-165 is printed and
+    a (0,) float32 array comes back; stream_generate yields nothing."""
+    out = generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=79, temperature=0.0)
+    assert out.shape == (0,) and out.dtype == torch.float32
+    assert "No samples generated" in capsys.readouterr().out
+    assert list(stream_generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=79, temperature=0.0)) == []
