@@ -83,6 +83,8 @@ _SIGS = {
     "csmb_decode_frame_fast_supported": (C.c_int, [C.POINTER(Model), C.POINTER(Sampler)]),
     "csmb_decode_frame_fast": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
                                          C.c_uint64, _P, C.c_size_t, _I, _P]),
+    "csmb_decode_frame_fast_admit": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
+                                               C.c_uint64, _P, _P, _P, C.c_size_t, _I, _P]),
     "csmb_debug_set_fast_frame": (None, [_I, _I, _I]),
     "csmb_debug_set_fast_frame_flags": (None, [_I]),
     "csmb_frame_batch_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I, _I]),

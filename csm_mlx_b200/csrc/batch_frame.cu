@@ -250,7 +250,9 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
 __global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restrict__ prev, const uint16_t* __restrict__ audio_emb,
                                                           int ncb, int V, int d, float* __restrict__ x,
                                                           const float* __restrict__ w, float eps,
-                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                          const float* __restrict__ x_override,
+                                                          const uint8_t* __restrict__ use_override) {
   __shared__ float red[8];
   pdl_launch_dependents();
   pdl_wait();
@@ -258,7 +260,14 @@ __global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restr
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int s = 0; s < ncb; ++s) {
+  // a sequence admitted this step: its input row is the (already embedded) last row of its prompt, not a previous frame
+  const bool over = use_override != nullptr && use_override[b] != 0;
+  if (over) {
+    const float4 a0 = *reinterpret_cast<const float4*>(x_override + (size_t)b * d + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(x_override + (size_t)b * d + c + 4);
+    acc[0] = a0.x; acc[1] = a0.y; acc[2] = a0.z; acc[3] = a0.w; acc[4] = a1.x; acc[5] = a1.y; acc[6] = a1.z; acc[7] = a1.w;
+  }
+  for (int s = 0; s < (over ? 0 : ncb); ++s) {
     int t = prev[(size_t)b * ncb + s];
     t = t < 0 ? 0 : (t >= V ? V - 1 : t);
     const uint4 q = *reinterpret_cast<const uint4*>(audio_emb + ((size_t)t + (size_t)s * V) * d + c);
@@ -715,7 +724,16 @@ int csmb_decode_frame_fast_supported(const csmb_model* m, const csmb_sampler* sa
 int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* prev_frame, const int32_t* pos,
                            int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
                            size_t workspace_bytes, int device, void* stream) {
+  return csmb_decode_frame_fast_admit(m, bt, prev_frame, pos, frame, sampler, draw_base, nullptr, nullptr, workspace,
+                                      workspace_bytes, device, stream);
+}
+
+int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, const int32_t* prev_frame, const int32_t* pos,
+                                 int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, const float* x_override,
+                                 const uint8_t* use_override, void* workspace, size_t workspace_bytes, int device,
+                                 void* stream) {
   CSMB_ENTER(device);
+  CSMB_REQUIRE((x_override == nullptr) == (use_override == nullptr));
   CSMB_REQUIRE(m && bt && prev_frame && pos && frame && sampler && workspace && bt->batch > 0);
   CSMB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   if (!bf_supported(*m, *sampler)) return CSMB_ERR_UNSUPPORTED;
@@ -738,7 +756,7 @@ int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* bt, const int3
 
   // ---- backbone step (generation.py:34-42 with T = 1)
   CSMB_CUDA(bf_launch(k_frame_embed_norm, dim3(B), dim3(256), 0, st, prev_frame, m->audio_emb, ncb, V, db, w.x, Bk.norm_in[0],
-                      Bk.eps, w.hi, w.lo));
+                      Bk.eps, w.hi, w.lo, x_override, use_override));
   if ((rc = bf_layers(w, Bk, w.x, bt->kv_pool, bt->kv_layer_stride, bt->block_table, bt->max_pages, pos, 0, 1, B, w.h_last, st)))
     return rc;
   if ((rc = bf_gemm(w, m->c0_head, B, V, db, &part, st))) return rc;

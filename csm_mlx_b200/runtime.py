@@ -208,7 +208,7 @@ class LMState:
         self._check_room()
         bd = self._batch_desc()
         s = sampler.to_c()
-        if self.persist_supported(sampler):
+        if self.persist_supported(sampler) and not getattr(self, "_ovr_armed", False):
             if getattr(self, "_persist_ws", None) is None:
                 nbytes = _lib.lib().csmb_frame_batch_workspace_bytes(C.byref(self.model.desc()), self.batch, self.dev_idx)
                 self._persist_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # barrier counters + error flag
@@ -219,19 +219,91 @@ class LMState:
             if getattr(self, "_fast_ws", None) is None:
                 nbytes = _lib.lib().csmb_decode_frame_fast_workspace_bytes(C.byref(self.model.desc()), self.batch)
                 self._fast_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # sticky error flag inside
-            _lib.check(_lib.lib().csmb_decode_frame_fast(
+            self._override_buffers()
+            _lib.check(_lib.lib().csmb_decode_frame_fast_admit(
                 C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
-                C.byref(s), 0, self._fast_ws.data_ptr(), self._fast_ws.numel(), self.dev_idx, self._stream()))
+                C.byref(s), 0, self._ovr_x.data_ptr(), self._ovr_flag.data_ptr(), self._fast_ws.data_ptr(),
+                self._fast_ws.numel(), self.dev_idx, self._stream()))
         else:
             _lib.check(_lib.lib().csmb_decode_frame(
                 C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
                 C.byref(s), 0, self.dev_idx, self._stream()))
         self._advance()
 
+    # ------------------------------------------------------------------ admission into a running batch (fused chain)
+    def _override_buffers(self) -> None:
+        if getattr(self, "_ovr_x", None) is None:
+            d = self.model.backbone.args.hidden_size
+            self._ovr_x = torch.zeros((self.batch, d), device=self.device, dtype=torch.float32)
+            self._ovr_flag = torch.zeros((self.batch,), device=self.device, dtype=torch.uint8)
+
+    def prefill_rows(self, slots: Sequence[int], tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
+        """Backbone over the given rows of the given sequence slots only (KV append at their current positions); the other
+        sequences are untouched.  generation.py:34-42 restricted to some sequences."""
+        lens = [int(t.shape[0]) for t in tokens]
+        R = sum(lens)
+        if R == 0:
+            return
+        for s, n in zip(slots, lens):
+            if self.pos_host[s] + n > self.max_len:
+                raise ValueError("sequence exceeds the KV pages reserved for it")
+        nb = dict(non_blocking=True)
+        tok = torch.cat([t.to(torch.int32) for t in tokens], 0).contiguous().to(self.device, **nb)
+        msk = torch.cat([m.to(torch.uint8) for m in masks], 0).contiguous().to(self.device, **nb)
+        seq = torch.cat([torch.full((n,), s, dtype=torch.int32) for s, n in zip(slots, lens)]).to(self.device, **nb)
+        pos = torch.cat([torch.arange(self.pos_host[s], self.pos_host[s] + n, dtype=torch.int32)
+                         for s, n in zip(slots, lens)]).to(self.device, **nb)
+        ends, acc = [], 0
+        for n in lens:
+            acc += n
+            ends.append(max(acc - 1, 0))
+        live = [i for i, n in enumerate(lens) if n > 0]
+        last = torch.tensor([ends[i] for i in live], dtype=torch.int32).to(self.device, **nb)
+        b = self.model.backbone.args
+        h_tmp = torch.empty((len(live), b.hidden_size), device=self.device, dtype=torch.float32)
+        lg_tmp = torch.empty((len(live), self.model.n_audio_vocab), device=self.device, dtype=torch.float32)
+        self._ensure_workspace(max(R, 2 * self.batch))
+        bd = self._batch_desc()
+        _lib.check(_lib.lib().csmb_backbone_forward(
+            C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
+            last.data_ptr(), len(live), h_tmp.data_ptr(), lg_tmp.data_ptr(), self.dev_idx, self._stream()))
+        for s, n in zip(slots, lens):
+            self.pos_host[s] += n
+
+    def arm_admission(self, slots: Sequence[int], tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
+        """Prepare the next fused-chain step so that the sequences in ``slots`` start from their prompts ((T, 33) rows
+        each) while every other slot decodes normally: rows 0..T-2 are prefilled now, the embedded last row becomes the
+        slot's backbone input of the step (csmb_decode_frame_fast_admit) and its position is set to T-1."""
+        self._override_buffers()
+        ncb = self.model.n_audio_codebooks
+        for s in slots:
+            self.pos_host[s] = 0
+        self.prefill_rows(slots, [t[:-1] for t in tokens], [m[:-1] for m in masks])
+        n = len(slots)
+        last_tok = torch.stack([t[-1].to(torch.int32) for t in tokens]).contiguous().to(self.device)
+        last_msk = torch.stack([m[-1].to(torch.uint8) for m in masks]).contiguous().to(self.device)
+        d = self.model.backbone.args.hidden_size
+        emb = torch.empty((n, d), device=self.device, dtype=torch.float32)
+        _lib.check(_lib.lib().csmb_embed_sum(
+            last_tok.data_ptr(), last_msk.data_ptr(), self.model.text_embeddings.weight.data_ptr(),
+            self.model.audio_embeddings.weight.data_ptr(), emb.data_ptr(), n, d, ncb, self.model.n_audio_vocab,
+            self.dev_idx, self._stream()))
+        idx = torch.tensor(list(slots), dtype=torch.long, device=self.device)
+        self._ovr_x.index_copy_(0, idx, emb)
+        self._ovr_flag.index_fill_(0, idx, 1)
+        self.pos.index_copy_(0, idx, torch.tensor([self.pos_host[s] for s in slots], dtype=torch.int32, device=self.device))
+        self._ovr_armed = True
+
+    def disarm_admission(self) -> None:
+        if getattr(self, "_ovr_armed", False):
+            self._ovr_flag.zero_()
+            self._ovr_armed = False
+
     def decode_frame_graphed(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
         """decode_frame through a CUDA graph captured on first use (fixed buffers; positions live on the device
         and advance inside the graph).  Returns a fresh (B, n_codebooks) int32 tensor."""
-        path = "persist" if self.persist_supported(sampler) else ("chain" if self.fast_supported(sampler) else "per-op")
+        armed = getattr(self, "_ovr_armed", False)  # admission overrides exist only on the chain
+        path = "persist" if (self.persist_supported(sampler) and not armed) else ("chain" if self.fast_supported(sampler) else "per-op")
         key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep, sampler.seed,
                path)
         if getattr(self, "_graph_key", None) != key:

@@ -9,8 +9,11 @@ libcsm_b200.so through ``runtime.LMState`` (prefill / mixed steps on the per-op 
 fused kernel chain replayed as a CUDA graph) and ``mimi.Mimi``.
 
 * ``Engine``: ``submit()`` queues a request, ``step()`` generates one frame for every occupied slot and admits queued
-  requests into free slots (their prompt rows are prefilled in the same backbone pass in which the running sequences
-  take their one-row step), ``run()`` drains everything.  EOS (an all-zero frame, generation.py:151-152) and the
+  requests into free slots — on the fused chain all but the last prompt row of a new request are prefilled on the side
+  and that last row is the slot's input of the very step in which the running sequences decode
+  (``csmb_decode_frame_fast_admit``), so admission never stalls the batch; with samplers the chain does not fuse, the
+  prompts are prefilled in one mixed per-op backbone pass together with the running sequences' rows —, ``run()``
+  drains everything.  EOS (an all-zero frame, generation.py:151-152) and the
   frame budget are checked on pinned host copies one step late, so the GPU never waits for Python; a finished
   sequence frees its slot, whose KV pages are simply overwritten by the next occupant.
 * ``ContextCache``: Mimi codes of context audio keyed by content, so a conversation's segments are encoded once
@@ -107,7 +110,7 @@ class Engine:
         self._host = [torch.empty((self.B, self.ncb), dtype=torch.int32).pin_memory() for _ in range(2)]
         self._events = [torch.cuda.Event() for _ in range(2)]
         self._flip = 0
-        self.steps = self.mixed_steps = 0
+        self.steps = self.mixed_steps = self.admissions = 0
 
     # ------------------------------------------------------------------ requests
     def build_prompt(self, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -150,7 +153,23 @@ class Engine:
         if self.active == 0 and not admit:
             newly_done += self._drain()
             return newly_done
-        if admit or self._prev is None:
+        if st.fast_supported(self.spec):
+            # fused chain: admitted requests prefill all but their last prompt row now; that row is their input of this
+            # step, in which everybody else decodes (csmb_decode_frame_fast_admit) — admission never stalls the batch
+            if admit:
+                reqs = []
+                for b in admit:
+                    r = self.queue.popleft()
+                    r.slot = b
+                    self.slots[b] = r
+                    reqs.append(r)
+                st.arm_admission(admit, [r.tokens for r in reqs], [r.mask for r in reqs])
+                self.admissions += len(admit)
+            self._park_idle_slots()
+            prev = self._prev if self._prev is not None else torch.zeros((self.B, self.ncb), device=st.device, dtype=torch.int32)
+            frame = st.decode_frame_graphed(prev, self.spec)
+            st.disarm_admission()
+        elif admit or self._prev is None:
             frame = self._mixed_step(admit)
         else:
             self._park_idle_slots()

@@ -200,6 +200,15 @@ int csmb_decode_frame_fast_supported(const csmb_model* m /*host*/, const csmb_sa
 int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
                            int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
                            size_t workspace_bytes, int device, void* stream);
+/* csmb_decode_frame_fast with admission: for sequences b with use_override[b] != 0 (DEVICE uint8 [batch]) the backbone input
+ * row is x_override[b] (DEVICE fp32 [batch][d_backbone]) — the already embedded LAST row of a prompt whose earlier rows
+ * were run through csmb_backbone_forward — instead of the embedding of prev_frame[b].  This is how a serving loop admits a
+ * new request into a free slot in the same step in which the running sequences decode (generation.py:34-42 for T > 1 is
+ * split into rows 0..T-2 and the causal last row).  Both pointers null = csmb_decode_frame_fast. */
+int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
+                                 int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, const float* x_override,
+                                 const uint8_t* use_override, void* workspace, size_t workspace_bytes, int device,
+                                 void* stream);
 /* tuning: minimum 64-wide K blocks per split-K CTA (>= 1), programmatic dependent launch on/off (-1 = keep),
    CTA budget per Linear (0 = keep) of later csmb_decode_frame_fast calls */
 void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas);

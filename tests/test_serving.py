@@ -58,7 +58,7 @@ def test_engine_continuous_batching_matches_single(model_1b, mimi_gpu):
     rids += [eng.submit(ids, spk, [], max_audio_length_ms=80 * f) for ids, spk, f in reqs[6:]]   # arrivals mid-flight
     eng.run()
     assert eng.active == 0 and not eng.queue
-    assert 0 < eng.mixed_steps < eng.steps          # admissions used mixed steps, steady state the graphed chain
+    assert eng.mixed_steps == 0 and eng.admissions == 9 and eng.steps >= 10   # admissions ride on the graphed chain
     for rid, (ids, spk, f) in zip(rids, reqs):
         (single,) = generation.generate_tokens(model_1b, [tokenizers.tokenize_text_segment(ids, spk)], f, temperature=0.0)
         assert torch.equal(single, eng.tokens(rid)), rid
@@ -141,3 +141,16 @@ def test_cfg4_full_size_engine_vs_single(model_1b, mimi_gpu, device):
         worst = max(worst, margin)
         assert margin < 2e-4 and below_max < 2e-4, (i, f, c, margin, below_max)
     assert identical >= 36, identical
+
+
+@pytest.mark.gpu
+def test_engine_falls_back_to_mixed_steps_for_unfused_samplers(model_1b, mimi_gpu):
+    """top-p is not fused into the chain: admissions then go through the mixed per-op backbone pass and steady-state
+    steps through the per-op frame; the engine still serves every request for its full frame budget."""
+    from csm_mlx_b200.runtime import SamplerSpec
+
+    eng = serving.Engine(model_1b, max_batch=2, max_len=96, sampler=SamplerSpec(temperature=0.8, top_p=0.9, seed=4))
+    rids = [eng.submit(prompt_ids(200 + i, 6 + i), 0, [], max_audio_length_ms=80 * (2 + i)) for i in range(3)]
+    eng.run()
+    assert eng.mixed_steps > 0 and eng.admissions == 0
+    assert [tuple(eng.tokens(r).shape) for r in rids] == [(2, 32), (3, 32), (4, 32)]
