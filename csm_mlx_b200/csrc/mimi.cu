@@ -309,17 +309,19 @@ __global__ void __launch_bounds__(128) k_mimi_attention(const float* __restrict_
   sum = warp_sum(sum);
   __syncwarp();
   float a0 = 0.f, a1 = 0.f;
-  for (int j0 = 0; j0 < S; j0 += 8) {  // eight independent loads in flight (the keys are L2-resident, not L1)
-    float v0[8], v1[8];
+  constexpr int PG = 32;  // keys per group: 2 x PG independent loads in flight (the values are L2-resident, not L1), so a
+                          // 250-key window costs 8 L2 round trips instead of 32; the accumulation order stays j ascending
+  for (int j0 = 0; j0 < S; j0 += PG) {
+    float v0[PG], v1[PG];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < PG; ++u) {
       const int j = min(j0 + u, S - 1);
       const float* vp = cb + (size_t)((first + j) % cap) * 2 * H * 64 + H * 64 + h * 64;
       v0[u] = vp[lane];
       v1[u] = vp[lane + 32];
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < PG; ++u)
       if (j0 + u < S) {
         const float p = sc[j0 + u];
         a0 = fmaf(p, v0[u], a0);
