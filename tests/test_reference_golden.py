@@ -130,6 +130,22 @@ def test_fixture_is_reproducible_from_the_reference_tree():
     assert "identical" in r.stdout
 
 
+def test_live_reference_vs_oracle_on_small_models():
+    """Where the reference tree is mounted: six random small checkpoints with ragged text / audio / EOS-row prompts, six
+    greedy frames each through the reference's own generate_frame (over the mlx stand-in) and through the oracle —
+    identical tokens, frame-0 logits within 2e-5 (scripts/reference_live_check.py)."""
+    import subprocess
+    import sys
+
+    if not os.path.isdir("/root/reference/csm_mlx"):
+        pytest.skip("no reference tree here")
+    root = GOLDEN.rsplit("/tests", 1)[0]
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "reference_live_check.py"), "6"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "reference == oracle" in r.stdout
+
+
 @pytest.mark.gpu
 def test_product_vs_reference_run(ref, model_1b, device):
     """The CUDA path against the reference's own run: 25 greedy frames token-exact, frame-0 hidden state and logits
