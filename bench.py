@@ -90,6 +90,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def oracle_sample(orc, mimi_w, prompt, frames: int) -> float:
     """Seconds for prefill + `frames` greedy frames + streaming Mimi decode of them with the CPU oracle."""
     from oracle import lm as olm, mimi as omimi
@@ -128,7 +138,7 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "sample": sample, "sampling": "greedy",
                    "note": "reference dependencies (mlx, mlx_lm, moshi_mlx) are not installable here; this is the "
                            "oracle port of the reference path in PyTorch CPU fp32 on all host cores"},
-        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": torch.get_num_threads(), "cpu_model": cpu_model(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -418,7 +428,7 @@ def run_ours(args):
         oracle_sample(orc, mw, cfg1_prompt_ids(), 1)
         nfr = args.ref_frames
         tc = oracle_sample(orc, mw, cfg1_prompt_ids(), nfr)
-        cpu = {"value": nfr * FRAME_S / tc, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": nfr * FRAME_S / tc, "unit": "audio-s/s", "cores": torch.get_num_threads(), "cpu_model": cpu_model(), "kind": "port",
                "sample": f"prefill(10 rows) + {nfr} greedy frames + Mimi streaming decode, oracle PyTorch-CPU fp32 "
                          f"({tc:.2f} s)"}
 
