@@ -41,6 +41,15 @@ constexpr int NTHREADS = (NCW + 1) * 32;
 #ifndef CSMB_FRAME_STAGE_KB
 #define CSMB_FRAME_STAGE_KB 32
 #endif
+// consume(): ring slots are handed back as soon as the stage's bytes are in registers, before the lane reduction
+// (-1.5 % per frame), and the first butterfly step is a transposing exchange (half the shuffles, bit-identical sums;
+// -0.3 %).  0 restores the older order for A/B runs (scripts/variant_ab.py).
+#ifndef CSMB_FRAME_EARLY_ARRIVE
+#define CSMB_FRAME_EARLY_ARRIVE 1
+#endif
+#ifndef CSMB_FRAME_XPOSE
+#define CSMB_FRAME_XPOSE 1
+#endif
 // ring geometry: 4 x 32 KiB (default; measured 3.30 ms per frame) or 8 x 16 KiB (3.52 ms: twice the mbarrier handshakes
 // and bulk copies per byte)
 constexpr int STAGE_BYTES = CSMB_FRAME_STAGE_KB * 1024;
@@ -299,6 +308,41 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     for (int g = 0; g < GS; ++g)
 #pragma unroll
       for (int i = 0; i < R; ++i) sum[g][i] = acc[g][i][0] + acc[g][i][1];
+#if CSMB_FRAME_EARLY_ARRIVE
+    // the stage's bytes are in registers (the sums above depend on every load): hand the ring slots back before the
+    // lane reduction so that the producer's next bulk copy overlaps it
+#pragma unroll
+    for (int g = 0; g < GS; ++g)
+#pragma unroll
+      for (int i = 0; i < R; ++i) asm volatile("" ::"f"(sum[g][i]));
+    __syncwarp();
+    if (c.lane == 0) {
+#pragma unroll
+      for (int g = 0; g < SPI; ++g)
+        if (g < ns) mbar_arrive(&c.ring.empty[(c.q + g) % NSTAGES]);
+    }
+#endif
+#if CSMB_FRAME_XPOSE && CSMB_FRAME_GS == 2
+    // transposing first step: the lower half-warp keeps unit 0, the upper half unit 1 (same additions, commuted, as the
+    // plain butterfly: bit-identical partials), then two steps on one value instead of two
+    {
+      const bool up = (c.lane & 16) != 0;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float keep = up ? sum[1][i] : sum[0][i], give = up ? sum[0][i] : sum[1][i];
+        float v = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        sum[0][i] = v;
+      }
+      const int g = c.lane >> 4;
+      const int u = (s * SUB + g) * NCW + c.warp;
+      if ((c.lane & 12) == 0 && g < ns * SUB && u < units) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) part[((size_t)i * MAXU + u) * 4 + (c.lane & 3)] = sum[0][i];
+      }
+    }
+#else
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1)
 #pragma unroll
@@ -315,12 +359,15 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
         }
       }
     }
+#endif
+#if !CSMB_FRAME_EARLY_ARRIVE
     __syncwarp();
     if (c.lane == 0) {
 #pragma unroll
       for (int g = 0; g < SPI; ++g)
         if (g < ns) mbar_arrive(&c.ring.empty[(c.q + g) % NSTAGES]);
     }
+#endif
     c.q += ns;
   }
 }
