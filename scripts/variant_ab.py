@@ -42,6 +42,10 @@ print("RESULT", os.environ.get("CSMB_LIB_PATH"), "golden25", ok, " ".join(f"{r:.
 
 for lib in sys.argv[1:]:
     env = dict(os.environ, CSMB_LIB_PATH=os.path.abspath(lib))
-    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
+    try:  # a variant that hangs must not eat the GPU budget: the frame kernel's own bounded waits give up after ~2 s
+        r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=150)
+    except subprocess.TimeoutExpired:
+        print(f"TIMEOUT {lib}", flush=True)
+        continue
     out = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
     print(out[0] if out else f"FAILED {lib}: {r.stderr[-800:]}", flush=True)
