@@ -167,24 +167,35 @@ def other_configs(model, mimi, dev):
         return a.elapsed_time(b) / n, r
 
     # configs[3]: 64 independent utterances in lock-step on one GPU (request batching; tcgen05 linears)
-    B = 64
-    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
-    st = LMState(model, B, max_len=64)
-    t_pre, _ = timed(lambda: st.prefill([p[0] for p in prompts], [p[1] for p in prompts]))
-    frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
-    st.sample_c0(frame, spec)
-    st.depth_decode(frame, spec)
-    state = {"f": frame}
-    for _ in range(3):
-        state["f"] = st.decode_frame_graphed(state["f"], spec)
+    def batch_step(B):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        st = LMState(model, B, max_len=64)
+        t_pre, _ = timed(lambda: st.prefill([p[0] for p in prompts], [p[1] for p in prompts]))
+        frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(frame, spec)
+        st.depth_decode(frame, spec)
+        state = {"f": frame}
+        for _ in range(3):
+            state["f"] = st.decode_frame_graphed(state["f"], spec)
 
-    def step():
-        state["f"] = st.decode_frame_graphed(state["f"], spec)
-    t_step, _ = timed(step, 10)
+        def step():
+            state["f"] = st.decode_frame_graphed(state["f"], spec)
+        t_step, _ = timed(step, 10)
+        st.check_status()
+        del st
+        return t_pre, t_step
+
+    B = 64
+    t_pre, t_step = batch_step(B)
     out["batch64_one_gpu"] = {"audio_s_per_s": B * FRAME_S / (t_step / 1e3), "ms_per_frame_step": t_step, "prefill_ms": t_pre,
                               "roofline_frac": lm_algorithmic_bytes(12, 20) / (t_step / 1e3) / 1e9 / 6557.8,
-                              "note": "LM frames only: CUDA graph of the fused kernel chain (csrc/batch_frame.cu: one tcgen05 launch per Linear, fused partial-sum kernels, programmatic dependent launch); 64 frames per step"}
-    del st
+                              "note": "LM frames only: CUDA graph of the fused kernel chain (csrc/batch_frame.cu: one tcgen05 launch per Linear, SwiGLU in the gate|up epilogue, fused partial-sum kernels, programmatic dependent launch); 64 frames per step"}
+    # the same chain at other batch sizes: every kernel is latency-bound, so a step costs almost the same from 2 to 256 sequences
+    sweep = {}
+    for Bs in (2, 8, 128, 256):
+        _, t = batch_step(Bs)
+        sweep[str(Bs)] = {"ms_per_frame_step": t, "audio_s_per_s": Bs * FRAME_S / (t / 1e3)}
+    out["batch_sweep_one_gpu"] = sweep
     # configs[2]: 2-segment context (2 x 5 s synthetic audio -> Mimi encode) + new text -> 164-row prefill -> frames
     tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
     try:

@@ -1,15 +1,16 @@
 // Fused batched decode frame (sm_100a): what csmb_decode_frame computes for B sequences in lock-step — generate_frame
-// with T = 1 (csm_mlx/generation.py:21-92) plus the next-input construction (:156-161) — as a chain of ~1 250 kernels
+// with T = 1 (csm_mlx/generation.py:21-92) plus the next-input construction (:156-161) — as a chain of ~1 100 kernels
 // per frame instead of ~3 700:
 //
-//   * every Linear is ONE tcgen05 launch (k_gemm_part): 128 weight rows x all token rows per CTA tile, fp32 TMEM
+//   * every Linear is ONE tcgen05 launch (k_gemm_part_t): 128 weight rows x all token rows per CTA tile, fp32 TMEM
 //     accumulators, TMA-fed 128B-swizzled stages, split along K so that ~148 CTAs stream the matrix; it reads the
 //     activations as bf16 hi + lo planes (x = hi + lo to 2^-17) that its PRODUCER kernel already wrote, and leaves
 //     fp32 split-K partials [S][R][N];
 //   * everything between two Linears is ONE kernel that starts by summing those partials in fixed order:
 //       k_resid_norm_split    partial sum + residual add + RMSNorm + hi/lo split
 //       k_attn_decode_fused   partial sum + RoPE + paged KV append + GQA attention + hi/lo split
-//       k_swiglu_split        partial sum + SwiGLU + hi/lo split
+//       (SwiGLU + hi/lo split run in the gate|up Linear's own epilogue, k_gemm_part_t<true>; k_swiglu_split is the
+//        separate-launch form kept for A/B runs)
 //       k_sample_embed        partial sum (logits) + sampling + next codebook embedding gather (+ hi/lo split)
 //       k_frame_embed_norm    previous frame -> summed audio embeddings + first RMSNorm + hi/lo split
 //   * all launches are chained with programmatic dependent launch: a GEMM CTA sets up its barriers / TMEM and already
@@ -32,7 +33,7 @@ constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
 static int g_bf_min_kblocks = 4;   // split-K: at least this many 64-wide K blocks per CTA
 static int g_bf_pdl = 1;           // programmatic dependent launch on/off (debug)
 static int g_bf_max_ctas = 148;
-static int g_bf_dbg = 0;
+static int g_bf_dbg = 0;          // bits 0, 1: timing experiments (GpArgs::dbg); bit 2: separate k_swiglu_split launch (A/B)
 
 // ---------------------------------------------------------------------------------------------- GEMM
 struct GpArgs {
@@ -40,12 +41,23 @@ struct GpArgs {
   int R, N, K, RN, nstages, S;
   int* err;
   int dbg;  // timing experiments only: bit 0 = no partial stores, bit 1 = no TMEM loads either (results are wrong)
+  // GU variant only: the matrix is gate rows [0, F) then up rows [F, 2F); output planes [R][F]
+  int F;
+  uint16_t *out_hi, *out_lo;
 };
 
 // dynamic smem: [stage][ W 128x64 | Xhi RNx64 | Xlo RNx64 ] bf16, 1024-byte aligned tiles
+//
+// GU = true is the gate|up Linear of the MLP with SwiGLU fused into its epilogue (no split-K): a CTA owns 64 features,
+// its weight tile is gate rows f0..f0+63 (UMMA rows 0..63) on top of up rows F+f0.. (rows 64..127; two 64-row TMA boxes
+// per stage, the 128B swizzle only depends on the address inside a 1 KiB atom), the four epilogue warps park their TMEM
+// quarters (gate: lanes 0..63, up: lanes 64..127) in the drained pipeline stages, and all 128 threads then write
+// silu(gate) * up as bf16 hi + lo planes [R][F] for the down projection — the k_swiglu_split launch disappears.  Same
+// sums and the same expression as k_swiglu_split over one partial: bit-identical planes.
+template <bool GU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
-            const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
+k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
+              const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[BF_MAX_STAGES], empty[BF_MAX_STAGES], acc_full;
@@ -61,6 +73,14 @@ k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
   const int nk = kb1 - kb0;
   uint32_t ncols = 32;
   while ((int)ncols < RN) ncols <<= 1;
+  auto load_w = [&](unsigned char* dst, int kb, uint64_t* bar) {
+    if (GU) {
+      tma_load_2d(dst, &map_w, kb * TC_BK, n0 / 2, bar);                                  // gate rows f0 .. f0+63
+      tma_load_2d(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, bar);  // up rows F+f0 ..
+    } else {
+      tma_load_2d(dst, &map_w, kb * TC_BK, n0, bar);
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < BF_MAX_STAGES; ++i) {
@@ -89,7 +109,7 @@ k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
       const int pre = nk < NS ? nk : NS;
       for (int kb = 0; kb < pre; ++kb) {
         tc_mbar_expect_tx(&full[kb], w_bytes + 2 * x_bytes);
-        tma_load_2d(smem + (size_t)kb * stage_bytes, &map_w, (kb0 + kb) * TC_BK, n0, &full[kb]);
+        load_w(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
       }
       pdl_wait();
       for (int kb = 0; kb < pre; ++kb) {
@@ -103,7 +123,7 @@ k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
         if (!tc_mbar_wait(&empty[s], par ^ 1, a.err)) break;
         unsigned char* st = smem + (size_t)s * stage_bytes;
         tc_mbar_expect_tx(&full[s], w_bytes + 2 * x_bytes);
-        tma_load_2d(st, &map_w, (kb0 + kb) * TC_BK, n0, &full[s]);
+        load_w(st, kb0 + kb, &full[s]);
         tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[s]);
         tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[s]);
       }
@@ -138,7 +158,33 @@ k_gemm_part(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ C
     const bool ok = tc_mbar_wait(&acc_full, 0, a.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int n = n0 + quarter * 32 + lane;
-    if (ok) {
+    if (GU) {
+      // park gate (quarters 0, 1) and up (quarters 2, 3) values as [2][RN][64] fp32 in the drained stages
+      float* ex = reinterpret_cast<float*>(smem);
+      if (ok) {
+        float* mine = ex + (size_t)(quarter >> 1) * RN * 64 + (quarter & 1) * 32 + lane;
+        for (int c0 = 0; c0 < RN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < RN) mine[(size_t)(c0 + j) * 64] = __uint_as_float(v[j]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ok) {
+        const int f0 = n0 / 2, te = threadIdx.x - 64;  // 0 .. 127
+        const int rows = min(RN, a.R - r0);
+        for (int idx = te; idx < rows * 16; idx += 128) {
+          const int t = idx >> 4, f4 = (idx & 15) * 4;
+          const float4 g = *reinterpret_cast<const float4*>(ex + (size_t)t * 64 + f4);
+          const float4 u = *reinterpret_cast<const float4*>(ex + (size_t)(RN + t) * 64 + f4);
+          const size_t o = (size_t)(r0 + t) * a.F + f0 + f4;
+          store_split4(a.out_hi + o, a.out_lo + o, (g.x / (1.f + expf(-g.x))) * u.x, (g.y / (1.f + expf(-g.y))) * u.y,
+                       (g.z / (1.f + expf(-g.z))) * u.z, (g.w / (1.f + expf(-g.w))) * u.w);
+        }
+      }
+    } else if (ok) {
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
       for (int c0 = 0; c0 < RN; c0 += 32) {
         uint32_t v[32];
@@ -563,7 +609,9 @@ static cudaError_t bf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 struct FastWs {
   int* err;
   float *x, *dx, *h_last, *part;
-  uint16_t *hi, *lo;
+  uint16_t *hi, *lo;    // activation planes every Linear reads ([rows][K])
+  uint16_t *hi2, *lo2;  // SwiGLU output planes [rows][d_ff]: written by the gate|up Linear's epilogue while other CTAs of that
+                        // launch still read hi / lo, read by the down projection
   size_t part_floats, bytes;
 };
 
@@ -591,6 +639,8 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base) {
   w.h_last = (float*)take((size_t)B * b.d_model * 4);
   w.hi = (uint16_t*)take(R2 * kmax * 2);
   w.lo = (uint16_t*)take(R2 * kmax * 2);
+  w.hi2 = (uint16_t*)take(R2 * kmax * 2);
+  w.lo2 = (uint16_t*)take(R2 * kmax * 2);
   size_t pf = 0;
   auto need = [&](int R, int N, int K) {
     const size_t f = bf_part_floats(R, N, K);
@@ -608,24 +658,46 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base) {
   return w;
 }
 
-static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st) {
+// y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
+static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
+                   const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr) {
   CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int S = bf_pick_split(R, N, K);
   CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
   const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
   CUtensorMap mw, mhi, mlo;
-  if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
+  if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, xhi ? xhi : w.hi, R, K, RN) ||
+      !tc_make_map(&mlo, xlo ? xlo : w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(BF_SMEM_BUDGET / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, g_bf_dbg};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, g_bf_dbg, 0, nullptr, nullptr};
   const size_t smem = stage * nstages + 1024;
-  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
-  CSMB_CUDA(bf_launch(k_gemm_part, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  CSMB_CUDA(bf_launch(k_gemm_part_t<false>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
   *out = PartIn{w.part, S, (size_t)R * N, N};
+  return CSMB_OK;
+}
+
+// SwiGLU MLP first half in one launch: w.hi2 / w.lo2 [R][F] = split(silu(x Wg^T) * (x Wu^T)), Wgu = gate rows then up rows
+static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K, cudaStream_t st) {
+  CSMB_REQUIRE(R > 0 && F % (TC_BM / 2) == 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(Wgu) & 15) == 0);
+  const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
+  CUtensorMap mw, mhi, mlo;
+  if (!tc_make_map(&mw, Wgu, 2 * F, K, TC_BM / 2) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
+    return CSMB_ERR_UNSUPPORTED;
+  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
+  int nstages = (int)(BF_SMEM_BUDGET / stage);
+  nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
+  CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
+  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, 0, F, w.hi2, w.lo2};
+  const size_t smem = stage * nstages + 1024;
+  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+  dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
+  CSMB_CUDA(bf_launch(k_gemm_part_t<true>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
   return CSMB_OK;
 }
 
@@ -671,12 +743,14 @@ static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool
     if ((rc = bf_attn(w, L, part, pool + (size_t)l * layer_stride, block_table, max_pages, pos_arr, pos0, rps, B, st))) return rc;
     if ((rc = bf_gemm(w, L.wo[l], R, d, L.n_heads * L.head_dim, &part, st))) return rc;
     if ((rc = bf_norm(w, x, d, part, 2, L.norm_post[l], L.eps, nullptr, R, 1, 0, st))) return rc;
-    if ((rc = bf_gemm(w, L.wgu[l], R, 2 * F, d, &part, st))) return rc;
-    {
+    if (g_bf_dbg & 4) {
+      if ((rc = bf_gemm(w, L.wgu[l], R, 2 * F, d, &part, st))) return rc;
       const size_t total4 = (size_t)R * F / 4;
-      CSMB_CUDA(bf_launch(k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi, w.lo));
+      CSMB_CUDA(bf_launch(k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi2, w.lo2));
+    } else {
+      if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st))) return rc;
     }
-    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st))) return rc;
+    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st, w.hi2, w.lo2))) return rc;
     if (l + 1 < L.n_layers) {
       if ((rc = bf_norm(w, x, d, part, 2, L.norm_in[l + 1], L.eps, nullptr, R, 1, 0, st))) return rc;
     } else {

@@ -197,7 +197,7 @@ class LMState:
     def persist_supported(self, sampler: SamplerSpec) -> bool:
         """True if the persistent batched frame kernel (csrc/batch_persist.cu) is requested (``CSMB_ENABLE_PERSIST=1``)
         and covers this model, sampler and batch.  It is token-identical to the kernel chain but measured slower
-        (13.3 vs 9.2 ms per frame-step at 64 sequences, profiles/r01_batched_frame.md), so the chain is the default."""
+        (13.3 vs 8.3 ms per frame-step at 64 sequences, profiles/r01_batched_frame.md), so the chain is the default."""
         if os.environ.get("CSMB_ENABLE_PERSIST", "0") != "1" or not self.fast_supported(sampler):
             return False
         s = sampler.to_c()

@@ -212,8 +212,8 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* b, const
 /* tuning: minimum 64-wide K blocks per split-K CTA (>= 1), programmatic dependent launch on/off (-1 = keep),
    CTA budget per Linear (0 = keep) of later csmb_decode_frame_fast calls */
 void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas);
-/* debug (timing experiments, results are wrong): bit 0 = the chain's Linears skip their partial stores, bit 1 = and their
-   TMEM loads */
+/* debug: bit 0 = the chain's Linears skip their partial stores, bit 1 = and their TMEM loads (timing experiments, results
+   are wrong); bit 2 = SwiGLU as a separate launch after the gate|up Linear instead of in its epilogue (A/B: same tokens) */
 void csmb_debug_set_fast_frame_flags(int flags);
 
 /* Throughput path, persistent form (csrc/batch_persist.cu): the frame of csmb_decode_frame for `batch` sequences in ONE

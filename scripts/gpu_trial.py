@@ -576,6 +576,47 @@ def _lanes():
         del states
 
 
+@section("gu")
+def _gu():
+    """SwiGLU fused into the gate|up Linear's epilogue (default) vs the separate k_swiglu_split launch (debug flag 4):
+    tokens must be identical; timing of the CUDA-graph replay."""
+    from csm_mlx_b200 import _lib
+    from tests.workloads import prompt_ids
+    spec = SamplerSpec()
+    for B in (3, 64, 130):
+        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+        frames = {}
+        for flags in (4, 0):
+            _lib.lib().csmb_debug_set_fast_frame_flags(flags)
+            st = LMState(model, B, max_len=64)
+            st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+            frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+            st.sample_c0(frame, spec); st.depth_decode(frame, spec)
+            out = [frame.clone()]
+            prev = frame
+            for _ in range(3):
+                nxt = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+                st.decode_frame(prev, nxt, spec)
+                out.append(nxt.clone()); prev = nxt
+            torch.cuda.synchronize()
+            st.check_status()
+            frames[flags] = torch.stack(out).cpu()
+            for _ in range(3):
+                prev = st.decode_frame_graphed(prev, spec)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                prev = st.decode_frame_graphed(prev, spec)
+            e1.record(); torch.cuda.synchronize()
+            st.check_status()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"B={B} {'separate swiglu' if flags else 'fused epilogue '}: {ms:.2f} ms/frame-step -> {B * 0.08 / (ms / 1e3):.0f} audio-s/s", flush=True)
+            del st
+        print(f"B={B} tokens identical: {torch.equal(frames[0], frames[4])}", flush=True)
+    _lib.lib().csmb_debug_set_fast_frame_flags(0)
+
+
 @section("setup")
 def _setup():
     """Where does the first-chunk time of stream_generate go?"""
