@@ -237,6 +237,44 @@ def test_fused_chain_filtered_sampler_falls_back(model_1b):
     assert all(t.shape == (2, 32) for t in toks)
 
 
+@pytest.mark.parametrize("B", [5, 130])
+def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, B):
+    """The gate|up Linear with SwiGLU in its epilogue (k_gemm_part_t<true>: 64 gate rows + the 64 matching up rows per
+    UMMA tile, planes written from the drained pipeline stages) against the separate k_swiglu_split launch (debug flag
+    4): identical tokens for a ragged row count (5 rows in a 16-row token tile) and for 130 sequences (first depth
+    step: 260 rows = three 128-row token tiles)."""
+    from csm_mlx_b200 import _lib
+    from csm_mlx_b200.runtime import LMState
+
+    spec = SamplerSpec(temperature=0.0)
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
+
+    def run(flags):
+        _lib.lib().csmb_debug_set_fast_frame_flags(flags)
+        st = LMState(model_1b, B, max_len=48)
+        assert st.fast_supported(spec)
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        frame = torch.zeros((B, 32), device=device, dtype=torch.int32)
+        st.sample_c0(frame, spec)
+        st.depth_decode(frame, spec)
+        out, prev = [frame.clone()], frame
+        for _ in range(2):
+            nxt = torch.zeros((B, 32), device=device, dtype=torch.int32)
+            st.decode_frame(prev, nxt, spec)
+            out.append(nxt.clone())
+            prev = nxt
+        torch.cuda.synchronize()
+        st.check_status()
+        return torch.stack(out).cpu()
+
+    try:
+        separate, fused = run(4), run(0)
+    finally:
+        _lib.lib().csmb_debug_set_fast_frame_flags(0)
+    assert torch.equal(separate, fused)
+    assert int((fused[1:] != fused[:-1]).sum()) > 0  # frames differ from step to step: the loop really decoded
+
+
 def test_persistent_batched_kernel_equals_chain(model_1b, monkeypatch):
     """csmb_frame_batch (one cooperative launch per frame-step: tcgen05 Linear phases with a persistent TMA ring,
     grid barriers, in-kernel sampling; opt-in with CSMB_ENABLE_PERSIST=1) produces the tokens of the kernel chain."""
