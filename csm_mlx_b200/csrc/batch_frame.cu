@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(256) k_swiglu_split(PartIn gu, int F, size_t t
 struct BfSample {
   int top_k;       // 0 = off
   float min_p;     // 0 = off
+  float top_p;     // 0 = off
   float inv_temp;  // 0 => greedy
   uint32_t seed_lo, seed_hi;
   uint64_t draw_base;
@@ -521,6 +522,7 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
   extern __shared__ float sl[];
   __shared__ float red_v[8];
   __shared__ int red_i[8];
+  __shared__ unsigned long long red_q[8];
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
     // top-k / min-p exactly as k_sample_filtered defines them: e_i = exp(logit_i - max), keep e_i >= max(k-th largest e,
     // min_p); the k-th largest e by a 31-step bisection on its bit pattern (see sample_token in frame_kernel.cu)
     float thresh = -1.f, m = 0.f;
-    if (a.top_k > 0 || a.min_p > 0.f) {
+    if (a.top_k > 0 || a.min_p > 0.f || a.top_p > 0.f) {
       float mx = -INFINITY;
       for (int i = threadIdx.x; i < V; i += 256) mx = fmaxf(mx, sl[i]);
       mx = warp_max(mx);
@@ -558,6 +560,33 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
           __syncthreads();
           if (tot >= a.top_k) T = cand;
         }
+      }
+      if (a.top_p > 0.f) {
+        // nucleus on exact integer masses q = floor(e * 2^32): largest T with sum(q : e >= T) >= top_p * sum(q)
+        // (identical to sample_token of frame_kernel.cu and to the sorter of k_sample_filtered)
+        auto block_mass = [&](unsigned cand) {
+          unsigned long long n = 0;
+          for (int i = threadIdx.x; i < V; i += 256) {
+            const float e = expf(sl[i] - m);
+            if (__float_as_uint(e) >= cand) n += __float2ull_rz(e * 4294967296.f);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+          if ((threadIdx.x & 31) == 0) red_q[threadIdx.x >> 5] = n;
+          __syncthreads();
+          unsigned long long tot = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) tot += red_q[w];
+          __syncthreads();
+          return tot;
+        };
+        const double need = (double)a.top_p * (double)block_mass(0u);
+        unsigned Tp = 0u;
+        for (int bit = 30; bit >= 0; --bit) {
+          const unsigned cand = Tp | (1u << bit);
+          if ((double)block_mass(cand) >= need) Tp = cand;
+        }
+        T = T > Tp ? T : Tp;
       }
       thresh = fmaxf(__uint_as_float(T), a.min_p);
     }
@@ -767,8 +796,8 @@ static bool bf_supported(const csmb_model& m, const csmb_sampler& s) {
            L.n_heads % L.n_kv_heads == 0 && L.n_heads / L.n_kv_heads <= 8 && L.d_ff % 64 == 0 && L.d_ff % 4 == 0 &&
            L.n_heads * L.head_dim == L.d_model;
   };
-  // fused samplers: greedy; temperature with optional top-k and / or min-p (min_keep 1); top-p stays on the per-op path
-  const bool filtered = s.temperature != 0.f && ((s.top_p > 0.f && s.top_p < 1.f) || (s.min_p > 0.f && s.min_keep > 1));
+  // fused samplers: greedy; temperature with optional top-k, top-p and / or min-p (min_keep 1)
+  const bool filtered = s.temperature != 0.f && s.min_p > 0.f && s.min_keep > 1;
   return llama_ok(b) && llama_ok(d) && b.d_model == 2048 && m.audio_vocab <= 8192 && m.n_codebooks >= 2 && !filtered &&
          s.temperature >= 0.f;
 }
@@ -821,6 +850,7 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   sa.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
   sa.top_k = (sampler->top_k > 0 && sampler->top_k < V) ? sampler->top_k : 0;
   sa.min_p = sampler->min_p > 0.f ? sampler->min_p : 0.f;
+  sa.top_p = (sampler->top_p > 0.f && sampler->top_p < 1.f) ? sampler->top_p : 0.f;
   sa.seed_lo = (uint32_t)sampler->seed;
   sa.seed_hi = (uint32_t)(sampler->seed >> 32);
   sa.draw_pos_mul = (uint32_t)ncb;

@@ -93,6 +93,7 @@ struct FrameParams {
   float inv_temp;
   int top_k;                   // 0 = off; else keep the k most likely tokens (ties included), like k_sample_filtered
   float min_p;                 // 0 = off; else drop tokens whose probability is below min_p x the best one's
+  float top_p;                 // 0 = off; else the nucleus: tokens whose strictly-more-likely mass is below top_p (k_sample_filtered)
   uint32_t seed_lo, seed_hi;
   unsigned long long draw_base;
 };
@@ -557,7 +558,7 @@ __device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, un
   // top-k / min-p (mlx_lm make_sampler as used by cli/generate.py:168-174): the same definition as k_sample_filtered —
   // e_i = exp(logit_i - max), threshold = max(k-th largest e, min_p), tokens with e_i >= threshold stay.  The k-th
   // largest e is found exactly by a 31-step bisection on its bit pattern (e >= 0 orders like an unsigned integer).
-  const bool filt = p.inv_temp != 0.f && (p.top_k > 0 || p.min_p > 0.f);
+  const bool filt = p.inv_temp != 0.f && (p.top_k > 0 || p.min_p > 0.f || p.top_p > 0.f);
   float ev[9];
   float thresh = 0.f;
   if (filt) {
@@ -591,6 +592,34 @@ __device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, un
         for (int w = 0; w < NCW; ++w) tot += buf[w];
         if (tot >= p.top_k) T = cand;
       }
+    }
+    if (p.top_p > 0.f) {
+      // nucleus: masses are exact integers q = floor(e * 2^32) (sums are order-independent, so this kernel, the chain's
+      // sampler and the per-op sorter agree bit for bit); keep the tokens at or above the largest T whose mass
+      // sum(q : e >= T) still reaches top_p * sum(q) — the same greedy bisection as for top-k, on mass instead of count
+      unsigned long long* qs = reinterpret_cast<unsigned long long*>(c.sred + 4 * NCW);  // [2][NCW]
+      auto block_mass = [&](unsigned cand, int slot) {
+        unsigned long long n = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          if (ev[j] >= 0.f && __float_as_uint(ev[j]) >= cand) n += __float2ull_rz(ev[j] * 4294967296.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        unsigned long long* buf = qs + slot * NCW;
+        if (c.lane == 0) buf[c.warp] = n;
+        csync();
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) tot += buf[w];
+        return tot;
+      };
+      const double need = (double)p.top_p * (double)block_mass(0u, 1);
+      unsigned Tp = 0u;
+      for (int bit = 30; bit >= 0; --bit) {
+        const unsigned cand = Tp | (1u << bit);
+        if ((double)block_mass(cand, bit & 1) >= need) Tp = cand;
+      }
+      T = T > Tp ? T : Tp;
     }
     thresh = fmaxf(__uint_as_float(T), p.min_p);
   }
@@ -1268,7 +1297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[2 * NSTAGES + 1];
   __shared__ __align__(16) float s_part[2 * 2 * MAXU * 4];  // [range][row][unit][4 partials]
-  __shared__ float s_red[NCW * 4];
+  __shared__ __align__(16) float s_red[NCW * 8];
   __shared__ __align__(16) float s_attn[2 * 1024 + NCW * 2 * 128];
   Ctx c;
   c.p = &p;
@@ -1371,10 +1400,9 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
                         D.d_ff == 8192 && B.d_ff == 8192 && m->n_codebooks <= 32 && m->n_codebooks >= 3 &&
                         m->audio_vocab <= 9 * NCT;
   if (!shape_ok) return CSMB_ERR_UNSUPPORTED;
-  // fused samplers: greedy; temperature with optional top-k and / or min-p (min_keep 1).  top-p needs the sorted
-  // cumulative distribution and stays on the per-op path (csmb_decode_frame).
-  if (sampler->temperature != 0.f && ((sampler->top_p > 0.f && sampler->top_p < 1.f) || (sampler->min_p > 0.f && sampler->min_keep > 1)))
-    return CSMB_ERR_UNSUPPORTED;
+  // fused samplers: greedy; temperature with optional top-k, top-p and / or min-p.  Only min-p with min_tokens_to_keep > 1
+  // (it needs the sorted order) stays on the per-op path (csmb_decode_frame).
+  if (sampler->temperature != 0.f && sampler->min_p > 0.f && sampler->min_keep > 1) return CSMB_ERR_UNSUPPORTED;
   CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m, device));
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 0;
@@ -1420,6 +1448,7 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   p.inv_temp = sampler->temperature == 0.f ? 0.f : 1.f / sampler->temperature;
   p.top_k = (sampler->top_k > 0 && sampler->top_k < m->audio_vocab) ? sampler->top_k : 0;
   p.min_p = sampler->min_p > 0.f ? sampler->min_p : 0.f;
+  p.top_p = (sampler->top_p > 0.f && sampler->top_p < 1.f) ? sampler->top_p : 0.f;
   p.seed_lo = (uint32_t)sampler->seed;
   p.seed_hi = (uint32_t)(sampler->seed >> 32);
   p.draw_base = draw_base;

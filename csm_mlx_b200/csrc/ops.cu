@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(1024) k_sample_filtered(const float* __restric
   __syncthreads();
   float tot = 0.f;
   for (int w = 0; w < 32; ++w) tot += red[w];
-  const float inv_tot = 1.f / tot;
+  (void)tot;  // the filters work on unnormalised e (top-p: on integer masses, below)
   __syncthreads();
   // bitonic sort, descending
   for (int k = 2; k <= 4096; k <<= 1) {
@@ -530,11 +530,18 @@ __global__ void __launch_bounds__(1024) k_sample_filtered(const float* __restric
     int n1 = (a.top_k > 0 && a.top_k < V) ? a.top_k : V;
     float t = sp[n1 - 1];
     if (a.top_p > 0.f && a.top_p < 1.f) {
-      float c = 0.f;
+      // the nucleus is defined on exact integer masses q = floor(e * 2^32), so that the result does not depend on a
+      // summation order and the fused samplers (frame_kernel.cu, batch_frame.cu), which find the same threshold by
+      // bisection, agree with this sorter bit for bit: token i stays while the mass of the strictly more likely
+      // tokens is below top_p * total mass
+      unsigned long long Q = 0;
+      for (int i = 0; i < V; ++i) Q += __float2ull_rz(sp[i] * 4294967296.f);
+      const double need = (double)a.top_p * (double)Q;
+      unsigned long long c = 0;
       int n2 = 0;
       for (int i = 0; i < n1; ++i) {
-        if (c * inv_tot < a.top_p) n2 = i + 1; else break;
-        c += sp[i];
+        if ((double)c < need) n2 = i + 1; else break;
+        c += __float2ull_rz(sp[i] * 4294967296.f);
       }
       t = fmaxf(t, sp[n2 - 1]);
     }

@@ -330,8 +330,8 @@ class LMState:
         a, d = self.model.backbone.args, self.model.decoder.args
         shape = (a.hidden_size, a.num_attention_heads, a.num_key_value_heads, a.head_dim, d.hidden_size,
                  d.num_attention_heads, d.num_key_value_heads, d.head_dim) == (2048, 32, 8, 64, 1024, 8, 2, 128)
-        # in-kernel samplers of k_frame: greedy; temperature with top-k and / or min-p (min_tokens_to_keep 1); not top-p
-        plain = sampler.temperature == 0 or not (0 < sampler.top_p < 1 or (sampler.min_p > 0 and sampler.min_tokens_to_keep > 1))
+        # in-kernel samplers of k_frame: greedy; temperature with top-k, top-p and / or min-p (not min-p with min_tokens_to_keep > 1)
+        plain = sampler.temperature == 0 or not (sampler.min_p > 0 and sampler.min_tokens_to_keep > 1)
         return self.batch == 1 and shape and plain and 3 <= self.model.n_audio_codebooks <= 32
 
     def _frame_workspace(self) -> None:

@@ -101,7 +101,9 @@ int csmb_attention(const float* qkv, int ldq, const float* kv_pool, const int32_
 /* Sampling (generation.py:51-54, 81-84 and mlx_lm.sample_utils.make_sampler as used by
  * cli/generate.py:168-174).  logits [R][V] fp32 -> out[r*out_stride] int32.
  * temperature==0: argmax (lowest index on ties).  Otherwise top-k (k>0), top-p (0<p<1), min-p (>0,
- * keeping at least min_keep) filters on softmax(logits), then categorical(logits/temperature) by the
+ * keeping at least min_keep) filters on softmax(logits) — top-p on exact integer masses floor(exp(l - max) * 2^32): a
+ * token stays while the mass of the strictly more likely tokens is below top_p * total, independent of any summation
+ * order, so every sampler of the library picks the same nucleus —, then categorical(logits/temperature) by the
  * Gumbel-max trick: argmax_i(logits[i]/temperature - log(-log(u_i))), u_i from Philox4x32-10 with
  * key = seed and counter = (i/4, d_lo, d_hi, r), word i%4 of the output block, where the draw index
  * d = draw + (row_pos ? row_pos[r] : 0) * pos_mul  (row_pos: optional DEVICE array [R]). */
@@ -193,7 +195,7 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
  * Launches are chained with programmatic dependent launch, so weight streaming continues across kernel boundaries.
  * Same argument meaning as csmb_decode_frame (b->workspace is not used); workspace = csmb_decode_frame_fast_workspace_bytes
  * bytes, 256-byte aligned, zeroed once by its owner (first int = sticky error flag of the bounded waits).
- * Fused samplers: greedy, or temperature with optional top-k and / or min-p (min_keep 1); top-p (or an unsupported
+ * Fused samplers: greedy, or temperature with optional top-k, top-p and / or min-p; min-p with min_keep > 1 (or an unsupported
  * model shape) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  csmb_decode_frame_fast_supported returns 1/0 up front. */
 size_t csmb_decode_frame_fast_workspace_bytes(const csmb_model* m /*host*/, int batch);
 int csmb_decode_frame_fast_supported(const csmb_model* m /*host*/, const csmb_sampler* sampler /*host*/);
@@ -242,8 +244,8 @@ void csmb_debug_set_frame_batch_prof(unsigned long long* device_buf);
  * workspace must be zero-initialised once (csmb_frame_workspace_bytes; ~40 MB on B200: one private decoder-KV
  * copy per SM) and belongs to one sequence.
  * block_table: this sequence's row of the paged-KV table; pos: DEVICE int, position of this frame's backbone row.
- * Fused samplers: greedy, or temperature with optional top-k and / or min-p (min_keep 1); top-p (and model shapes other
- * than csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
+ * Fused samplers: greedy, or temperature with optional top-k, top-p and / or min-p; min-p with min_keep > 1 (and model shapes
+ * other than csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
  * code if an internal wait timed out (all waits are bounded). */
 size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/, int device);
 /* debug: device buffer [n_sms][16] u64 that later csmb_frame_b1 launches fill with per-CTA phase timers (ns); null = off */

@@ -54,19 +54,22 @@ def keep_mask(logits: np.ndarray, top_k: int = 0, top_p: float = 0.0, min_p: flo
     """Boolean mask of the tokens that survive the filters (logits (V,) fp32)."""
     V = logits.shape[0]
     e = np.exp((logits - logits.max()).astype(np.float32), dtype=np.float32)
-    tot = np.float32(e.sum(dtype=np.float32))
     s = np.sort(e)[::-1]
     n1 = top_k if 0 < top_k < V else V
     t = s[n1 - 1]
     if 0.0 < top_p < 1.0:
-        c = np.float32(0.0)
+        # nucleus on exact integer masses q = floor(e * 2^32) (order-independent sums: the definition every CUDA sampler of
+        # the library shares): token i stays while the mass of the strictly more likely tokens is below top_p * total
+        q = np.floor(s.astype(np.float64) * 4294967296.0).astype(np.uint64)
+        need = float(np.float32(top_p)) * float(int(q.sum(dtype=np.uint64)))
+        c = 0
         n2 = 0
         for i in range(n1):
-            if c / tot < np.float32(top_p):
+            if float(c) < need:
                 n2 = i + 1
             else:
                 break
-            c = np.float32(c + s[i])
+            c += int(q[i])
         t = max(t, s[n2 - 1])
     if min_p > 0.0:
         mk = min(max(min_keep, 1), V)

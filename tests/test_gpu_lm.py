@@ -211,7 +211,8 @@ def test_batch64_fused_chain_matches_single(model_1b):
 
 
 @pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.0), SamplerSpec(temperature=0.8, seed=5),
-                                  SamplerSpec(temperature=0.9, top_k=50, seed=7), SamplerSpec(temperature=0.9, top_k=20, min_p=0.03, seed=8)])
+                                  SamplerSpec(temperature=0.9, top_k=50, seed=7), SamplerSpec(temperature=0.9, top_k=20, min_p=0.03, seed=8),
+                                  SamplerSpec(temperature=0.8, top_p=0.9, seed=9), SamplerSpec(temperature=1.1, top_k=64, top_p=0.7, seed=10)])
 def test_fused_chain_equals_per_op_batched_path(model_1b, monkeypatch, spec):
     """Same batch through csmb_decode_frame_fast and through the per-op csmb_decode_frame (CSMB_DISABLE_FAST=1):
     identical tokens, greedy and with in-kernel Gumbel/Philox temperature sampling."""
@@ -224,16 +225,18 @@ def test_fused_chain_equals_per_op_batched_path(model_1b, monkeypatch, spec):
 
 
 def test_fused_chain_filtered_sampler_falls_back(model_1b):
-    """top-p is not fused: the batched path must route to the per-op frame (csmb_decode_frame) and still work."""
+    """min-p with min_tokens_to_keep > 1 (it needs the sorted order) is not fused: the batched path must route to the
+    per-op frame (csmb_decode_frame) and still work."""
     from csm_mlx_b200.runtime import LMState
 
     st = LMState(model_1b, 3, max_len=32)
     assert st.fast_supported(SamplerSpec(temperature=0.0))
     assert st.fast_supported(SamplerSpec(temperature=0.7))
     assert st.fast_supported(SamplerSpec(temperature=0.7, top_k=50))
-    assert not st.fast_supported(SamplerSpec(temperature=0.7, top_p=0.9))
+    assert st.fast_supported(SamplerSpec(temperature=0.7, top_p=0.9))
+    assert not st.fast_supported(SamplerSpec(temperature=0.7, min_p=0.05, min_tokens_to_keep=2))
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(70 + i, 7), 0) for i in range(3)]
-    toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, top_p=0.9, seed=3))
+    toks = generation.generate_tokens(model_1b, prompts, 2, sampler=SamplerSpec(temperature=0.7, min_p=0.05, min_tokens_to_keep=2, seed=3))
     assert all(t.shape == (2, 32) for t in toks)
 
 
@@ -308,15 +311,17 @@ def test_cfg2_full_length_two_implementations_agree(model_1b, monkeypatch):
 
 
 @pytest.mark.parametrize("spec", [SamplerSpec(temperature=0.9, top_k=50, seed=21), SamplerSpec(temperature=0.7, min_p=0.05, seed=22),
-                                  SamplerSpec(temperature=1.1, top_k=8, min_p=0.02, seed=23)])
+                                  SamplerSpec(temperature=1.1, top_k=8, min_p=0.02, seed=23), SamplerSpec(temperature=0.9, top_p=0.9, seed=24),
+                                  SamplerSpec(temperature=1.2, top_k=40, top_p=0.8, min_p=0.01, seed=25)])
 def test_fused_frame_kernel_topk_minp_equals_per_op_sampler(model_1b, monkeypatch, spec):
-    """top-k / min-p inside the persistent frame kernel (exact k-th-largest search by bisection on the bit pattern of
-    exp(logit - max)) selects exactly the tokens of the per-op sampler (k_sample_filtered: sorted probabilities), so
-    with the same Philox noise both paths generate the same frames (the README / CLI sampler, cli/generate.py:168-174)."""
+    """top-k / top-p / min-p inside the persistent frame kernel (exact k-th-largest search by bisection on the bit pattern
+    of exp(logit - max); nucleus by the same bisection on exact integer masses) selects exactly the tokens of the per-op
+    sampler (k_sample_filtered: sorted probabilities), so with the same Philox noise both paths generate the same frames
+    (the README / CLI sampler, cli/generate.py:168-174)."""
     from csm_mlx_b200.runtime import LMState
 
     assert LMState(model_1b, 1, max_len=32).fused_supported(spec)
-    assert not LMState(model_1b, 1, max_len=32).fused_supported(SamplerSpec(temperature=0.9, top_p=0.9))
+    assert not LMState(model_1b, 1, max_len=32).fused_supported(SamplerSpec(temperature=0.9, min_p=0.1, min_tokens_to_keep=2))
     (fused,) = generation.generate_tokens(model_1b, [_prompt()], 6, sampler=spec)
     monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
     (per_op,) = generation.generate_tokens(model_1b, [_prompt()], 6, sampler=spec)

@@ -145,11 +145,11 @@ def test_cfg4_full_size_engine_vs_single(model_1b, mimi_gpu, device):
 
 @pytest.mark.gpu
 def test_engine_falls_back_to_mixed_steps_for_unfused_samplers(model_1b, mimi_gpu):
-    """top-p is not fused into the chain: admissions then go through the mixed per-op backbone pass and steady-state
-    steps through the per-op frame; the engine still serves every request for its full frame budget."""
+    """min-p with min_tokens_to_keep > 1 is not fused into the chain: admissions then go through the mixed per-op backbone
+    pass and steady-state steps through the per-op frame; the engine still serves every request for its full frame budget."""
     from csm_mlx_b200.runtime import SamplerSpec
 
-    eng = serving.Engine(model_1b, max_batch=2, max_len=96, sampler=SamplerSpec(temperature=0.8, top_p=0.9, seed=4))
+    eng = serving.Engine(model_1b, max_batch=2, max_len=96, sampler=SamplerSpec(temperature=0.8, min_p=0.05, min_tokens_to_keep=2, seed=4))
     rids = [eng.submit(prompt_ids(200 + i, 6 + i), 0, [], max_audio_length_ms=80 * (2 + i)) for i in range(3)]
     eng.run()
     assert eng.mixed_steps > 0 and eng.admissions == 0
