@@ -26,6 +26,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON record: libraries that chat on file descriptor 1 (NCCL prints its version
+# banner there) are sent to stderr, and the record is written to a private duplicate of the original stdout.
+sys.stdout.flush()
+_RECORD_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(record: dict) -> None:
+    _RECORD_OUT.write(json.dumps(record) + "\n")
+    _RECORD_OUT.flush()
+
+
 import torch  # noqa: E402
 
 FRAME_S = 0.08
@@ -142,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- other configs
@@ -477,7 +489,7 @@ def run_ours(args):
         "tokens_checksum": int(sum(int(t.long().sum()) for t in all_tokens)) if all_tokens else None,
         "other_configs": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
