@@ -179,6 +179,36 @@ def test_philox_known_answers():
         assert tuple(int(x) for x in r) == out
 
 
+def test_nucleus_by_bisection_equals_sorted_definition():
+    """The fused samplers (frame_kernel.cu::sample_token, batch_frame.cu::k_sample_embed) do not sort: they find the
+    largest bit pattern T whose integer mass sum(q : e >= T) still reaches top_p * sum(q) by a 31-step greedy bisection,
+    and keep e >= T.  Restated here in numpy and compared with the sorted definition of oracle/sampling.py (the one
+    k_sample_filtered implements), including ties, one-hot and flat distributions."""
+    rng = np.random.default_rng(3)
+
+    def by_bisection(logits, top_p):
+        e = np.exp((logits - logits.max()).astype(np.float32), dtype=np.float32)
+        bits = e.view(np.uint32).astype(np.int64)
+        q = np.floor(e.astype(np.float64) * 4294967296.0).astype(np.uint64)
+        need = float(np.float32(top_p)) * float(int(q.sum(dtype=np.uint64)))
+        T = 0
+        for bit in range(30, -1, -1):
+            cand = T | (1 << bit)
+            if float(int(q[bits >= cand].sum(dtype=np.uint64))) >= need:
+                T = cand
+        return bits >= T
+
+    cases = [rng.standard_normal(2051).astype(np.float32) * s for s in (0.3, 2.0, 6.0)]
+    cases.append(np.zeros(2051, dtype=np.float32))                                   # flat: everything ties
+    one_hot = np.full(2051, -60.0, dtype=np.float32); one_hot[77] = 0.0
+    cases.append(one_hot)
+    tied = rng.standard_normal(2051).astype(np.float32); tied[::3] = tied[0]          # large tie groups
+    cases.append(tied)
+    for lg in cases:
+        for top_p in (0.05, 0.5, 0.9, 0.999):
+            assert np.array_equal(by_bisection(lg, top_p), osamp.keep_mask(lg, top_p=top_p)), top_p
+
+
 def test_oracle_sampler_filters():
     lg = np.log(np.array([0.5, 0.2, 0.15, 0.1, 0.05], dtype=np.float32))
     assert osamp.keep_mask(lg, top_k=2).tolist() == [True, True, False, False, False]
