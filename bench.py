@@ -480,7 +480,7 @@ def run_ours(args):
                              "the Mimi streaming step replays a CUDA graph of ~110 captured kernels per frame on top",
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 9.1230e9 if fused else None,
+                     "traffic": 9.1205e9 if fused else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_frame, profiles/r01_frame_kernel_ncu.md" if fused else None,
                      "kernel": "csmb::k_frame (persistent whole-frame kernel)" if fused else "LM frame as a CUDA graph of per-op kernels",
                      "ms_per_frame": frame_ms,
