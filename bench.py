@@ -28,14 +28,22 @@ if ROOT not in sys.path:
 
 # stdout carries exactly ONE line, the JSON record: libraries that chat on file descriptor 1 (NCCL prints its version
 # banner there) are sent to stderr, and the record is written to a private duplicate of the original stdout.
-sys.stdout.flush()
-_RECORD_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_RECORD_OUT = None
+
+
+def claim_stdout() -> None:
+    """Called once by the command-line entry (never on import)."""
+    global _RECORD_OUT
+    if _RECORD_OUT is None:
+        sys.stdout.flush()
+        _RECORD_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(record: dict) -> None:
-    _RECORD_OUT.write(json.dumps(record) + "\n")
-    _RECORD_OUT.flush()
+    out = _RECORD_OUT if _RECORD_OUT is not None else sys.stdout
+    out.write(json.dumps(record) + "\n")
+    out.flush()
 
 
 import torch  # noqa: E402
@@ -511,4 +519,5 @@ def main():
 
 
 if __name__ == "__main__":
+    claim_stdout()
     main()
