@@ -23,3 +23,16 @@ def test_reference_arm_prints_exactly_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == rec["value"] and cb["sample"]
     e2e = rec["e2e"]
     assert e2e["value"] == rec["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_prints_on_rank0_only():
+    """N > 1: the driver launches the reference arm through torchrun like the CUDA arm; rank 0 alone runs and prints, the
+    other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, lines[:3]
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["value"] > 0 and rec["cpu_baseline"]["kind"] == "port"
