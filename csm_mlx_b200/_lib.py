@@ -100,6 +100,8 @@ _SIGS = {
     "csmb_set_frame_ctas": (None, [_I]),
     "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P,
                                 C.c_size_t, _P, _I, _P]),
+    "csmb_frame_b1_slot": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _I, _P,
+                                     C.c_size_t, _P, _I, _P]),
     "csmb_frame_b1_depth": (C.c_int, [C.POINTER(Model), _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P, C.c_size_t, _P,
                                       _I, _P]),
     "csmb_gemm_f32": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -96,6 +96,7 @@ struct FrameParams {
   float top_p;                 // 0 = off; else the nucleus: tokens whose strictly-more-likely mass is below top_p (k_sample_filtered)
   uint32_t seed_lo, seed_hi;
   unsigned long long draw_base;
+  uint32_t seq;                // sequence word of the Philox counter (row index of this sequence in its batch; csmb_sample's r)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -531,8 +532,8 @@ __device__ void phase_gate_up(Ctx& c, const uint16_t* Wgu, int F, int K, const f
 }
 
 // ------------------------------------------------------------------------------------------------ sampling
-__device__ __forceinline__ float gumbel_at(int idx, uint32_t dlo, uint32_t dhi, uint32_t k0, uint32_t k1) {
-  uint32_t ctr[4] = {(uint32_t)(idx >> 2), dlo, dhi, 0u};
+__device__ __forceinline__ float gumbel_at(int idx, uint32_t dlo, uint32_t dhi, uint32_t seq, uint32_t k0, uint32_t k1) {
+  uint32_t ctr[4] = {(uint32_t)(idx >> 2), dlo, dhi, seq};
   philox4x32_10(ctr, k0, k1);
   return -logf(-logf(u01(ctr[idx & 3])));
 }
@@ -631,7 +632,7 @@ __device__ int sample_token(Ctx& c, const uint2* logits, int V, unsigned tag, un
     const int i = c.tid + j * NCT;
     if (i < V && !(filt && !(ev[j] >= thresh))) {
       float t = __uint_as_float(v[j].x);
-      if (p.inv_temp != 0.f) t = t * p.inv_temp + gumbel_at(i, dlo, dhi, p.seed_lo, p.seed_hi);
+      if (p.inv_temp != 0.f) t = t * p.inv_temp + gumbel_at(i, dlo, dhi, p.seq, p.seed_lo, p.seed_hi);
       argmax_combine(bv, bi, t, i);
     }
   }
@@ -1389,7 +1390,7 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
 
 static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                         const int32_t* prev_frame, const float* h_in, const int32_t* pos, int32_t* frame,
-                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
+                        const csmb_sampler* sampler, uint64_t draw_base, uint32_t seq, void* workspace, size_t workspace_bytes,
                         int32_t* status, int device, void* stream) {
   CSMB_ENTER(device);
   CSMB_REQUIRE(m && pos && frame && sampler && workspace);
@@ -1452,6 +1453,7 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   p.seed_lo = (uint32_t)sampler->seed;
   p.seed_hi = (uint32_t)(sampler->seed >> 32);
   p.draw_base = draw_base;
+  p.seq = seq;
   p.prof = g_prof_ptr;
   p.dbg = g_dbg_flags;
   p.pf_max = g_pf_max;
@@ -1493,15 +1495,24 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
                   void* stream) {
-  return launch_frame(m, kv_pool, kv_layer_stride, block_table, prev_frame, nullptr, pos, frame, sampler, draw_base,
+  return launch_frame(m, kv_pool, kv_layer_stride, block_table, prev_frame, nullptr, pos, frame, sampler, draw_base, 0u,
                       workspace, workspace_bytes, status, device, stream);
+}
+
+int csmb_frame_b1_slot(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table_row,
+                       const int32_t* prev_frame_row, const int32_t* pos, int32_t* frame_row, const csmb_sampler* sampler,
+                       uint64_t draw_base, int seq_index, void* workspace, size_t workspace_bytes, int32_t* status,
+                       int device, void* stream) {
+  if (seq_index < 0) return CSMB_ERR_INVALID;
+  return launch_frame(m, kv_pool, kv_layer_stride, block_table_row, prev_frame_row, nullptr, pos, frame_row, sampler,
+                      draw_base, (uint32_t)seq_index, workspace, workspace_bytes, status, device, stream);
 }
 
 int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t* pos, int32_t* frame,
                         const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
                         int32_t* status, int device, void* stream) {
   if (!h_last) return CSMB_ERR_INVALID;
-  return launch_frame(m, nullptr, 0, nullptr, nullptr, h_last, pos, frame, sampler, draw_base, workspace,
+  return launch_frame(m, nullptr, 0, nullptr, nullptr, h_last, pos, frame, sampler, draw_base, 0u, workspace,
                       workspace_bytes, status, device, stream);
 }
 

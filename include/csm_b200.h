@@ -262,6 +262,14 @@ int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, c
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
                   uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
                   void* stream);
+/* csmb_frame_b1 for ONE sequence of a batched state (serving with a single active slot): the pointers are that sequence's
+ * rows (block_table + slot * max_pages, prev_frame + slot * n_codebooks, pos + slot, frame + slot * n_codebooks) and
+ * seq_index is its row in the batch, so that sampling draws the same Philox noise as csmb_decode_frame(_fast) would for
+ * that row (csmb_sample's r).  Everything else as csmb_frame_b1 (which is seq_index 0). */
+int csmb_frame_b1_slot(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table_row,
+                       const int32_t* prev_frame_row, const int32_t* pos, int32_t* frame_row, const csmb_sampler* sampler,
+                       uint64_t draw_base, int seq_index, void* workspace, size_t workspace_bytes, int32_t* status,
+                       int device, void* stream);
 /* The same kernel without its backbone part, for the first frame after a prompt (generation.py:139-146 with the
  * whole prompt as `tokens`): h_last = csmb_backbone_forward's normalised last hidden row [d_backbone] of this sequence,
  * pos = DEVICE int holding the sequence length (the sampled row is pos-1, which also indexes the random draws exactly

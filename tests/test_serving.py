@@ -154,3 +154,28 @@ def test_engine_falls_back_to_mixed_steps_for_unfused_samplers(model_1b, mimi_gp
     eng.run()
     assert eng.mixed_steps > 0 and eng.admissions == 0
     assert [tuple(eng.tokens(r).shape) for r in rids] == [(2, 32), (3, 32), (4, 32)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec_kw", [dict(temperature=0.0), dict(temperature=0.8, top_k=50, seed=6)])
+def test_engine_single_busy_slot_uses_the_batch1_kernel(model_1b, mimi_gpu, monkeypatch, spec_kw):
+    """While exactly one slot is busy and nothing waits, the engine runs that sequence's frames through the persistent
+    batch-1 kernel on the slot's own rows (csmb_frame_b1_slot, Philox sequence word = slot) instead of a chain step over
+    all slots: same tokens as the chain-only engine (CSMB_DISABLE_FUSED=1), greedy and sampled, also for the request
+    that keeps running alone after its neighbour finished."""
+    from csm_mlx_b200.runtime import SamplerSpec
+
+    def run():
+        eng = serving.Engine(model_1b, max_batch=4, max_len=96, sampler=SamplerSpec(**spec_kw))
+        rids = [eng.submit(prompt_ids(300, 7), 0, [], max_audio_length_ms=80 * 3),
+                eng.submit(prompt_ids(301, 9), 0, [], max_audio_length_ms=80 * 9)]
+        eng.run()
+        return eng, [eng.tokens(r) for r in rids]
+
+    eng, toks = run()
+    assert eng.solo_steps >= 3 and [tuple(t.shape) for t in toks] == [(3, 32), (9, 32)]
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    eng2, toks2 = run()
+    assert eng2.solo_steps == 0
+    for a, b in zip(toks, toks2):
+        assert torch.equal(a, b)
