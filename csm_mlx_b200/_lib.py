@@ -48,7 +48,23 @@ class Model(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("batch", C.c_int), ("max_pages", C.c_int), ("kv_pool", C.c_void_p),
                 ("kv_layer_stride", C.c_size_t), ("block_table", C.c_void_p), ("dec_kv_pool", C.c_void_p),
-                ("dec_kv_layer_stride", C.c_size_t), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("dec_kv_layer_stride", C.c_size_t), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("flags", C.c_int)]
+
+
+BATCH_ROW_INVARIANT = 1
+ABI_VERSION = 2
+
+
+class ChainOpts(C.Structure):
+    """csmb_chain_opts: per-call switches of the fused batched chain (NULL = defaults)."""
+    _fields_ = [("no_pdl", C.c_int), ("flags", C.c_int), ("smem_kb", C.c_int), ("proj_table", C.c_void_p)]
+
+
+class FrameOpts(C.Structure):
+    """csmb_frame_opts: per-call switches of the batch-1 frame kernel (NULL = defaults)."""
+    _fields_ = [("ctas", C.c_int), ("flags", C.c_int), ("prefetch_stages", C.c_int), ("prefetch_interval", C.c_int),
+                ("prof", C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -84,26 +100,17 @@ _SIGS = {
     "csmb_decode_frame_fast": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
                                          C.c_uint64, _P, C.c_size_t, _I, _P]),
     "csmb_decode_frame_fast_admit": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
-                                               C.c_uint64, _P, _P, _P, C.c_size_t, _I, _P]),
-    "csmb_debug_set_fast_frame": (None, [_I, _I, _I]),
-    "csmb_debug_set_fast_frame_flags": (None, [_I]),
-    "csmb_frame_batch_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I, _I]),
-    "csmb_frame_batch_supported": (C.c_int, [C.POINTER(Model), C.POINTER(Sampler), _I]),
-    "csmb_frame_batch": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
-                                   C.c_uint64, _P, C.c_size_t, _I, _P]),
-    "csmb_debug_set_frame_batch": (None, [_I]),
-    "csmb_debug_set_frame_batch_prof": (None, [_P]),
+                                               C.c_uint64, _P, _P, C.POINTER(ChainOpts), _P, C.c_size_t, _I, _P]),
+    "csmb_proj_table_bytes": (C.c_size_t, [C.POINTER(Model)]),
+    "csmb_proj_table_workspace_bytes": (C.c_size_t, [C.POINTER(Model)]),
+    "csmb_build_proj_table": (C.c_int, [C.POINTER(Model), _P, _P, C.c_size_t, _I, _P]),
     "csmb_frame_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I]),
-    "csmb_debug_set_frame_prof": (None, [_P]),
-    "csmb_debug_set_frame_flags": (None, [_I]),
-    "csmb_debug_set_frame_prefetch": (None, [_I, _I]),
-    "csmb_set_frame_ctas": (None, [_I]),
-    "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P,
-                                C.c_size_t, _P, _I, _P]),
-    "csmb_frame_b1_slot": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _I, _P,
-                                     C.c_size_t, _P, _I, _P]),
-    "csmb_frame_b1_depth": (C.c_int, [C.POINTER(Model), _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _P, C.c_size_t, _P,
-                                      _I, _P]),
+    "csmb_frame_b1": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64,
+                                C.POINTER(FrameOpts), _P, C.c_size_t, _P, _I, _P]),
+    "csmb_frame_b1_slot": (C.c_int, [C.POINTER(Model), _P, C.c_size_t, _P, _P, _P, _P, C.POINTER(Sampler), C.c_uint64, _I,
+                                     C.POINTER(FrameOpts), _P, C.c_size_t, _P, _I, _P]),
+    "csmb_frame_b1_depth": (C.c_int, [C.POINTER(Model), _P, _P, _P, C.POINTER(Sampler), C.c_uint64, C.POINTER(FrameOpts), _P,
+                                      C.c_size_t, _P, _I, _P]),
     "csmb_gemm_f32": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_layernorm": (C.c_int, [_P, _LL, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
     "csmb_mimi_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -131,6 +138,8 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.csmb_abi_version() != ABI_VERSION:
+            raise CsmbError(f"{LIB_PATH} has ABI version {handle.csmb_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
         _lib = handle
     return _lib
 

@@ -30,10 +30,25 @@ namespace csmb {
 constexpr int BF_MAX_STAGES = 6;
 constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
 
-static int g_bf_min_kblocks = 4;   // split-K: at least this many 64-wide K blocks per CTA
-static int g_bf_pdl = 1;           // programmatic dependent launch on/off (debug)
-static int g_bf_max_ctas = 148;
-static int g_bf_dbg = 0;          // bits 0, 1: timing experiments (GpArgs::dbg); bit 2: separate k_swiglu_split launch (A/B)
+// Split-K geometry is a constant of the library (see bf_pick_split): at least BF_MIN_KBLOCKS 64-wide K blocks per CTA and
+// about BF_SPLIT_CTAS CTAs per Linear.  No process-global tuning state: per-call switches travel in csmb_chain_opts.
+constexpr int BF_MIN_KBLOCKS = 4;
+constexpr int BF_SPLIT_CTAS = 148;
+
+struct ChainCfg {
+  int pdl;          // programmatic dependent launch
+  int dbg;          // bits 0, 1: timing experiments (GpArgs::dbg); bit 2: separate k_swiglu_split launch (A/B)
+  size_t smem;      // shared-memory budget of a Linear CTA (pipeline stages)
+};
+static ChainCfg chain_cfg(const csmb_chain_opts* o) {
+  ChainCfg c{1, 0, BF_SMEM_BUDGET};
+  if (o) {
+    c.pdl = o->no_pdl ? 0 : 1;
+    c.dbg = o->flags;
+    if (o->smem_kb >= 48 && (size_t)o->smem_kb * 1024 <= BF_SMEM_BUDGET) c.smem = (size_t)o->smem_kb * 1024;
+  }
+  return c;
+}
 
 // ---------------------------------------------------------------------------------------------- GEMM
 struct GpArgs {
@@ -211,17 +226,17 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   }
 }
 
-static int bf_pick_split_k(int R, int N, int K, int min_kblocks, int max_ctas) {
-  const int tiles = cdiv(N, TC_BM) * (R <= 256 ? 1 : cdiv(R, 128));
+// Split-K factor of a Linear: a function of its shape (N, K) ONLY — never of the number of rows, of the device or of a
+// tuning knob — so that a row's K blocks are summed in the same order in every batch: a sequence's tokens do not depend on
+// how many other sequences share the step (generation.py:139-161 is a batch-1 loop) or on how a job is sharded over GPUs.
+static int bf_pick_split(int N, int K) {
+  const int tiles = cdiv(N, TC_BM);
   const int nk = K / TC_BK;
-  int S = max_ctas / tiles;
-  const int cap = nk / (min_kblocks > 0 ? min_kblocks : 1);
+  int S = BF_SPLIT_CTAS / tiles;
+  const int cap = nk / BF_MIN_KBLOCKS;
   S = S < cap ? S : cap;
   return S < 1 ? 1 : S;
 }
-static int bf_pick_split(int R, int N, int K) { return bf_pick_split_k(R, N, K, g_bf_min_kblocks, g_bf_max_ctas); }
-// knob-independent bound used for sizing the partials buffer
-constexpr int BF_SIZING_MIN_KBLOCKS = 1, BF_SIZING_MAX_CTAS = 296;
 
 // ---------------------------------------------------------------------------------------------- fused element kernels
 struct PartIn {
@@ -289,6 +304,31 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
   for (int i = 0; i < 8; ++i) tot += red[i];
   __syncthreads();
   return tot;
+}
+
+// sum of squares of four values on top of ss, explicit fmas: every kernel that normalises a row rounds identically
+__device__ __forceinline__ float sumsq4(const float4 s, float ss) {
+  ss = __fmaf_rn(s.x, s.x, ss);
+  ss = __fmaf_rn(s.y, s.y, ss);
+  ss = __fmaf_rn(s.z, s.z, ss);
+  return __fmaf_rn(s.w, s.w, ss);
+}
+// y = RMSNorm(v) * w for one row of d = NV * 1024 values held as v[j] = columns threadIdx.x*4 + j*1024 (256 threads),
+// written as bf16 hi/lo planes (and fp32 y32 if given).  ss = this thread's sum of squares.
+template <int NV>
+__device__ __forceinline__ void norm_split_row(const float4 (&v)[NV], float ss, const float* __restrict__ w, float eps,
+                                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ y32,
+                                               float* red) {
+  constexpr int d = NV * 1024;
+  const float scale = rsqrtf(block_sum256(ss, red) / (float)d + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = threadIdx.x * 4 + j * 1024;
+    const float4 g = *reinterpret_cast<const float4*>(w + c);
+    const float4 y = make_float4(v[j].x * scale * g.x, v[j].y * scale * g.y, v[j].z * scale * g.z, v[j].w * scale * g.w);
+    store_split4(hi + c, lo + c, y.x, y.y, y.z, y.w);
+    if (y32) *reinterpret_cast<float4*>(y32 + c) = y;
+  }
 }
 
 // x[b][:] = sum_k audio_emb[prev[b][k] + k*V][:]   (generation.py:156-161 + models.py:82-92 + generation.py:32-36),
@@ -364,17 +404,9 @@ __global__ void __launch_bounds__(256) k_resid_norm_split(float* __restrict__ x,
       *reinterpret_cast<float4*>(xp) = s;
     }
     v[j] = s;
-    ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+    ss = sumsq4(s, ss);
   }
-  const float scale = rsqrtf(block_sum256(ss, red) / (float)d + eps);
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int c = threadIdx.x * 4 + j * 1024;
-    const float4 g = *reinterpret_cast<const float4*>(w + c);
-    const float4 y = make_float4(v[j].x * scale * g.x, v[j].y * scale * g.y, v[j].z * scale * g.z, v[j].w * scale * g.w);
-    store_split4(hi + (size_t)rout * d + c, lo + (size_t)rout * d + c, y.x, y.y, y.z, y.w);
-    if (y32) *reinterpret_cast<float4*>(y32 + (size_t)rout * d + c) = y;
-  }
+  norm_split_row<NV>(v, ss, w, eps, hi + (size_t)rout * d, lo + (size_t)rout * d, y32 ? y32 + (size_t)rout * d : nullptr, red);
 }
 
 // One block per (sequence b, kv head), warp g = query head kvh*G + g.  Stage 0 (all threads): sum the qkv partials of the
@@ -514,11 +546,21 @@ struct BfSample {
 // 81-84; same draw indexing as csmb_sample); frame[b][cb] = token; then the next depth step's input row
 // embed_audio(cb, token) (generation.py:86-89) as hi (the embedding is bf16: lo = 0) at row b*out_mul + out_mul-1,
 // and, for the first depth step (out_mul == 2), row 2b = h_last[b] (generation.py:56-64).
+// With a projected-embedding table (ptab = rows of codebook cb of csmb_build_proj_table, out_mul == 1) the next depth
+// step's projection Linear and first RMSNorm are done here instead: dx[b] = ptab[token] (= projection . embed_audio(cb,
+// token), the very fp32 values that Linear would produce) and hi/lo row b = split(RMSNorm(dx[b]) * nw), d_d = NVD * 1024.
+struct ProjIn {
+  const float* ptab;  // [V][dd] or null
+  float* dx;          // decoder residual stream [B][dd]
+  const float* nw;    // decoder layer 0 input-norm weight
+  float eps;
+  int dd;
+};
 __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample a, const int32_t* __restrict__ row_pos,
                                                       int cb, int32_t* __restrict__ frame, int ncb,
                                                       const uint16_t* __restrict__ audio_emb, int d, int embed,
                                                       const float* __restrict__ h_last, uint16_t* __restrict__ hi,
-                                                      uint16_t* __restrict__ lo, int out_mul) {
+                                                      uint16_t* __restrict__ lo, int out_mul, ProjIn pj) {
   extern __shared__ float sl[];
   __shared__ float red_v[8];
   __shared__ int red_i[8];
@@ -603,6 +645,27 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
   if (threadIdx.x == 0) frame[(size_t)b * ncb + cb] = tok;
   if (!embed) return;
   const int t = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  if (pj.ptab != nullptr) {
+    const float* src32 = pj.ptab + (size_t)t * pj.dd;
+    float* xr = pj.dx + (size_t)b * pj.dd;
+    if (pj.dd == 1024) {
+      float4 v[1];
+      v[0] = __ldg(reinterpret_cast<const float4*>(src32 + threadIdx.x * 4));
+      *reinterpret_cast<float4*>(xr + threadIdx.x * 4) = v[0];
+      norm_split_row<1>(v, sumsq4(v[0], 0.f), pj.nw, pj.eps, hi + (size_t)b * 1024, lo + (size_t)b * 1024, nullptr, red_v);
+    } else {
+      float4 v[2];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(src32 + threadIdx.x * 4 + j * 1024));
+        *reinterpret_cast<float4*>(xr + threadIdx.x * 4 + j * 1024) = v[j];
+        ss = sumsq4(v[j], ss);
+      }
+      norm_split_row<2>(v, ss, pj.nw, pj.eps, hi + (size_t)b * 2048, lo + (size_t)b * 2048, nullptr, red_v);
+    }
+    return;
+  }
   const uint16_t* src = audio_emb + ((size_t)t + (size_t)cb * V) * d;
   const size_t re = (size_t)(b * out_mul + out_mul - 1) * d;
   for (int c = threadIdx.x * 8; c < d; c += 256 * 8) {
@@ -618,9 +681,17 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
   }
 }
 
+// out[i] = sum of the S partials in the chain's fixed order (part_sum4): builds the projected-embedding table
+__global__ void __launch_bounds__(256) k_part_reduce(PartIn pi, size_t total4, float* __restrict__ out) {
+  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  *reinterpret_cast<float4*>(out + i4 * 4) = part_sum4(pi, i4 * 4);
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 template <typename... KArgs, typename... Args>
-static cudaError_t bf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static cudaError_t bf_launch(const ChainCfg& cc, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -630,7 +701,7 @@ static cudaError_t bf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_bf_pdl ? 1 : 0;
+  cfg.numAttrs = cc.pdl ? 1 : 0;
   count_launch();
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
@@ -642,13 +713,12 @@ struct FastWs {
   uint16_t *hi2, *lo2;  // SwiGLU output planes [rows][d_ff]: written by the gate|up Linear's epilogue while other CTAs of that
                         // launch still read hi / lo, read by the down projection
   size_t part_floats, bytes;
+  ChainCfg cc;
 };
 
-static size_t bf_part_floats(int R, int N, int K) {
-  return (size_t)bf_pick_split_k(R, N, K, BF_SIZING_MIN_KBLOCKS, BF_SIZING_MAX_CTAS) * R * N;
-}
+static size_t bf_part_floats(int R, int N, int K) { return (size_t)bf_pick_split(N, K) * R * N; }
 
-static FastWs bf_carve(const csmb_model& m, int B, void* base) {
+static FastWs bf_carve(const csmb_model& m, int B, void* base, const ChainCfg& cc = ChainCfg{1, 0, BF_SMEM_BUDGET}) {
   const csmb_llama &b = m.backbone, &d = m.decoder;
   const int qkv_b = (b.n_heads + 2 * b.n_kv_heads) * b.head_dim, qkv_d = (d.n_heads + 2 * d.n_kv_heads) * d.head_dim;
   const size_t R2 = (size_t)2 * B;
@@ -662,6 +732,7 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base) {
     return r;
   };
   FastWs w;
+  w.cc = cc;
   w.err = (int*)take(256);
   w.x = (float*)take((size_t)B * b.d_model * 4);
   w.dx = (float*)take(R2 * d.d_model * 4);
@@ -681,7 +752,7 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base) {
     need(R, d.d_model, b.d_model); need(R, qkv_d, d.d_model); need(R, d.d_model, d.n_heads * d.head_dim);
     need(R, 2 * d.d_ff, d.d_model); need(R, d.d_model, d.d_ff);
   }
-  w.part_floats = pf;  // sized for the most generous split the tuning knobs allow
+  w.part_floats = pf;
   w.part = (float*)take(w.part_floats * 4);
   w.bytes = off;
   return w;
@@ -691,7 +762,7 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base) {
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
                    const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr) {
   CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  const int S = bf_pick_split(R, N, K);
+  const int S = bf_pick_split(N, K);
   CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
   const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
   CUtensorMap mw, mhi, mlo;
@@ -699,14 +770,14 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
       !tc_make_map(&mlo, xlo ? xlo : w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
-  int nstages = (int)(BF_SMEM_BUDGET / stage);
+  int nstages = (int)(w.cc.smem / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, g_bf_dbg, 0, nullptr, nullptr};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & 3, 0, nullptr, nullptr};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
-  CSMB_CUDA(bf_launch(k_gemm_part_t<false>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
   *out = PartIn{w.part, S, (size_t)R * N, N};
   return CSMB_OK;
 }
@@ -719,23 +790,23 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   if (!tc_make_map(&mw, Wgu, 2 * F, K, TC_BM / 2) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
-  int nstages = (int)(BF_SMEM_BUDGET / stage);
+  int nstages = (int)(w.cc.smem / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
   GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, 0, F, w.hi2, w.lo2};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
-  CSMB_CUDA(bf_launch(k_gemm_part_t<true>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
   return CSMB_OK;
 }
 
 static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, const float* nw, float eps, float* y32, int rows,
                    int row_mul, int row_add, cudaStream_t st) {
   if (d == 1024)
-    CSMB_CUDA(bf_launch(k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
   else if (d == 2048)
-    CSMB_CUDA(bf_launch(k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
   else
     return CSMB_ERR_UNSUPPORTED;
   return CSMB_OK;
@@ -748,10 +819,10 @@ static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool
   CSMB_REQUIRE(smem <= 48 * 1024 && G >= 1 && G <= 8);
   const dim3 grid(B * L.n_kv_heads), block(32 * G);
   if (L.head_dim == 64)
-    CSMB_CUDA(bf_launch(k_attn_decode_fused<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+    CSMB_CUDA(bf_launch(w.cc, k_attn_decode_fused<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
                         rps, L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
   else if (L.head_dim == 128)
-    CSMB_CUDA(bf_launch(k_attn_decode_fused<128>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+    CSMB_CUDA(bf_launch(w.cc, k_attn_decode_fused<128>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
                         rps, L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
   else
     return CSMB_ERR_UNSUPPORTED;
@@ -772,10 +843,10 @@ static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool
     if ((rc = bf_attn(w, L, part, pool + (size_t)l * layer_stride, block_table, max_pages, pos_arr, pos0, rps, B, st))) return rc;
     if ((rc = bf_gemm(w, L.wo[l], R, d, L.n_heads * L.head_dim, &part, st))) return rc;
     if ((rc = bf_norm(w, x, d, part, 2, L.norm_post[l], L.eps, nullptr, R, 1, 0, st))) return rc;
-    if (g_bf_dbg & 4) {
+    if (w.cc.dbg & 4) {
       if ((rc = bf_gemm(w, L.wgu[l], R, 2 * F, d, &part, st))) return rc;
       const size_t total4 = (size_t)R * F / 4;
-      CSMB_CUDA(bf_launch(k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi2, w.lo2));
+      CSMB_CUDA(bf_launch(w.cc, k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi2, w.lo2));
     } else {
       if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st))) return rc;
     }
@@ -808,13 +879,6 @@ using namespace csmb;
 
 extern "C" {
 
-void csmb_debug_set_fast_frame_flags(int flags) { g_bf_dbg = flags; }
-void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas) {
-  if (min_kblocks >= BF_SIZING_MIN_KBLOCKS) g_bf_min_kblocks = min_kblocks;
-  if (pdl >= 0) g_bf_pdl = pdl ? 1 : 0;
-  if (max_ctas > 0) g_bf_max_ctas = max_ctas < BF_SIZING_MAX_CTAS ? max_ctas : BF_SIZING_MAX_CTAS;
-}
-
 size_t csmb_decode_frame_fast_workspace_bytes(const csmb_model* m, int batch) {
   if (!m || batch <= 0) return 0;
   return bf_carve(*m, batch, nullptr).bytes;
@@ -827,14 +891,14 @@ int csmb_decode_frame_fast_supported(const csmb_model* m, const csmb_sampler* sa
 int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* prev_frame, const int32_t* pos,
                            int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
                            size_t workspace_bytes, int device, void* stream) {
-  return csmb_decode_frame_fast_admit(m, bt, prev_frame, pos, frame, sampler, draw_base, nullptr, nullptr, workspace,
+  return csmb_decode_frame_fast_admit(m, bt, prev_frame, pos, frame, sampler, draw_base, nullptr, nullptr, nullptr, workspace,
                                       workspace_bytes, device, stream);
 }
 
 int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, const int32_t* prev_frame, const int32_t* pos,
                                  int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, const float* x_override,
-                                 const uint8_t* use_override, void* workspace, size_t workspace_bytes, int device,
-                                 void* stream) {
+                                 const uint8_t* use_override, const csmb_chain_opts* opts, void* workspace,
+                                 size_t workspace_bytes, int device, void* stream) {
   CSMB_ENTER(device);
   CSMB_REQUIRE((x_override == nullptr) == (use_override == nullptr));
   CSMB_REQUIRE(m && bt && prev_frame && pos && frame && sampler && workspace && bt->batch > 0);
@@ -842,8 +906,9 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   if (!bf_supported(*m, *sampler)) return CSMB_ERR_UNSUPPORTED;
   const csmb_llama &Bk = m->backbone, &D = m->decoder;
   const int B = bt->batch, db = Bk.d_model, dd = D.d_model, V = m->audio_vocab, ncb = m->n_codebooks;
-  FastWs w = bf_carve(*m, B, workspace);
+  FastWs w = bf_carve(*m, B, workspace, chain_cfg(opts));
   CSMB_REQUIRE(workspace_bytes >= w.bytes);
+  const float* ptab = opts ? opts->proj_table : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const int dec_pages = cdiv(ncb, CSMB_PAGE);
   BfSample sa;
@@ -857,28 +922,74 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   int rc;
   PartIn part;
   const size_t lg_smem = (size_t)V * sizeof(float);
+  const ProjIn no_proj{nullptr, nullptr, nullptr, 0.f, 0};
 
   // ---- backbone step (generation.py:34-42 with T = 1)
-  CSMB_CUDA(bf_launch(k_frame_embed_norm, dim3(B), dim3(256), 0, st, prev_frame, m->audio_emb, ncb, V, db, w.x, Bk.norm_in[0],
+  CSMB_CUDA(bf_launch(w.cc, k_frame_embed_norm, dim3(B), dim3(256), 0, st, prev_frame, m->audio_emb, ncb, V, db, w.x, Bk.norm_in[0],
                       Bk.eps, w.hi, w.lo, x_override, use_override));
   if ((rc = bf_layers(w, Bk, w.x, bt->kv_pool, bt->kv_layer_stride, bt->block_table, bt->max_pages, pos, 0, 1, B, w.h_last, st)))
     return rc;
   if ((rc = bf_gemm(w, m->c0_head, B, V, db, &part, st))) return rc;
   sa.draw_base = draw_base;
-  CSMB_CUDA(bf_launch(k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, 0, frame, ncb, m->audio_emb, db, 1,
-                      (const float*)w.h_last, w.hi, w.lo, 2));
+  CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, 0, frame, ncb, m->audio_emb, db, 1,
+                      (const float*)w.h_last, w.hi, w.lo, 2, no_proj));
   // ---- depth decoder (generation.py:56-90)
   for (int i = 1; i < ncb; ++i) {
     const int rps = (i == 1) ? 2 : 1, R = B * rps;
-    if ((rc = bf_gemm(w, m->projection, R, dd, db, &part, st))) return rc;
-    if ((rc = bf_norm(w, w.dx, dd, part, 1, D.norm_in[0], D.eps, nullptr, R, 1, 0, st))) return rc;
+    if (i == 1 || ptab == nullptr) {
+      // projection Linear + first RMSNorm; with the table, k_sample_embed of step i-1 already left dx and its planes
+      if ((rc = bf_gemm(w, m->projection, R, dd, db, &part, st))) return rc;
+      if ((rc = bf_norm(w, w.dx, dd, part, 1, D.norm_in[0], D.eps, nullptr, R, 1, 0, st))) return rc;
+    }
     if ((rc = bf_layers(w, D, w.dx, bt->dec_kv_pool, bt->dec_kv_layer_stride, nullptr, dec_pages, nullptr, i == 1 ? 0 : i, rps, B,
                         nullptr, st)))
       return rc;
     if ((rc = bf_gemm(w, m->audio_head_t + (size_t)(i - 1) * V * dd, B, V, dd, &part, st))) return rc;
     sa.draw_base = draw_base + (uint64_t)i;
-    CSMB_CUDA(bf_launch(k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, i, frame, ncb, m->audio_emb, db,
-                        i + 1 < ncb ? 1 : 0, (const float*)nullptr, w.hi, w.lo, 1));
+    const int embed = i + 1 < ncb ? 1 : 0;
+    const ProjIn pj = (ptab && embed) ? ProjIn{ptab + (size_t)i * V * dd, w.dx, D.norm_in[0], D.eps, dd} : no_proj;
+    CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, i, frame, ncb, m->audio_emb, db,
+                        embed, (const float*)nullptr, w.hi, w.lo, 1, pj));
+  }
+  return CSMB_OK;
+}
+
+// ---- projected-embedding table -------------------------------------------------------------------------------------
+size_t csmb_proj_table_bytes(const csmb_model* m) {
+  if (!m) return 0;
+  return (size_t)m->n_codebooks * m->audio_vocab * m->decoder.d_model * sizeof(float);
+}
+size_t csmb_proj_table_workspace_bytes(const csmb_model* m) {
+  if (!m) return 0;
+  const size_t V = m->audio_vocab, db = m->backbone.d_model, dd = m->decoder.d_model;
+  return 256 + ((V * db * 2 + 255) & ~(size_t)255) + bf_part_floats((int)V, (int)dd, (int)db) * sizeof(float);
+}
+
+int csmb_build_proj_table(const csmb_model* m, float* table, void* workspace, size_t workspace_bytes, int device, void* stream) {
+  CSMB_ENTER(device);
+  CSMB_REQUIRE(m && table && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  CSMB_REQUIRE(workspace_bytes >= csmb_proj_table_workspace_bytes(m));
+  const int V = m->audio_vocab, db = m->backbone.d_model, dd = m->decoder.d_model, ncb = m->n_codebooks;
+  CSMB_REQUIRE(db % TC_BK == 0 && dd % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = static_cast<char*>(workspace);
+  FastWs w = {};
+  w.cc = ChainCfg{0, 0, BF_SMEM_BUDGET};
+  w.err = reinterpret_cast<int*>(p);
+  uint16_t* zero = reinterpret_cast<uint16_t*>(p + 256);
+  const size_t zbytes = ((size_t)V * db * 2 + 255) & ~(size_t)255;
+  w.part = reinterpret_cast<float*>(p + 256 + zbytes);
+  w.part_floats = bf_part_floats(V, dd, db);
+  CSMB_CUDA(cudaMemsetAsync(p, 0, 256 + zbytes, st));
+  int rc;
+  for (int cb = 0; cb < ncb; ++cb) {
+    // the rows of codebook cb are exact bf16 values: hi plane = the embedding table itself, lo plane = 0, which is what
+    // k_sample_embed hands to the projection Linear of the chain; same kernel, same split, same summation order
+    PartIn part;
+    if ((rc = bf_gemm(w, m->projection, V, dd, db, &part, st, m->audio_emb + (size_t)cb * V * db, zero))) return rc;
+    const size_t total4 = (size_t)V * dd / 4;
+    k_part_reduce<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(part, total4, table + (size_t)cb * V * dd);
+    CSMB_LAUNCH_CHECK();
   }
   return CSMB_OK;
 }

@@ -86,6 +86,7 @@ struct FrameParams {
   unsigned* nonce;             // launch counter in the workspace: read by every CTA at start, bumped by CTA 0 at the
                                // end, so consecutive launches (also CUDA-graph replays) never share tags
   int* abort_flag;
+  int32_t* status;             // caller's sticky status word (optional): receives the first abort code, never cleared here
   int pf_max, pf_interval;     // producer: L2 prefetch distance (16 KiB stages, 0 = off) and pacing (SM cycles)
   int dbg;                     // debug switches (0 in production): 1 = skip GEMV math, 8 = no weight streaming
   unsigned long long* prof;    // optional [gridDim][16] phase timers in SM cycles (debug); null in production
@@ -203,6 +204,7 @@ __device__ __forceinline__ bool check_abort(Ctx& c) {
 }
 __device__ __forceinline__ void raise_abort(Ctx& c, int code) {
   atomicCAS(c.p->abort_flag, 0, code);
+  if (c.p->status != nullptr) atomicCAS(c.p->status, 0, code);  // sticky across launches: the caller reads it whenever it likes
   c.aborted = true;
 }
 __device__ __forceinline__ void mbar_wait(Ctx& c, uint64_t* b, uint32_t parity, int code) {
@@ -1353,18 +1355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
 
 using namespace csmb;
 
-static unsigned long long* g_prof_ptr = nullptr;  // debug only: csmb_debug_set_frame_prof
-static int g_dbg_flags = 0;
-static int g_pf_max = 0, g_pf_interval = 700;
-static int g_frame_ctas = 0;  // 0 = automatic (see launch_frame)
-
 extern "C" {
-
-/* debug: device buffer [n_sms][16] u64 receiving per-CTA phase timers (SM cycles) of later csmb_frame_b1 launches */
-void csmb_debug_set_frame_prof(unsigned long long* device_buf) { g_prof_ptr = device_buf; }
-void csmb_debug_set_frame_flags(int flags) { g_dbg_flags = flags & 0xff; }
-void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles) { g_pf_max = max_stages; g_pf_interval = interval_cycles; }
-void csmb_set_frame_ctas(int n) { g_frame_ctas = n > 0 ? n : 0; }
 
 static size_t frame_ws_words(const csmb_model* m) {
   const csmb_llama &B = m->backbone, &D = m->decoder;
@@ -1390,8 +1381,8 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
 
 static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                         const int32_t* prev_frame, const float* h_in, const int32_t* pos, int32_t* frame,
-                        const csmb_sampler* sampler, uint64_t draw_base, uint32_t seq, void* workspace, size_t workspace_bytes,
-                        int32_t* status, int device, void* stream) {
+                        const csmb_sampler* sampler, uint64_t draw_base, uint32_t seq, const csmb_frame_opts* opts,
+                        void* workspace, size_t workspace_bytes, int32_t* status, int device, void* stream) {
   CSMB_ENTER(device);
   CSMB_REQUIRE(m && pos && frame && sampler && workspace);
   CSMB_REQUIRE(h_in || (kv_pool && block_table && prev_frame));
@@ -1454,10 +1445,12 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   p.seed_hi = (uint32_t)(sampler->seed >> 32);
   p.draw_base = draw_base;
   p.seq = seq;
-  p.prof = g_prof_ptr;
-  p.dbg = g_dbg_flags;
-  p.pf_max = g_pf_max;
-  p.pf_interval = g_pf_interval;
+  p.status = status;
+  p.prof = opts ? opts->prof : nullptr;
+  p.dbg = opts ? (opts->flags & 0xff) : 0;
+  p.pf_max = opts ? opts->prefetch_stages : 0;
+  p.pf_interval = (opts && opts->prefetch_interval > 0) ? opts->prefetch_interval : 700;
+  const int want_ctas = opts ? opts->ctas : 0;
 
   static const size_t dyn_smem = (size_t)NSTAGES * STAGE_BYTES + KVS_BYTES;  // ring + decoder KV staging
   CSMB_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
@@ -1476,8 +1469,8 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   // run the codec's streaming step of the previous frame concurrently (second stream).
   auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
   int grid = sms;
-  if (g_frame_ctas > 0) {
-    grid = g_frame_ctas < sms ? g_frame_ctas : sms;
+  if (want_ctas > 0) {
+    grid = want_ctas < sms ? want_ctas : sms;
   } else {
     const int g = gcd(gcd(gcd(B.d_model, B.d_ff), gcd(D.d_model, D.d_ff)), gcd((int)nqkv_b, (int)nqkv_d));
     for (int c = sms; c >= (sms * 3) / 4; --c)
@@ -1487,32 +1480,31 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   CSMB_REQUIRE(fits(grid));
   CSMB_CUDA(cudaLaunchCooperativeKernel((void*)k_frame, dim3(grid), dim3(NTHREADS), args, dyn_smem, st));
   count_launch();
-  if (status) CSMB_CUDA(cudaMemcpyAsync(status, p.abort_flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return CSMB_OK;
 }
 
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
-                  uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
-                  void* stream) {
-  return launch_frame(m, kv_pool, kv_layer_stride, block_table, prev_frame, nullptr, pos, frame, sampler, draw_base, 0u,
+                  uint64_t draw_base, const csmb_frame_opts* opts, void* workspace, size_t workspace_bytes, int32_t* status,
+                  int device, void* stream) {
+  return launch_frame(m, kv_pool, kv_layer_stride, block_table, prev_frame, nullptr, pos, frame, sampler, draw_base, 0u, opts,
                       workspace, workspace_bytes, status, device, stream);
 }
 
 int csmb_frame_b1_slot(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table_row,
                        const int32_t* prev_frame_row, const int32_t* pos, int32_t* frame_row, const csmb_sampler* sampler,
-                       uint64_t draw_base, int seq_index, void* workspace, size_t workspace_bytes, int32_t* status,
-                       int device, void* stream) {
+                       uint64_t draw_base, int seq_index, const csmb_frame_opts* opts, void* workspace, size_t workspace_bytes,
+                       int32_t* status, int device, void* stream) {
   if (seq_index < 0) return CSMB_ERR_INVALID;
   return launch_frame(m, kv_pool, kv_layer_stride, block_table_row, prev_frame_row, nullptr, pos, frame_row, sampler,
-                      draw_base, (uint32_t)seq_index, workspace, workspace_bytes, status, device, stream);
+                      draw_base, (uint32_t)seq_index, opts, workspace, workspace_bytes, status, device, stream);
 }
 
 int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t* pos, int32_t* frame,
-                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
-                        int32_t* status, int device, void* stream) {
+                        const csmb_sampler* sampler, uint64_t draw_base, const csmb_frame_opts* opts, void* workspace,
+                        size_t workspace_bytes, int32_t* status, int device, void* stream) {
   if (!h_last) return CSMB_ERR_INVALID;
-  return launch_frame(m, nullptr, 0, nullptr, nullptr, h_last, pos, frame, sampler, draw_base, 0u, workspace,
+  return launch_frame(m, nullptr, 0, nullptr, nullptr, h_last, pos, frame, sampler, draw_base, 0u, opts, workspace,
                       workspace_bytes, status, device, stream);
 }
 

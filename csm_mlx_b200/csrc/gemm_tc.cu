@@ -174,8 +174,11 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-static int pick_split(int R, int N, int K) {
-  const int tiles = cdiv(N, TC_BM) * (R <= 256 ? 1 : cdiv(R, 128));
+// Split-K factor: a function of the Linear's shape (N, K) ONLY.  A row's K blocks are therefore summed in the same
+// order whatever the number of rows in the call (and whichever other sequences' rows they are): a sequence's tokens do
+// not depend on its neighbours in a batch, like the reference's batch-1 loop (generation.py:139-161).
+static int pick_split(int N, int K) {
+  const int tiles = cdiv(N, TC_BM);
   const int nk = K / TC_BK;
   int S = 1;
   while (S < 16 && tiles * S * 2 <= 160 && nk / (S * 2) >= 4) S *= 2;
@@ -211,7 +214,7 @@ bool tc_make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows
 }
 
 size_t linear_tc_workspace_bytes(int R, int N, int K) {
-  const int S = pick_split(R, N, K);
+  const int S = pick_split(N, K);
   return (size_t)2 * R * K * sizeof(uint16_t) + (S > 1 ? (size_t)S * R * N * sizeof(float) : 0) + 1024;
 }
 
@@ -226,7 +229,7 @@ int launch_linear_tc(const float* x, int ldx, const uint16_t* W, float* y, int l
   uint16_t* lo = hi + (size_t)R * K;
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(lo + (size_t)R * K) + ((256 - (((size_t)4 * R * K) & 255)) & 255));
   const size_t total = (size_t)R * K;
-  const int S = pick_split(R, N, K);
+  const int S = pick_split(N, K);
   // the error flag (first int of the workspace) is sticky: the owner zeroes the workspace once
   k_split_bf16<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(x, ldx, hi, lo, K, total);
   CSMB_LAUNCH_CHECK();

@@ -24,10 +24,14 @@ struct Workspace {
   void* tc;                                // scratch of the tensor-core linear (bf16 hi/lo split, split-K partials)
   size_t tc_bytes;
   size_t bytes;
+  bool row_invariant;                      // CSMB_BATCH_ROW_INVARIANT: every Linear on the tensor-core path, whatever R
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-constexpr int TC_MIN_ROWS = 9;   // from this many rows on, linears run on the tensor cores (gemm_tc.cu); <= 8: GEMV kernels
+// From this many rows on, linears run on the tensor cores (gemm_tc.cu); <= 8: GEMV kernels.  A batch flagged
+// CSMB_BATCH_ROW_INVARIANT takes the tensor-core path for ANY row count, so that what a row computes never depends on
+// how many other rows (other sequences' prompts, other requests of a serving step) share the call.
+constexpr int TC_MIN_ROWS = 9;
 
 struct Workspace;
 static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
@@ -71,7 +75,7 @@ static Workspace carve(const csmb_model& m, int max_rows, void* base) {
   w.c0_tmp = (int32_t*)take(R * 4);
   // tensor-core linear scratch: the largest requirement over this model's (N, K) shapes at max_rows rows
   size_t tcb = 0;
-  if (max_rows >= TC_MIN_ROWS) {
+  {
     const int shapes[][2] = {{qkv_b, b.d_model}, {b.d_model, b.n_heads * b.head_dim}, {2 * b.d_ff, b.d_model}, {b.d_model, b.d_ff},
                              {qkv_d, d.d_model}, {d.d_model, d.n_heads * d.head_dim}, {2 * d.d_ff, d.d_model}, {d.d_model, d.d_ff},
                              {m.audio_vocab, b.d_model}, {m.audio_vocab, d.d_model}, {d.d_model, b.d_model}};
@@ -84,12 +88,13 @@ static Workspace carve(const csmb_model& m, int max_rows, void* base) {
   w.tc = take(tcb);
   w.tc_bytes = tcb;
   w.bytes = off;
+  w.row_invariant = false;
   return w;
 }
 
 static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
                int accumulate, cudaStream_t st) {
-  if (R >= TC_MIN_ROWS && K % 64 == 0 && w.tc != nullptr && w.tc_bytes >= linear_tc_workspace_bytes(R, N, K))
+  if ((R >= TC_MIN_ROWS || w.row_invariant) && K % 64 == 0 && w.tc != nullptr && w.tc_bytes >= linear_tc_workspace_bytes(R, N, K))
     return launch_linear_tc(x, ldx, W, y, ldy, R, N, K, accumulate, w.tc, w.tc_bytes, st);
   return launch_linear(x, ldx, W, y, ldy, R, N, K, accumulate, st);
 }
@@ -243,6 +248,7 @@ int csmb_backbone_forward(const csmb_model* m, const csmb_batch* b, const int32_
   CSMB_REQUIRE(b && b->workspace && R > 0 && n_last > 0 && n_last <= R);
   CSMB_REQUIRE(b->workspace_bytes >= carve(*m, R, nullptr).bytes);
   Workspace w = carve(*m, R, b->workspace);
+  w.row_invariant = (b->flags & CSMB_BATCH_ROW_INVARIANT) != 0;
   return backbone_forward(*m, *b, w, tokens, mask, row_seq, row_pos, R, last_rows, n_last, h_last, c0_logits,
                           (cudaStream_t)stream);
 }
@@ -257,6 +263,7 @@ int csmb_depth_decode(const csmb_model* m, const csmb_batch* b, const float* h_l
   CSMB_REQUIRE(step_begin >= 1 && step_begin <= step_end && step_end <= m->n_codebooks);
   CSMB_REQUIRE(b->workspace_bytes >= carve(*m, 2 * b->batch, nullptr).bytes);
   Workspace w = carve(*m, 2 * b->batch, b->workspace);
+  w.row_invariant = (b->flags & CSMB_BATCH_ROW_INVARIANT) != 0;
   return depth_decode(*m, *b, w, h_last, frame, *sampler, draw_base, pos, logits_out, forced, step_begin, step_end,
                       (cudaStream_t)stream);
 }
@@ -270,6 +277,7 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
   const int B = b->batch, ncb = m->n_codebooks;
   CSMB_REQUIRE(b->workspace_bytes >= carve(*m, 2 * B, nullptr).bytes);
   Workspace w = carve(*m, 2 * B, b->workspace);
+  w.row_invariant = (b->flags & CSMB_BATCH_ROW_INVARIANT) != 0;
   cudaStream_t st = (cudaStream_t)stream;
   k_frame_to_input<<<cdiv(B * (ncb + 1), 128), 128, 0, st>>>(prev_frame, w.tokens, w.mask, B, ncb);
   CSMB_LAUNCH_CHECK();

@@ -42,13 +42,13 @@ def _resolve_sampler(temperature: float, sampler, seed: Optional[int]):
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
         return SamplerSpec(temperature=float(temperature), seed=seed), None
-    if isinstance(sampler, DeviceSampler):
-        spec = sampler.spec
+    if isinstance(sampler, (DeviceSampler, SamplerSpec)):
+        spec = sampler.spec if isinstance(sampler, DeviceSampler) else sampler
+        if seed is None and spec.seed is None:   # unseeded sampler: a fresh Philox key per call, like the temperature= form
+            seed = int.from_bytes(os.urandom(8), "little")
         if seed is not None:
             spec = SamplerSpec(**{**spec.__dict__, "seed": seed})
         return spec, None
-    if isinstance(sampler, SamplerSpec):
-        return sampler, None
     if callable(sampler):
         return SamplerSpec(temperature=0.0), sampler  # foreign callable: host round trip per codebook
     raise TypeError("sampler must be a csm_mlx.sample_utils.make_sampler(...) object or a callable logits -> ids")
@@ -136,6 +136,16 @@ class _Session:
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
         self.prev = frame
         return frame
+
+    def status_word(self) -> torch.Tensor:
+        return self.state.status_word()
+
+    @staticmethod
+    def raise_if_aborted(host_status: torch.Tensor) -> None:
+        """Called on the pinned copy that travels with every frame: a bounded wait that timed out inside a fused kernel
+        (its tokens are garbage) surfaces one frame late instead of at the end of the utterance, or never."""
+        if int(host_status[0]) != 0:
+            raise RuntimeError(f"libcsm_b200: a fused LM kernel aborted (code {int(host_status[0])}); the frame is invalid")
 
     def close(self) -> None:
         """Raises if the persistent kernel reported an abort; otherwise returns the state to the model's pool."""
@@ -230,13 +240,14 @@ def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tens
     spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
     sess = _Session(model, prompts, max_audio_frames, spec, host_sampler, logits_processors)
     B, ncb = len(prompts), model.n_audio_codebooks
-    mirror = _HostMirror([((B, ncb), torch.int32)], model.device)
+    mirror = _HostMirror([((B, ncb), torch.int32), ((1,), torch.int32)], model.device)
     out: List[List[torch.Tensor]] = [[] for _ in range(B)]
     done = [False] * B
     pending: Optional[int] = None
 
     def drain(slot: int) -> None:
-        (host,) = mirror.wait(slot)
+        host, host_status = mirror.wait(slot)
+        sess.raise_if_aborted(host_status)
         for b in range(B):
             if done[b]:
                 continue
@@ -247,7 +258,7 @@ def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tens
 
     for _ in range(max_audio_frames):
         frame = sess.step()
-        slot = mirror.push([frame])
+        slot = mirror.push([frame, sess.status_word()])
         if pending is not None:
             drain(pending)
             if all(done):
@@ -316,22 +327,24 @@ def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, c
     ncb = model.n_audio_codebooks
     mimi = get_audio_tokenizer(ncb)
     lane = _CodecLane(mimi.acquire_decode_stream(batch=1), model.device)
-    mirror = _HostMirror([((1, ncb), torch.int32), ((1, 1, 1920), torch.float32)], model.device)
+    mirror = _HostMirror([((1, ncb), torch.int32), ((1, 1, 1920), torch.float32), ((1,), torch.int32)], model.device)
     pending: Optional[int] = None
     try:
         for _ in range(max_audio_frames):
             frame = sess.step()
             audio = lane.step(frame)
             with torch.cuda.stream(lane.stream):
-                slot = mirror.push([frame, audio])
+                slot = mirror.push([frame, audio, sess.status_word()])
             if pending is not None:
-                host_frame, host_audio = mirror.wait(pending)
+                host_frame, host_audio, host_status = mirror.wait(pending)
+                sess.raise_if_aborted(host_status)
                 if not bool(host_frame.any()):
                     return  # eos: the speculative frame just enqueued is discarded
                 yield host_audio.reshape(-1).clone()
             pending = slot
         if pending is not None:
-            host_frame, host_audio = mirror.wait(pending)
+            host_frame, host_audio, host_status = mirror.wait(pending)
+            sess.raise_if_aborted(host_status)
             if bool(host_frame.any()):
                 yield host_audio.reshape(-1).clone()
     finally:

@@ -97,6 +97,7 @@ class CSM:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
             if torch.cuda.is_available() else torch.device("cuda")
         self._desc: Optional[_lib.Model] = None
+        self._proj_table: Optional[torch.Tensor] = None
         self._loaded = False
 
     # ------------------------------------------------------------------ reference-visible views
@@ -177,6 +178,7 @@ class CSM:
             self._finalize(known)
         else:
             cur = self.parameters()
+            self._proj_table = None  # derived from projection / audio_embeddings: rebuilt on next use
             for k, v in known.items():
                 if k == "audio_head":
                     self._audio_head_t.copy_(v.transpose(1, 2).to(self._audio_head_t.dtype))
@@ -243,6 +245,29 @@ class CSM:
             m.n_codebooks, m.max_pos = self.n_audio_codebooks, MAX_SEQ_LEN
             self._desc = m
         return self._desc
+
+    def proj_table(self) -> Optional[torch.Tensor]:
+        """(n_codebooks, n_audio_vocab, d_decoder) fp32 table of ``projection(embed_audio(cb, token))`` (generation.py:75 over
+        models.py:79-80 rows) for the batched chain's depth steps, built once on first use with the chain's own projection
+        Linear (``csmb_build_proj_table``: bit-identical to running it).  None if the shapes are not the chain's."""
+        self._require_loaded()
+        if self._proj_table is None:
+            if self.n_backbone_embedding % 64 != 0 or self.n_decoder_embedding not in (1024, 2048):
+                return None
+            import ctypes as C
+
+            dev_idx = _lib.require_device(self.device)
+            l, m = _lib.lib(), self.desc()
+            tab = torch.empty((self.n_audio_codebooks, self.n_audio_vocab, self.n_decoder_embedding), device=self.device,
+                              dtype=torch.float32)
+            ws = torch.empty((l.csmb_proj_table_workspace_bytes(C.byref(m)),), device=self.device, dtype=torch.uint8)
+            _lib.check(l.csmb_build_proj_table(C.byref(m), tab.data_ptr(), ws.data_ptr(), ws.numel(), dev_idx,
+                                               _lib.stream_ptr(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()  # the scratch is freed on return
+            if int(ws[:4].view(torch.int32).item()) != 0:
+                raise _lib.CsmbError("csmb_build_proj_table: a bounded wait of the tensor-core linear timed out")
+            self._proj_table = tab
+        return self._proj_table
 
     # ------------------------------------------------------------------ reference methods (models.py:79-92)
     def embed_audio(self, codebook: int, tokens: torch.Tensor) -> torch.Tensor:

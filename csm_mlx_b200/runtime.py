@@ -28,18 +28,22 @@ class SamplerSpec:
     top_p: float = 0.0
     min_p: float = 0.0
     min_tokens_to_keep: int = 1
-    seed: int = 0
+    seed: Optional[int] = 0    # None: "draw a fresh key per generate() call" (resolved by generation._resolve_sampler)
 
     def to_c(self) -> _lib.Sampler:
         return _lib.Sampler(float(self.temperature), int(self.top_k) if self.top_k and self.top_k > 0 else 0,
                             float(self.top_p), float(self.min_p), int(self.min_tokens_to_keep),
-                            int(self.seed) & 0xFFFFFFFFFFFFFFFF)
+                            int(self.seed or 0) & 0xFFFFFFFFFFFFFFFF)
 
 
 class LMState:
-    def __init__(self, model: CSM, batch: int, max_len: int = MAX_SEQ_LEN):
+    def __init__(self, model: CSM, batch: int, max_len: int = MAX_SEQ_LEN, row_invariant: bool = False):
+        """``row_invariant``: every Linear of the row-based calls runs on the tensor-core path whatever the row count
+        (``CSMB_BATCH_ROW_INVARIANT``) and the fused chain is used from one sequence up, so that a sequence's tokens do
+        not depend on what it is batched with — the serving engine sets it (generation.py:139-161 is a batch-1 loop)."""
         model._require_loaded()
         self.model = model
+        self.row_invariant = bool(row_invariant)
         self.device = model.device
         self.dev_idx = _lib.require_device(self.device)
         self.batch = batch
@@ -65,6 +69,20 @@ class LMState:
         self.h_last = torch.empty((batch, b.hidden_size), device=self.device, dtype=torch.float32)
         self.c0_logits = torch.empty((batch, model.n_audio_vocab), device=self.device, dtype=torch.float32)
         self._seq_iota = torch.arange(batch, device=self.device, dtype=torch.int32)
+        # Buffers of the fused chain are created HERE, never lazily inside decode_frame: a torch.zeros under CUDA-graph
+        # capture becomes a memset node that every replay would repeat (wiping the sticky error flag and the admission
+        # overrides armed for that step).
+        self._fast_ws: Optional[torch.Tensor] = None
+        self._ovr_x: Optional[torch.Tensor] = None
+        self._ovr_flag: Optional[torch.Tensor] = None
+        self._ovr_armed = False
+        self._chain_opts = None   # (key, _lib.ChainOpts) of the last chain call
+        self._fws: Optional[torch.Tensor] = None
+        self.frame_status: Optional[torch.Tensor] = None
+        self._frame_opts: Optional[_lib.FrameOpts] = None
+        self._graph_key = None
+        if self._chain_possible():
+            self._prepare_chain()
 
     # ------------------------------------------------------------------ reuse across utterances
     @classmethod
@@ -74,7 +92,7 @@ class LMState:
         need = min(int(max_len), MAX_SEQ_LEN)
         pool = model.__dict__.setdefault("_lm_pool", [])
         for i, st in enumerate(pool):
-            if st.model is model and st.batch == batch and st.max_len >= need:
+            if st.model is model and st.batch == batch and st.max_len >= need and not st.row_invariant:
                 pool.pop(i)
                 st.reset()
                 return st
@@ -102,6 +120,7 @@ class LMState:
         b.block_table = self.block_table.data_ptr()
         b.dec_kv_pool, b.dec_kv_layer_stride = self.dec_kv_pool.data_ptr(), self.dec_kv_pool.stride(0)
         b.workspace, b.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        b.flags = _lib.BATCH_ROW_INVARIANT if self.row_invariant else 0
         return b
 
     def _stream(self) -> int:
@@ -184,46 +203,59 @@ class LMState:
             self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx, self._stream()))
         self._advance()
 
-    def fast_supported(self, sampler: SamplerSpec) -> bool:
-        """True if the fused kernel chain of csrc/batch_frame.cu covers this model and sampler (tensor-core linears
-        from 2 sequences up; ``CSMB_DISABLE_FAST=1`` or ``CSMB_FAST_MIN_BATCH`` override)."""
-        if os.environ.get("CSMB_DISABLE_FAST", "0") == "1":
+    def _chain_min_batch(self) -> int:
+        return 1 if self.row_invariant else int(os.environ.get("CSMB_FAST_MIN_BATCH", "2"))
+
+    def _chain_possible(self) -> bool:
+        if os.environ.get("CSMB_DISABLE_FAST", "0") == "1" or self.batch < self._chain_min_batch():
             return False
-        if self.batch < int(os.environ.get("CSMB_FAST_MIN_BATCH", "2")):
+        s = SamplerSpec().to_c()
+        return bool(_lib.lib().csmb_decode_frame_fast_supported(C.byref(self.model.desc()), C.byref(s)))
+
+    def _prepare_chain(self) -> None:
+        """Workspace, admission-override buffers and per-call options of the fused chain (eager; see __init__)."""
+        if self._fast_ws is not None:
+            return
+        nbytes = _lib.lib().csmb_decode_frame_fast_workspace_bytes(C.byref(self.model.desc()), self.batch)
+        self._fast_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # sticky error flag inside
+        d = self.model.backbone.args.hidden_size
+        self._ovr_x = torch.zeros((self.batch, d), device=self.device, dtype=torch.float32)
+        self._ovr_flag = torch.zeros((self.batch,), device=self.device, dtype=torch.uint8)
+        if os.environ.get("CSMB_NO_PROJ_TABLE", "0") != "1":
+            self.model.proj_table()   # built once per model (260 MB for csm_1b), outside any capture
+
+    def _chain_opts_now(self):
+        """csmb_chain_opts of the next chain call, from the (A/B, debug) environment switches: (key tuple, struct)."""
+        no_pdl = 1 if os.environ.get("CSMB_CHAIN_NO_PDL", "0") == "1" else 0
+        flags = int(os.environ.get("CSMB_CHAIN_FLAGS", "0"))
+        smem_kb = int(os.environ.get("CSMB_CHAIN_SMEM_KB", "0"))
+        tab = None if os.environ.get("CSMB_NO_PROJ_TABLE", "0") == "1" else self.model.proj_table()
+        key = (no_pdl, flags, smem_kb, tab is not None)
+        if self._chain_opts is None or self._chain_opts[0] != key:
+            o = _lib.ChainOpts()
+            o.no_pdl, o.flags, o.smem_kb = no_pdl, flags, smem_kb
+            o.proj_table = tab.data_ptr() if tab is not None else None
+            self._chain_opts = (key, o)
+        return self._chain_opts
+
+    def fast_supported(self, sampler: SamplerSpec) -> bool:
+        """True if the fused kernel chain of csrc/batch_frame.cu covers this model, batch and sampler (tensor-core linears
+        from 2 sequences up — from 1 for a row-invariant state; ``CSMB_DISABLE_FAST=1`` / ``CSMB_FAST_MIN_BATCH`` override)."""
+        if self._fast_ws is None or os.environ.get("CSMB_DISABLE_FAST", "0") == "1":
             return False
         s = sampler.to_c()
         return bool(_lib.lib().csmb_decode_frame_fast_supported(C.byref(self.model.desc()), C.byref(s)))
-
-    def persist_supported(self, sampler: SamplerSpec) -> bool:
-        """True if the persistent batched frame kernel (csrc/batch_persist.cu) is requested (``CSMB_ENABLE_PERSIST=1``)
-        and covers this model, sampler and batch.  It is token-identical to the kernel chain but measured slower
-        (13.3 vs 8.3 ms per frame-step at 64 sequences, profiles/r01_batched_frame.md), so the chain is the default."""
-        if os.environ.get("CSMB_ENABLE_PERSIST", "0") != "1" or not self.fast_supported(sampler):
-            return False
-        s = sampler.to_c()
-        return bool(_lib.lib().csmb_frame_batch_supported(C.byref(self.model.desc()), C.byref(s), self.batch))
 
     def decode_frame(self, prev_frame: torch.Tensor, frame: torch.Tensor, sampler: SamplerSpec) -> None:
         """Whole frame on device, no host round trip (generation.py:21-92 with T=1)."""
         self._check_room()
         bd = self._batch_desc()
         s = sampler.to_c()
-        if self.persist_supported(sampler) and not getattr(self, "_ovr_armed", False):
-            if getattr(self, "_persist_ws", None) is None:
-                nbytes = _lib.lib().csmb_frame_batch_workspace_bytes(C.byref(self.model.desc()), self.batch, self.dev_idx)
-                self._persist_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # barrier counters + error flag
-            _lib.check(_lib.lib().csmb_frame_batch(
-                C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
-                C.byref(s), 0, self._persist_ws.data_ptr(), self._persist_ws.numel(), self.dev_idx, self._stream()))
-        elif self.fast_supported(sampler):
-            if getattr(self, "_fast_ws", None) is None:
-                nbytes = _lib.lib().csmb_decode_frame_fast_workspace_bytes(C.byref(self.model.desc()), self.batch)
-                self._fast_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)  # sticky error flag inside
-            self._override_buffers()
+        if self.fast_supported(sampler):
             _lib.check(_lib.lib().csmb_decode_frame_fast_admit(
                 C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
-                C.byref(s), 0, self._ovr_x.data_ptr(), self._ovr_flag.data_ptr(), self._fast_ws.data_ptr(),
-                self._fast_ws.numel(), self.dev_idx, self._stream()))
+                C.byref(s), 0, self._ovr_x.data_ptr(), self._ovr_flag.data_ptr(), C.byref(self._chain_opts_now()[1]),
+                self._fast_ws.data_ptr(), self._fast_ws.numel(), self.dev_idx, self._stream()))
         else:
             _lib.check(_lib.lib().csmb_decode_frame(
                 C.byref(self.model.desc()), C.byref(bd), prev_frame.data_ptr(), self.pos.data_ptr(), frame.data_ptr(),
@@ -231,12 +263,6 @@ class LMState:
         self._advance()
 
     # ------------------------------------------------------------------ admission into a running batch (fused chain)
-    def _override_buffers(self) -> None:
-        if getattr(self, "_ovr_x", None) is None:
-            d = self.model.backbone.args.hidden_size
-            self._ovr_x = torch.zeros((self.batch, d), device=self.device, dtype=torch.float32)
-            self._ovr_flag = torch.zeros((self.batch,), device=self.device, dtype=torch.uint8)
-
     def prefill_rows(self, slots: Sequence[int], tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
         """Backbone over the given rows of the given sequence slots only (KV append at their current positions); the other
         sequences are untouched.  generation.py:34-42 restricted to some sequences."""
@@ -274,7 +300,8 @@ class LMState:
         """Prepare the next fused-chain step so that the sequences in ``slots`` start from their prompts ((T, 33) rows
         each) while every other slot decodes normally: rows 0..T-2 are prefilled now, the embedded last row becomes the
         slot's backbone input of the step (csmb_decode_frame_fast_admit) and its position is set to T-1."""
-        self._override_buffers()
+        if self._fast_ws is None:
+            raise _lib.CsmbError("arm_admission needs the fused chain (unsupported model shape, or disabled)")
         ncb = self.model.n_audio_codebooks
         for s in slots:
             self.pos_host[s] = 0
@@ -295,18 +322,20 @@ class LMState:
         self._ovr_armed = True
 
     def disarm_admission(self) -> None:
-        if getattr(self, "_ovr_armed", False):
+        if self._ovr_armed:
             self._ovr_flag.zero_()
             self._ovr_armed = False
 
     def decode_frame_graphed(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
         """decode_frame through a CUDA graph captured on first use (fixed buffers; positions live on the device
         and advance inside the graph).  Returns a fresh (B, n_codebooks) int32 tensor."""
-        armed = getattr(self, "_ovr_armed", False)  # admission overrides exist only on the chain
-        path = "persist" if (self.persist_supported(sampler) and not armed) else ("chain" if self.fast_supported(sampler) else "per-op")
-        key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep, sampler.seed,
-               path)
-        if getattr(self, "_graph_key", None) != key:
+        path = "chain" if self.fast_supported(sampler) else "per-op"
+        # greedy decoding draws no random numbers: the seed is not part of the key then, so that the graph of a pooled state
+        # survives from utterance to utterance
+        greedy = sampler.temperature == 0
+        key = (sampler.temperature, sampler.top_k, sampler.top_p, sampler.min_p, sampler.min_tokens_to_keep,
+               None if greedy else sampler.seed, path, self._chain_opts_now()[0] if path == "chain" else None)
+        if self._graph_key != key:
             ncb = self.model.n_audio_codebooks
             self._g_prev = torch.zeros((self.batch, ncb), device=self.device, dtype=torch.int32)
             self._g_out = torch.zeros((self.batch, ncb), device=self.device, dtype=torch.int32)
@@ -339,12 +368,13 @@ class LMState:
         return self.batch == 1 and self.slot_fused_supported(sampler)
 
     def _frame_workspace(self) -> None:
-        if getattr(self, "_fws", None) is None:
+        if self._fws is None:
             nbytes = _lib.lib().csmb_frame_workspace_bytes(C.byref(self.model.desc()), self.dev_idx)
             self._fws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)
-            self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)
-            if os.environ.get("CSMB_FRAME_CTAS"):
-                _lib.lib().csmb_set_frame_ctas(int(os.environ["CSMB_FRAME_CTAS"]))
+            self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)  # sticky: first abort code ever
+            o = _lib.FrameOpts()
+            o.ctas = int(os.environ.get("CSMB_FRAME_CTAS", "0"))
+            self._frame_opts = o
 
     def first_frame_fused(self, sampler: SamplerSpec) -> torch.Tensor:
         """The frame that follows a prefill (codebook-0 head + sampling + depth loop on ``h_last``) in one launch of
@@ -354,7 +384,8 @@ class LMState:
         s = sampler.to_c()
         _lib.check(_lib.lib().csmb_frame_b1_depth(
             C.byref(self.model.desc()), self.h_last.data_ptr(), self.pos.data_ptr(), frame.data_ptr(), C.byref(s), 0,
-            self._fws.data_ptr(), self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
+            C.byref(self._frame_opts), self._fws.data_ptr(), self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx,
+            self._stream()))
         return frame
 
     def decode_frame_fused(self, prev_frame: torch.Tensor, sampler: SamplerSpec) -> torch.Tensor:
@@ -366,8 +397,8 @@ class LMState:
         prev = prev_frame if prev_frame.dtype == torch.int32 and prev_frame.is_contiguous() else prev_frame.to(torch.int32).contiguous()
         _lib.check(_lib.lib().csmb_frame_b1(
             C.byref(self.model.desc()), self.kv_pool.data_ptr(), self.kv_pool.stride(0), self.block_table.data_ptr(),
-            prev.data_ptr(), self.pos.data_ptr(), frame.data_ptr(), C.byref(s), 0, self._fws.data_ptr(),
-            self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
+            prev.data_ptr(), self.pos.data_ptr(), frame.data_ptr(), C.byref(s), 0, C.byref(self._frame_opts),
+            self._fws.data_ptr(), self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
         self._advance()
         return frame
 
@@ -385,22 +416,35 @@ class LMState:
         _lib.check(_lib.lib().csmb_frame_b1_slot(
             C.byref(self.model.desc()), self.kv_pool.data_ptr(), self.kv_pool.stride(0),
             self.block_table.data_ptr() + slot * self.block_table.stride(0) * 4, prev.data_ptr() + slot * ncb * 4,
-            self.pos.data_ptr() + slot * 4, frame.data_ptr() + slot * ncb * 4, C.byref(s), 0, slot, self._fws.data_ptr(),
-            self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx, self._stream()))
+            self.pos.data_ptr() + slot * 4, frame.data_ptr() + slot * ncb * 4, C.byref(s), 0, slot,
+            C.byref(self._frame_opts), self._fws.data_ptr(), self._fws.numel(), self.frame_status.data_ptr(), self.dev_idx,
+            self._stream()))
         self._advance()
         return frame
 
+    def status_word(self) -> torch.Tensor:
+        """(1,) int32 DEVICE view of the sticky abort flag of whichever fused path this state runs (zero = healthy): cheap
+        enough to ride along with every frame's device-to-host copy, so a failed frame is noticed one frame late."""
+        if self.frame_status is not None:
+            return self.frame_status
+        if self._fast_ws is not None:
+            return self._fast_ws[:4].view(torch.int32)
+        if getattr(self, "_zero_status", None) is None:
+            self._zero_status = torch.zeros((1,), device=self.device, dtype=torch.int32)
+        return self._zero_status
+
     def check_status(self) -> None:
-        """Raises if the persistent kernel reported a timed-out wait (synchronises)."""
-        st = getattr(self, "frame_status", None)
+        """Raises if any frame since the state was created reported a timed-out wait (synchronises).  Both flags are sticky:
+        the kernels only ever set them, so a failure in an early frame is still seen at the end of an utterance."""
+        st = self.frame_status
         if st is not None and int(st.item()) != 0:
-            raise _lib.CsmbError(f"persistent frame kernel aborted (code {int(st.item())})")
-        fw = getattr(self, "_fast_ws", None)
+            code = int(st.item())
+            st.zero_()
+            raise _lib.CsmbError(f"persistent frame kernel aborted (code {code})")
+        fw = self._fast_ws
         if fw is not None and int(fw[:4].view(torch.int32).item()) != 0:
+            fw[:4].zero_()
             raise _lib.CsmbError("fused batched frame: a bounded wait of the tensor-core linear timed out")
-        pw = getattr(self, "_persist_ws", None)
-        if pw is not None and int(pw[256:260].view(torch.int32).item()) != 0:
-            raise _lib.CsmbError(f"persistent batched frame kernel aborted (code {int(pw[256:260].view(torch.int32).item())})")
 
     def reset(self) -> None:
         """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply

@@ -13,6 +13,7 @@ Semantics: temp 0 -> argmax; otherwise top-k, then top-p (0<p<1
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -25,6 +26,7 @@ class DeviceSampler:
     def __init__(self, spec: SamplerSpec):
         self.spec = spec
         self._calls = 0
+        self._own_seed = spec.seed if spec.seed is not None else int.from_bytes(os.urandom(8), "little")
 
     def __call__(self, logits: torch.Tensor) -> torch.Tensor:
         """(B,V) or (V,) device logits -> (B,) / () int32 ids."""
@@ -32,7 +34,7 @@ class DeviceSampler:
         lg = logits.reshape(-1, logits.shape[-1]).to(torch.float32).contiguous()
         dev = _lib.require_device(lg.device)
         out = torch.empty((lg.shape[0],), device=lg.device, dtype=torch.int32)
-        s = self.spec.to_c()
+        s = SamplerSpec(**{**self.spec.__dict__, "seed": self._own_seed}).to_c()
         _lib.check(_lib.lib().csmb_sample(lg.data_ptr(), lg.shape[1], out.data_ptr(), 1, lg.shape[0], lg.shape[1],
                                           C.byref(s), self._calls, None, 0, dev, _lib.stream_ptr(lg.device)))
         self._calls += 1
@@ -40,10 +42,13 @@ class DeviceSampler:
 
 
 def make_sampler(temp: float = 0.0, top_p: float = 0.0, min_p: float = 0.0, min_tokens_to_keep: int = 1,
-                 top_k: int = -1, seed: int = 0) -> DeviceSampler:
+                 top_k: int = -1, seed: Optional[int] = None) -> DeviceSampler:
+    """``seed=None`` (default): a fresh Philox key is drawn from the OS for every ``generate`` call that uses the sampler,
+    like ``mx.random.categorical`` without an explicit key; pass a seed for reproducible utterances."""
     return DeviceSampler(SamplerSpec(temperature=float(temp), top_k=int(top_k) if top_k and top_k > 0 else 0,
                                      top_p=float(top_p), min_p=float(min_p),
-                                     min_tokens_to_keep=int(min_tokens_to_keep), seed=int(seed)))
+                                     min_tokens_to_keep=int(min_tokens_to_keep),
+                                     seed=None if seed is None else int(seed)))
 
 
 def make_logits_processors(logit_bias: Optional[Dict[int, float]] = None, repetition_penalty: Optional[float] = None,

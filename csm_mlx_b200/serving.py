@@ -12,15 +12,21 @@ fused kernel chain replayed as a CUDA graph) and ``mimi.Mimi``.
   requests into free slots — on the fused chain all but the last prompt row of a new request are prefilled on the side
   and that last row is the slot's input of the very step in which the running sequences decode
   (``csmb_decode_frame_fast_admit``), so admission never stalls the batch; with samplers the chain does not fuse, the
-  prompts are prefilled in one mixed per-op backbone pass together with the running sequences' rows —; while exactly one
-  slot is busy and nothing waits, its frames go through the batch-1 persistent kernel (``csmb_frame_b1_slot``: 3.2 ms
-  instead of a 6.7 ms chain step over all slots, same random draws); ``run()`` drains everything.  EOS (an all-zero frame, generation.py:151-152) and the
+  prompts are prefilled in one mixed per-op backbone pass together with the running sequences' rows —; ``run()`` drains
+  everything.  EOS (an all-zero frame, generation.py:151-152) and the
   frame budget are checked on pinned host copies one step late, so the GPU never waits for Python; a finished
   sequence frees its slot, whose KV pages are simply overwritten by the next occupant.
 * ``ContextCache``: Mimi codes of context audio keyed by content, so a conversation's segments are encoded once
   (tokenizers.py:61-85 is re-run per turn by the reference).
 
-Greedy results are identical to ``generate`` / ``generate_tokens`` of each request alone (tests/test_gpu_api.py).
+**Batch invariance.**  A request's greedy tokens do not depend on ``max_batch``, on which other requests share its steps,
+on when it is admitted or on how a job is sharded over GPUs: the engine's ``LMState`` is ``row_invariant`` (every Linear of
+the prompt prefill on the tensor-core path with a split-K factor that is a function of the Linear's shape only, the fused
+chain from one sequence up), so one numeric path serves every batch size — the property of the reference's batch-1 loop
+(generation.py:139-161).  ``tests/test_gpu_api.py::test_engine_tokens_invariant_to_batch_size`` and the token checksum of
+``bench.py`` gate it.  The batch-1 frame kernel (``generate`` / ``stream_generate``'s latency path, CUDA-core fp32 sums) is a
+different summation order: against it, argmax near-ties of a random-init model can break differently; ``solo_kernel=True``
+opts a lone busy slot into that kernel (3.2 instead of 6.7 ms per frame) at the price of that invariance.
 With temperature sampling the random draws are indexed by (seed, position, slot), so they depend on the slot a
 request lands in — like any batched sampler.
 """
@@ -97,10 +103,11 @@ class Engine:
     """Fixed ``max_batch`` sequence slots over one ``LMState``; see the module docstring."""
 
     def __init__(self, model: CSM, max_batch: int = 64, max_len: int = MAX_SEQ_LEN, sampler: Optional[SamplerSpec] = None,
-                 context_cache: Optional[ContextCache] = None):
+                 context_cache: Optional[ContextCache] = None, solo_kernel: bool = False):
         self.model, self.B = model, int(max_batch)
         self.spec = sampler if sampler is not None else SamplerSpec(temperature=0.0)
-        self.state = LMState(model, self.B, max_len=max_len)
+        self.solo_kernel = bool(solo_kernel)
+        self.state = LMState(model, self.B, max_len=max_len, row_invariant=True)
         self.ncb = model.n_audio_codebooks
         self.cache = context_cache if context_cache is not None else ContextCache(n_audio_codebooks=self.ncb)
         self.queue: Deque[Request] = deque()
@@ -156,10 +163,11 @@ class Engine:
             newly_done += self._drain()
             return newly_done
         busy = [b for b, r in enumerate(self.slots) if r is not None]
-        if (len(busy) == 1 and not admit and self._prev is not None and self.B > 1 and st.slot_fused_supported(self.spec)
-                and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"):
-            # one running sequence and nothing to admit: its frame through the batch-1 persistent kernel (3.2 ms) instead of
-            # a chain step over all slots (6.7 ms); same Philox draws as the chain would use for this slot
+        if (self.solo_kernel and len(busy) == 1 and not admit and self._prev is not None and self.B > 1
+                and st.slot_fused_supported(self.spec) and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"):
+            # opt-in: one running sequence and nothing to admit: its frame through the batch-1 persistent kernel (3.2 ms)
+            # instead of a chain step over all slots (6.7 ms); same Philox draws as the chain would use for this slot, but
+            # CUDA-core summation order (see "Batch invariance" in the module docstring)
             self._park_idle_slots()
             frame = st.decode_frame_slot(busy[0], self._prev, self.spec)
             self.solo_steps += 1

@@ -20,7 +20,7 @@ from .config import TOKENIZERS
 from .segment import Segment
 
 _text_tokenizer = None
-_audio_tokenizer = None
+_audio_tokenizers: dict = {}   # n_audio_codebooks -> Mimi (the reference caches per argument with functools.cache)
 
 
 class SyntheticTextTokenizer:
@@ -49,8 +49,11 @@ def set_text_tokenizer(tok) -> None:
 
 
 def set_audio_tokenizer(mimi) -> None:
-    global _audio_tokenizer
-    _audio_tokenizer = mimi
+    """Install (or, with None, drop) the codec served by ``get_audio_tokenizer(mimi.n_q)``."""
+    if mimi is None:
+        _audio_tokenizers.clear()
+    else:
+        _audio_tokenizers[int(getattr(mimi, "n_q", 32))] = mimi
 
 
 def get_text_tokenizer():
@@ -77,21 +80,24 @@ def get_text_tokenizer():
 
 
 def get_audio_tokenizer(n_audio_codebooks: int = 32):
-    """tokenizers.py:14-21: the process-wide Mimi holding the codec weights."""
-    global _audio_tokenizer
-    if _audio_tokenizer is None:
+    """tokenizers.py:14-21: the process-wide Mimi holding the codec weights, one per codebook count like the reference's
+    ``@cache`` (a model with another ``n_audio_codebooks`` never gets a codec of the wrong depth)."""
+    n_audio_codebooks = int(n_audio_codebooks)
+    if n_audio_codebooks not in _audio_tokenizers:
         try:
             from huggingface_hub import hf_hub_download
 
             from .mimi import Mimi
 
             weight = hf_hub_download(**TOKENIZERS["audio"])
-            _audio_tokenizer = Mimi(n_audio_codebooks).load_pytorch_weights(weight)
+            _audio_tokenizers[n_audio_codebooks] = Mimi(n_audio_codebooks).load_pytorch_weights(weight)
         except Exception as e:
+            have = sorted(_audio_tokenizers)
             raise RuntimeError(
-                f"Mimi weights {TOKENIZERS['audio']['repo_id']} are not available offline ({type(e).__name__}); "
-                "install a codec with csm_mlx.tokenizers.set_audio_tokenizer(...)") from e
-    return _audio_tokenizer
+                f"no Mimi codec with {n_audio_codebooks} codebooks: the weights {TOKENIZERS['audio']['repo_id']} are not "
+                f"available offline ({type(e).__name__}) and the installed codecs have {have} codebooks; "
+                "install one with csm_mlx.tokenizers.set_audio_tokenizer(...)") from e
+    return _audio_tokenizers[n_audio_codebooks]
 
 
 def tokenize_text_segment(text: Union[str, Sequence[int]], speaker: int, *, n_audio_codebooks: int = 32

@@ -8,9 +8,14 @@
  *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name says host.
  *  - activations fp32, Linear/embedding weights bf16 (uint16_t bit patterns), norm weights fp32.
  *  - every function takes the CUDA device ordinal and a cudaStream_t (as void*), is asynchronous on
- *    that stream, allocates nothing, keeps no thread-local or global mutable state and may be called
- *    from any host thread (the reference's demo hops threads between frames,
- *    run_streaming_csm_mlx.py:984-1000).
+ *    that stream, allocates nothing and may be called from any host thread (the reference's demo
+ *    hops threads between frames, run_streaming_csm_mlx.py:984-1000).  The library keeps NO mutable
+ *    state that changes what a later call computes: tuning and debug switches travel per call in
+ *    caller-owned structs (csmb_chain_opts, csmb_frame_opts, NULL = defaults).  The only process-wide
+ *    data are diagnostics (the launch counter and the text of the last CUDA error).
+ *  - batch invariance: what a call computes for one row / one sequence never depends on how many other
+ *    rows or sequences share the call (split-K factors and tilings are functions of the Linear's shape
+ *    only), matching the reference's batch-1 loop (generation.py:139-161).
  *  - return value: 0 = ok, negative = csmb_status; csmb_strerror() gives text.
  *  - "rows": all LM ops work on R flattened token rows; row r belongs to sequence row_seq[r] at
  *    position row_pos[r] (prefill: many rows per sequence; decode: one row per sequence).
@@ -27,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CSMB_ABI_VERSION 1
+#define CSMB_ABI_VERSION 2
 #define CSMB_PAGE 16          /* tokens per KV page */
 #define CSMB_MAX_LAYERS 16
 #define CSMB_MAX_CODEBOOKS 32
@@ -74,7 +79,7 @@ int csmb_linear(const float* x, int ldx, const uint16_t* W, float* y, int ldy, i
  * accumulators) fed by TMA; the weight tile is the UMMA A operand (M = 128 rows), the token rows are N (<= 256 per
  * tile); X is split into bf16 hi + lo on the fly and both halves are accumulated, so results match fp32 math on the
  * bf16 weights to ~1e-5.  Small-N shapes are split along K over up to 16 CTAs per tile (fp32 partials, fixed-order
- * reduction).  Requires K % 64 == 0; workspace = csmb_linear_tc_workspace_bytes(R, N, K) bytes, 256-byte aligned, zeroed
+ * reduction; the split factor depends on (N, K) only, never on R).  Requires K % 64 == 0; workspace = csmb_linear_tc_workspace_bytes(R, N, K) bytes, 256-byte aligned, zeroed
  * once by its owner (first int = sticky error flag set if an internal bounded wait timed out). */
 size_t csmb_linear_tc_workspace_bytes(int R, int N, int K);
 int csmb_linear_tc(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K, int accumulate,
@@ -156,7 +161,13 @@ typedef struct {
   size_t dec_kv_layer_stride;
   void* workspace;              /* csmb_lm_workspace_bytes() bytes */
   size_t workspace_bytes;
+  int flags;                    /* CSMB_BATCH_* */
 } csmb_batch;
+
+/* csmb_batch.flags bit: the row-based entry points (csmb_backbone_forward, csmb_depth_decode, csmb_decode_frame) run every
+ * Linear on the tensor-core path whatever the row count (instead of GEMV kernels up to 8 rows), so that a row's result
+ * is independent of the rows it is batched with.  A serving loop that admits prompts into a running batch sets it. */
+#define CSMB_BATCH_ROW_INVARIANT 1
 
 /* bytes of scratch for up to max_rows rows (prefill) / batch sequences (decode). */
 size_t csmb_lm_workspace_bytes(const csmb_model* m /*host*/, int max_rows);
@@ -187,6 +198,17 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
                       const int32_t* pos, int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base,
                       int device, void* stream);
 
+/* Per-call switches of the fused chain; caller-owned, read during the call only; NULL = all defaults. */
+typedef struct {
+  int no_pdl;               /* 1 = plain stream order instead of programmatic dependent launch (A/B timing) */
+  int flags;                /* debug: bit 0 = Linears skip their partial stores, bit 1 = and their TMEM loads (timing
+                               experiments, results are wrong); bit 2 = SwiGLU as a separate launch (A/B: same tokens) */
+  int smem_kb;              /* shared-memory budget of a Linear CTA in KiB (48..200, 0 = 200): <= 100 lets two Linear CTAs
+                               (of this or of another stream's chain) share an SM */
+  const float* proj_table;  /* optional DEVICE table of csmb_build_proj_table: depth steps >= 2 read projection(embedding)
+                               rows from it instead of running the projection Linear (same fp32 values, 60 launches less) */
+} csmb_chain_opts;
+
 /* Throughput path: the same frame as csmb_decode_frame for `batch` sequences in lock-step, as a fused kernel chain
  * (csrc/batch_frame.cu): every nn.Linear of the frame (attention.py:216-218,253; mlx_lm MLP; generation.py:42,75,79)
  * is one tcgen05/TMEM/TMA launch that reads bf16 hi+lo activation planes written by its producer kernel and leaves
@@ -206,36 +228,22 @@ int csmb_decode_frame_fast(const csmb_model* m, const csmb_batch* b, const int32
  * row is x_override[b] (DEVICE fp32 [batch][d_backbone]) — the already embedded LAST row of a prompt whose earlier rows
  * were run through csmb_backbone_forward — instead of the embedding of prev_frame[b].  This is how a serving loop admits a
  * new request into a free slot in the same step in which the running sequences decode (generation.py:34-42 for T > 1 is
- * split into rows 0..T-2 and the causal last row).  Both pointers null = csmb_decode_frame_fast. */
+ * split into rows 0..T-2 and the causal last row).  x_override / use_override both null and opts null =
+ * csmb_decode_frame_fast. */
 int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
                                  int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, const float* x_override,
-                                 const uint8_t* use_override, void* workspace, size_t workspace_bytes, int device,
-                                 void* stream);
-/* tuning: minimum 64-wide K blocks per split-K CTA (>= 1), programmatic dependent launch on/off (-1 = keep),
-   CTA budget per Linear (0 = keep) of later csmb_decode_frame_fast calls */
-void csmb_debug_set_fast_frame(int min_kblocks, int pdl, int max_ctas);
-/* debug: bit 0 = the chain's Linears skip their partial stores, bit 1 = and their TMEM loads (timing experiments, results
-   are wrong); bit 2 = SwiGLU as a separate launch after the gate|up Linear instead of in its epilogue (A/B: same tokens) */
-void csmb_debug_set_fast_frame_flags(int flags);
+                                 const uint8_t* use_override, const csmb_chain_opts* opts /*host*/, void* workspace,
+                                 size_t workspace_bytes, int device, void* stream);
 
-/* Throughput path, persistent form (csrc/batch_persist.cu): the frame of csmb_decode_frame for `batch` sequences in ONE
- * cooperative launch (one CTA per SM): the dataflow of csmb_decode_frame_fast with grid barriers instead of kernel
- * boundaries, a persistent TMA ring whose producer streams the next Linear's weight tiles through the element-wise
- * phases and barriers, one TMEM accumulator reused by every Linear, and all tensor maps in the kernel's parameter block.
- * Replaces per frame: generation.py:21-92 (T = 1) + :156-161.  Same arguments and sampler restrictions as
- * csmb_decode_frame_fast; batch <= 256.  workspace = csmb_frame_batch_workspace_bytes bytes, 256-byte aligned, zeroed
- * once by its owner and then owned by this sequence group (it carries the barrier counters between launches; the int
- * at byte offset 256 is the sticky error flag of the bounded waits). */
-size_t csmb_frame_batch_workspace_bytes(const csmb_model* m /*host*/, int batch, int device);
-int csmb_frame_batch_supported(const csmb_model* m /*host*/, const csmb_sampler* sampler /*host*/, int batch);
-int csmb_frame_batch(const csmb_model* m, const csmb_batch* b, const int32_t* prev_frame, const int32_t* pos,
-                     int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, void* workspace,
-                     size_t workspace_bytes, int device, void* stream);
-/* tuning: minimum 64-wide K blocks per split-K work item of later csmb_frame_batch launches */
-void csmb_debug_set_frame_batch(int min_kblocks);
-/* debug: device buffer [n_sms][2][12] u64 receiving the phase timers (SM cycles; threads 0 and 128 of every CTA; categories
-   gemm, prefetch, barrier, attention, norm, swiglu, sample, embed, accumulator wait, epilogue) of later csmb_frame_batch launches; null = off */
-void csmb_debug_set_frame_batch_prof(unsigned long long* device_buf);
+/* Projected-embedding table for csmb_chain_opts.proj_table: table[cb][token][:] = projection . embed_audio(cb, token)
+ * (generation.py:75 applied to models.py:79-80 rows) for every codebook and token, [n_codebooks][audio_vocab][d_decoder]
+ * fp32, computed with the chain's own projection Linear (same tcgen05 tiles, same split-K, same summation order), so
+ * reading a row is bit-identical to running that Linear.  csmb_proj_table_bytes = size of the table;
+ * workspace = csmb_proj_table_workspace_bytes bytes, 256-byte aligned (scratch, free afterwards). */
+size_t csmb_proj_table_bytes(const csmb_model* m /*host*/);
+size_t csmb_proj_table_workspace_bytes(const csmb_model* m /*host*/);
+int csmb_build_proj_table(const csmb_model* m, float* table, void* workspace, size_t workspace_bytes, int device,
+                          void* stream);
 
 /* Batch-1 latency path: ONE persistent cooperative kernel per frame (csrc/frame_kernel.cu) doing what
  * csmb_decode_frame does for a single sequence — generate_frame with T=1 (generation.py:21-92) plus the input
@@ -245,38 +253,41 @@ void csmb_debug_set_frame_batch_prof(unsigned long long* device_buf);
  * copy per SM) and belongs to one sequence.
  * block_table: this sequence's row of the paged-KV table; pos: DEVICE int, position of this frame's backbone row.
  * Fused samplers: greedy, or temperature with optional top-k, top-p and / or min-p; min-p with min_keep > 1 (and model shapes
- * other than csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame.  status (optional, DEVICE int): 0, or the abort
- * code if an internal wait timed out (all waits are bounded). */
+ * other than csm_1b) returns CSMB_ERR_UNSUPPORTED — use csmb_decode_frame. */
 size_t csmb_frame_workspace_bytes(const csmb_model* m /*host*/, int device);
-/* debug: device buffer [n_sms][16] u64 that later csmb_frame_b1 launches fill with per-CTA phase timers (ns); null = off */
-void csmb_debug_set_frame_prof(unsigned long long* device_buf);
-/* debug: bit 0 = skip the GEMV arithmetic of csmb_frame_b1 (timing experiments only; results are wrong) */
-void csmb_debug_set_frame_flags(int flags);
-/* tuning: L2 prefetch distance (16 KiB stages per SM, 0 = off) and pacing (SM cycles between prefetches) of csmb_frame_b1 */
-void csmb_debug_set_frame_prefetch(int max_stages, int interval_cycles);
-/* tuning: CTAs of later csmb_frame_b1 launches; 0 = automatic: the largest count <= SMs that splits every weight matrix
-   into equal row slices (128 for csm_1b on a 148-SM B200).  The SMs left over let the codec's streaming step of the
-   previous frame run beside the frame kernel on a second stream (generation.py:251 moved off the critical path). */
-void csmb_set_frame_ctas(int n);
+/* Per-call switches of the frame kernel; caller-owned, read during the call only; NULL = all defaults. */
+typedef struct {
+  int ctas;                  /* CTAs of the launch; 0 = automatic: the largest count <= SMs that splits every weight matrix
+                                into equal row slices (128 for csm_1b on a 148-SM B200).  The SMs left over let the codec's
+                                streaming step of the previous frame run beside the frame kernel on a second stream
+                                (generation.py:251 moved off the critical path). */
+  int flags;                 /* debug: bit 0 = skip the GEMV arithmetic (timing experiments only; results are wrong) */
+  int prefetch_stages;       /* L2 prefetch distance in 16 KiB stages per SM (0 = off) */
+  int prefetch_interval;     /* SM cycles between prefetches (0 = 700) */
+  unsigned long long* prof;  /* debug: DEVICE buffer [n_sms][16] u64 filled with per-CTA phase timers; null = off */
+} csmb_frame_opts;
+/* status (optional, DEVICE int, zeroed once by its owner): receives the abort code of the FIRST internal wait that ever timed
+ * out on this state (all waits are bounded) and is never cleared by the library, so the owner may look at it at any later
+ * point — e.g. once per utterance — without losing an earlier frame's failure. */
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
-                  uint64_t draw_base, void* workspace, size_t workspace_bytes, int32_t* status, int device,
-                  void* stream);
+                  uint64_t draw_base, const csmb_frame_opts* opts /*host*/, void* workspace, size_t workspace_bytes,
+                  int32_t* status, int device, void* stream);
 /* csmb_frame_b1 for ONE sequence of a batched state (serving with a single active slot): the pointers are that sequence's
  * rows (block_table + slot * max_pages, prev_frame + slot * n_codebooks, pos + slot, frame + slot * n_codebooks) and
  * seq_index is its row in the batch, so that sampling draws the same Philox noise as csmb_decode_frame(_fast) would for
  * that row (csmb_sample's r).  Everything else as csmb_frame_b1 (which is seq_index 0). */
 int csmb_frame_b1_slot(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table_row,
                        const int32_t* prev_frame_row, const int32_t* pos, int32_t* frame_row, const csmb_sampler* sampler,
-                       uint64_t draw_base, int seq_index, void* workspace, size_t workspace_bytes, int32_t* status,
-                       int device, void* stream);
+                       uint64_t draw_base, int seq_index, const csmb_frame_opts* opts /*host*/, void* workspace,
+                       size_t workspace_bytes, int32_t* status, int device, void* stream);
 /* The same kernel without its backbone part, for the first frame after a prompt (generation.py:139-146 with the
  * whole prompt as `tokens`): h_last = csmb_backbone_forward's normalised last hidden row [d_backbone] of this sequence,
  * pos = DEVICE int holding the sequence length (the sampled row is pos-1, which also indexes the random draws exactly
  * like csmb_sample + csmb_depth_decode do).  Codebook-0 head, sampling and the 31 depth steps run in one launch. */
 int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t* pos, int32_t* frame,
-                        const csmb_sampler* sampler, uint64_t draw_base, void* workspace, size_t workspace_bytes,
-                        int32_t* status, int device, void* stream);
+                        const csmb_sampler* sampler, uint64_t draw_base, const csmb_frame_opts* opts /*host*/, void* workspace,
+                        size_t workspace_bytes, int32_t* status, int device, void* stream);
 
 /* ---------------------------------------------------------------- Mimi codec ------------------- */
 /* moshi_mlx Mimi.encode / decode / decode_step (csm_mlx/tokenizers.py:14-21,70,150; generation.py:224-225,

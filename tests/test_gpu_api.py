@@ -182,3 +182,38 @@ def test_zero_length_request_returns_empty_audio(model_1b, mimi_gpu, capsys):
     assert out.shape == (0,) and out.dtype == torch.float32
     assert "No samples generated" in capsys.readouterr().out
     assert list(stream_generate(model_1b, cfg1_prompt_ids(), 0, [], max_audio_length_ms=79, temperature=0.0)) == []
+
+
+def test_engine_tokens_invariant_to_batch_size(model_1b, mimi_gpu):
+    """The reference generates one utterance at a time (generation.py:139-161), so an utterance's tokens cannot depend on
+    its neighbours.  Same property here: the same 16 utterances x 125 frames (BASELINE.json configs[3] prompts) through
+    engines of 4, 8, 16 and 64 slots — different waves, admissions and row counts in every Linear — and through the
+    request sharding of a 2-GPU job (requests i mod 2 on engines of 8 slots) give identical tokens, bit for bit; the first
+    three also equal the utterance served alone by a 1-slot engine."""
+    from csm_mlx_b200 import serving
+    from csm_mlx_b200.sharding import shard_indices
+    from tests.workloads import prompt_ids
+
+    frames = 125
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(16)]
+
+    def through(max_batch, idx):
+        eng = serving.Engine(model_1b, max_batch=max_batch, max_len=32 + frames + 2)
+        rids = [eng.submit_prompt(prompts[i][0], prompts[i][1], frames) for i in idx]
+        eng.run()
+        return {i: eng.tokens(r) for i, r in zip(idx, rids)}
+
+    ref = through(16, list(range(16)))
+    assert all(t.shape == (frames, 32) for t in ref.values())
+    for B in (4, 8, 64):
+        got = through(B, list(range(16)))
+        for i in range(16):
+            assert torch.equal(ref[i], got[i]), (B, i, int((ref[i] != got[i]).nonzero()[0][0]))
+    for rank in range(2):
+        mine = shard_indices(16, rank, 2)
+        got = through(len(mine), mine)
+        for i in mine:
+            assert torch.equal(ref[i], got[i]), ("shard", rank, i)
+    for i in range(3):
+        alone = through(1, [i])
+        assert torch.equal(ref[i], alone[i]), ("alone", i)

@@ -241,7 +241,7 @@ def test_fused_chain_filtered_sampler_falls_back(model_1b):
 
 
 @pytest.mark.parametrize("B", [5, 130])
-def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, B):
+def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, monkeypatch, B):
     """The gate|up Linear with SwiGLU in its epilogue (k_gemm_part_t<true>: 64 gate rows + the 64 matching up rows per
     UMMA tile, planes written from the drained pipeline stages) against the separate k_swiglu_split launch (debug flag
     4): identical tokens for a ragged row count (5 rows in a 16-row token tile) and for 130 sequences (first depth
@@ -253,7 +253,7 @@ def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, B):
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
 
     def run(flags):
-        _lib.lib().csmb_debug_set_fast_frame_flags(flags)
+        monkeypatch.setenv("CSMB_CHAIN_FLAGS", str(flags))   # csmb_chain_opts.flags of the states created from here on
         st = LMState(model_1b, B, max_len=48)
         assert st.fast_supported(spec)
         st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
@@ -270,28 +270,24 @@ def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, B):
         st.check_status()
         return torch.stack(out).cpu()
 
-    try:
-        separate, fused = run(4), run(0)
-    finally:
-        _lib.lib().csmb_debug_set_fast_frame_flags(0)
+    separate, fused = run(4), run(0)
     assert torch.equal(separate, fused)
     assert int((fused[1:] != fused[:-1]).sum()) > 0  # frames differ from step to step: the loop really decoded
 
 
-def test_persistent_batched_kernel_equals_chain(model_1b, monkeypatch):
-    """csmb_frame_batch (one cooperative launch per frame-step: tcgen05 Linear phases with a persistent TMA ring,
-    grid barriers, in-kernel sampling; opt-in with CSMB_ENABLE_PERSIST=1) produces the tokens of the kernel chain."""
+def test_chain_projected_embedding_table_is_bit_exact(model_1b, monkeypatch):
+    """csmb_build_proj_table: depth steps >= 2 read projection(embed_audio(cb, token)) rows from a table built with the
+    chain's own projection Linear instead of running that Linear (60 launches less per frame-step): identical tokens,
+    greedy and sampled, ragged batch of 20."""
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(80 + i, 7 + i % 6), i % 3) for i in range(20)]
-    chain = generation.generate_tokens(model_1b, prompts, 4, temperature=0.0)
-    monkeypatch.setenv("CSMB_ENABLE_PERSIST", "1")
-    persist = generation.generate_tokens(model_1b, prompts, 4, temperature=0.0)
-    for a, b in zip(chain, persist):
-        assert torch.equal(a, b)
-    spec = SamplerSpec(temperature=0.9, seed=11)
-    sampled_p = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
-    monkeypatch.setenv("CSMB_ENABLE_PERSIST", "0")
-    sampled_c = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
-    for a, b in zip(sampled_c, sampled_p):
+    spec = SamplerSpec(temperature=0.9, top_k=50, seed=11)
+    with_table = generation.generate_tokens(model_1b, prompts, 6, temperature=0.0)
+    sampled_t = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
+    assert model_1b._proj_table is not None and tuple(model_1b._proj_table.shape) == (32, 2051, 1024)
+    monkeypatch.setenv("CSMB_NO_PROJ_TABLE", "1")
+    without = generation.generate_tokens(model_1b, prompts, 6, temperature=0.0)
+    sampled_w = generation.generate_tokens(model_1b, prompts[:5], 3, sampler=spec)
+    for a, b in zip(with_table + sampled_t, without + sampled_w):
         assert torch.equal(a, b)
 
 

@@ -46,8 +46,33 @@ def test_context_cache_encodes_each_audio_once(monkeypatch):
     assert calls == [100, 200, 100, 100]       # c was still cached (b was the least recently used)
 
 
+def _alone(model, prompt, frames, max_len=128):
+    """The request served by itself: an engine with ONE slot (same numeric path as any other engine batch)."""
+    eng = serving.Engine(model, max_batch=1, max_len=max_len)
+    rid = eng.submit_prompt(prompt[0], prompt[1], frames)
+    eng.run()
+    return eng.tokens(rid)
+
+
+def _same_or_near_tie(model, prompt, a, b, device, tol=2e-4):
+    """Two implementations that sum in different orders (tensor-core chain vs CUDA-core frame kernel) may break an argmax
+    near-tie of the random-init model differently; from there on the utterance legitimately differs.  Requires identity
+    up to the first difference and, there, a logit margin below `tol` on a third implementation (per-op kernels)."""
+    assert a.shape == b.shape
+    diff = (a != b).nonzero()
+    if len(diff) == 0:
+        return True
+    f, c = int(diff[0][0]), int(diff[0][1])
+    margin, below_max = _margin_at(model, prompt, a, f, c, int(a[f, c]), int(b[f, c]), device)
+    assert margin < tol and below_max < tol, (f, c, margin, below_max)
+    return False
+
+
 @pytest.mark.gpu
-def test_engine_continuous_batching_matches_single(model_1b, mimi_gpu):
+def test_engine_continuous_batching_matches_single(model_1b, mimi_gpu, device):
+    """Ragged prompts and budgets through 4 slots with arrivals mid-flight: every request's tokens equal, bit for bit, what
+    the request produces when served alone (batch invariance), and agree with the batch-1 latency path of
+    generate_tokens (a different summation order) up to argmax near-ties."""
     from csm_mlx_b200 import generation
 
     eng = serving.Engine(model_1b, max_batch=4, max_len=128)
@@ -60,8 +85,10 @@ def test_engine_continuous_batching_matches_single(model_1b, mimi_gpu):
     assert eng.active == 0 and not eng.queue
     assert eng.mixed_steps == 0 and eng.admissions == 9 and eng.steps >= 10   # admissions ride on the graphed chain
     for rid, (ids, spk, f) in zip(rids, reqs):
-        (single,) = generation.generate_tokens(model_1b, [tokenizers.tokenize_text_segment(ids, spk)], f, temperature=0.0)
-        assert torch.equal(single, eng.tokens(rid)), rid
+        prompt = tokenizers.tokenize_text_segment(ids, spk)
+        assert torch.equal(_alone(model_1b, prompt, f), eng.tokens(rid)), rid
+        (single,) = generation.generate_tokens(model_1b, [prompt], f, temperature=0.0)
+        _same_or_near_tie(model_1b, prompt, single, eng.tokens(rid), device)
     audio = eng.audio(rids[:2])
     assert [a.shape for a in audio] == [(1920 * reqs[0][2],), (1920 * reqs[1][2],)]
 
@@ -79,8 +106,7 @@ def test_engine_context_segments_use_the_cache(model_1b, mimi_gpu):
         eng.run()
         assert (eng.cache.hits, eng.cache.misses) == (1, 1)
         prompt = generation._build_prompt(model_1b, "second answer", 1, [seg])
-        (single,) = generation.generate_tokens(model_1b, [prompt], 3, temperature=0.0)
-        assert torch.equal(single, eng.tokens(r1)) and eng.tokens(r0).shape == (3, 32)
+        assert torch.equal(_alone(model_1b, prompt, 3), eng.tokens(r1)) and eng.tokens(r0).shape == (3, 32)
     finally:
         tokenizers.set_text_tokenizer(None)
 
@@ -127,19 +153,12 @@ def test_cfg4_full_size_engine_vs_single(model_1b, mimi_gpu, device):
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(64)]
     rids = [eng.submit_prompt(t, m, 125) for t, m in prompts]
     eng.run()
-    identical, worst = 0, 0.0
+    identical = 0
     for i in range(64):
         (single,) = generation.generate_tokens(model_1b, [prompts[i]], 125, temperature=0.0)
         got = eng.tokens(rids[i])
         assert got.shape == (125, 32)
-        diff = (single != got).nonzero()
-        if len(diff) == 0:
-            identical += 1
-            continue
-        f, c = int(diff[0][0]), int(diff[0][1])
-        margin, below_max = _margin_at(model_1b, prompts[i], single, f, c, int(single[f, c]), int(got[f, c]), device)
-        worst = max(worst, margin)
-        assert margin < 2e-4 and below_max < 2e-4, (i, f, c, margin, below_max)
+        identical += bool(_same_or_near_tie(model_1b, prompts[i], single, got, device))
     assert identical >= 36, identical
 
 
@@ -157,25 +176,22 @@ def test_engine_falls_back_to_mixed_steps_for_unfused_samplers(model_1b, mimi_gp
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("spec_kw", [dict(temperature=0.0), dict(temperature=0.8, top_k=50, seed=6)])
-def test_engine_single_busy_slot_uses_the_batch1_kernel(model_1b, mimi_gpu, monkeypatch, spec_kw):
-    """While exactly one slot is busy and nothing waits, the engine runs that sequence's frames through the persistent
-    batch-1 kernel on the slot's own rows (csmb_frame_b1_slot, Philox sequence word = slot) instead of a chain step over
-    all slots: same tokens as the chain-only engine (CSMB_DISABLE_FUSED=1), greedy and sampled, also for the request
-    that keeps running alone after its neighbour finished."""
-    from csm_mlx_b200.runtime import SamplerSpec
+def test_engine_solo_kernel_is_opt_in(model_1b, mimi_gpu, device):
+    """By default a lone busy slot keeps stepping through the chain (one numeric path for every batch size).  With
+    solo_kernel=True its frames go through the batch-1 persistent kernel on the slot's own rows (csmb_frame_b1_slot): the
+    same tokens up to argmax near-ties between the two summation orders, also for the request that keeps running alone
+    after its neighbour finished."""
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(300, 7), 0), tokenizers.tokenize_text_segment(prompt_ids(301, 9), 0)]
 
-    def run():
-        eng = serving.Engine(model_1b, max_batch=4, max_len=96, sampler=SamplerSpec(**spec_kw))
-        rids = [eng.submit(prompt_ids(300, 7), 0, [], max_audio_length_ms=80 * 3),
-                eng.submit(prompt_ids(301, 9), 0, [], max_audio_length_ms=80 * 9)]
+    def run(solo):
+        eng = serving.Engine(model_1b, max_batch=4, max_len=96, solo_kernel=solo)
+        rids = [eng.submit_prompt(prompts[0][0], prompts[0][1], 3), eng.submit_prompt(prompts[1][0], prompts[1][1], 9)]
         eng.run()
         return eng, [eng.tokens(r) for r in rids]
 
-    eng, toks = run()
-    assert eng.solo_steps >= 3 and [tuple(t.shape) for t in toks] == [(3, 32), (9, 32)]
-    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
-    eng2, toks2 = run()
-    assert eng2.solo_steps == 0
-    for a, b in zip(toks, toks2):
-        assert torch.equal(a, b)
+    eng, toks = run(False)
+    assert eng.solo_steps == 0 and [tuple(t.shape) for t in toks] == [(3, 32), (9, 32)]
+    eng2, toks2 = run(True)
+    assert eng2.solo_steps >= 3
+    for p, a, b in zip(prompts, toks, toks2):
+        _same_or_near_tie(model_1b, p, a, b, device)
