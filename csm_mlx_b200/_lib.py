@@ -67,6 +67,17 @@ class FrameOpts(C.Structure):
                 ("prof", C.c_void_p)]
 
 
+class Tc3(C.Structure):
+    """csmb_tc3: one tensor-core strided-row GEMM of the codec (see include/csm_b200.h)."""
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_rows", C.c_longlong), ("lda", C.c_int), ("rpb", C.c_int),
+                ("C", C.c_int), ("taps", C.c_int), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_rows", C.c_int),
+                ("ldw", C.c_int), ("y32", C.c_void_p), ("y_batch", C.c_longlong), ("ldy", C.c_int), ("y_hi", C.c_void_p),
+                ("y_lo", C.c_void_p), ("p_batch", C.c_longlong), ("ldp", C.c_int), ("plane_act", C.c_int),
+                ("bias", C.c_void_p), ("scale", C.c_void_p), ("residual", C.c_void_p), ("r_batch", C.c_longlong),
+                ("ldr", C.c_int), ("B", C.c_int), ("T", C.c_int), ("N", C.c_int), ("act_out", C.c_int),
+                ("err_flag", C.c_void_p)]
+
+
 _lib: Optional[C.CDLL] = None
 
 _P = C.c_void_p
@@ -112,6 +123,11 @@ _SIGS = {
     "csmb_frame_b1_depth": (C.c_int, [C.POINTER(Model), _P, _P, _P, C.POINTER(Sampler), C.c_uint64, C.POINTER(FrameOpts), _P,
                                       C.c_size_t, _P, _I, _P]),
     "csmb_gemm_f32": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "csmb_gemm_tc3": (C.c_int, [C.POINTER(Tc3), _I, _P]),
+    "csmb_split_planes": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _P]),
+    "csmb_layernorm_planes": (C.c_int, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
+    "csmb_conv_in_planes": (C.c_int, [_P, _LL, _P, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _P]),
+    "csmb_rvq_argmin_update_planes": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_layernorm": (C.c_int, [_P, _LL, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
     "csmb_mimi_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_rvq_gather": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -202,10 +202,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 // bf16 [rows][K] row-major, box = box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
 bool tc_make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+  return tc_make_map_ld(m, base, rows, K, K, box_rows);
+}
+// the same with a leading dimension: row r starts at element r * ld (ld >= K, ld % 8 == 0)
+bool tc_make_map_ld(CUtensorMap* m, const void* base, long long rows, int K, int ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,

@@ -14,6 +14,8 @@ constexpr unsigned TC_SPIN = 1u << 24;
 
 // bf16 [rows][K] row-major tensor map, box = box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
 bool tc_make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows);
+// the same with a leading dimension: row r starts at element r * ld (ld >= K, ld % 8 == 0)
+bool tc_make_map_ld(CUtensorMap* m, const void* base, long long rows, int K, int ld, int box_rows);
 
 #ifdef __CUDACC__
 
@@ -123,6 +125,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns of the accumulator -> registers (waits for the load)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two fp32 -> packed bf16 pair (element 0 in the low half), round to nearest even: one cvt instead of ~10 integer ops
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+// four values -> 4 hi + 4 lo (x = hi + lo up to 2^-17), 8-byte stores; the cvt form of store_split4
+__device__ __forceinline__ void store_split4_cvt(uint16_t* hi, uint16_t* lo, float a, float b, float c, float d) {
+  const uint32_t h01 = pack_bf16x2_rn(a, b), h23 = pack_bf16x2_rn(c, d);
+  const uint32_t l01 = pack_bf16x2_rn(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
+  const uint32_t l23 = pack_bf16x2_rn(c - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
+  *reinterpret_cast<uint2*>(hi) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(lo) = make_uint2(l01, l23);
 }
 
 #endif  // __CUDACC__

@@ -204,9 +204,28 @@ class Mimi:
             raise RuntimeError("Mimi weights are not loaded: call load_pytorch_weights(...) first")
 
     # ------------------------------------------------------------------ decode
+    def tc(self):
+        """The tensor-core (tcgen05) whole-clip path, built on first use (bf16 hi/lo weight planes; mimi_tc.MimiTC)."""
+        self._require()
+        if self.__dict__.get("_tc") is None:
+            from .mimi_tc import MimiTC
+
+            self._tc = MimiTC(self)
+        return self._tc
+
+    @staticmethod
+    def _use_tc() -> bool:
+        """Whole-clip encode / decode run on the tensor cores unless ``CSMB_MIMI_FP32=1`` (the fp32 CUDA-core kernels, kept
+        as the streaming path and as an A/B reference)."""
+        import os
+
+        return os.environ.get("CSMB_MIMI_FP32", "0") != "1"
+
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """(B,K,F) int -> (B,1,1920*F) fp32 (``Mimi.decode``; tokenizers.py:148-150)."""
         self._require()
+        if self._use_tc() and int(codes.shape[2]) > 0:
+            return self.tc().decode(codes)
         st = MimiDecodeStream(self, int(codes.shape[0]), max_frames=int(codes.shape[2]), offline=True)
         return st.step(codes)
 
@@ -244,6 +263,8 @@ class Mimi:
     def encode(self, audio: torch.Tensor) -> torch.Tensor:
         """(B,1,N) fp32 -> (B,n_q,ceil(N/1920)) int32 (``Mimi.encode``; tokenizers.py:70-72)."""
         self._require()
+        if self._use_tc() and int(audio.shape[2]) > 0:
+            return self.tc().encode(audio)
         dev = self.device
         x = audio.to(device=dev, dtype=torch.float32)
         B, _, N = x.shape

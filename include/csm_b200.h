@@ -331,6 +331,56 @@ int csmb_shift_rows(float* buf, long long batch, int B, int T, int pad, int C, i
 /* *p += v on the device (position counters of captured graphs). */
 int csmb_add_int(int* p, int v, int device, void* stream);
 
+/* ---------------------------------------------------------------- Mimi codec on the tensor cores ---------- */
+/* Batch-scale codec path (csrc/mimi_tc.cu): Mimi.encode / Mimi.decode of many clips (csm_mlx/tokenizers.py:61-85, 148-150;
+ * BASELINE.json configs[4]).  Activations and weights travel as two bf16 planes, x = hi + lo up to 2^-17, and
+ *
+ *   Y[b][t][n] = epi( sum_{j < taps} sum_{c < C} A[b][t + j][c] * W[n][j*C + c] ),   A = a_hi + a_lo, W = w_hi + w_lo
+ *
+ * runs as ONE persistent tcgen05 kernel (three MMAs per K step: Ahi.Whi + Alo.Whi + Ahi.Wlo, fp32 TMEM accumulators, TMA
+ * 128B-swizzled boxes, two accumulators so the epilogue overlaps the next tile).  Conv1d(k, stride 1): taps = k, C = Cin on
+ * the left-padded input; Conv1d(k = 2s, stride s): the input viewed as rows of s*Cin values, taps = 2; ConvTranspose1d
+ * (k = 2s, stride s): taps = 2 over rows (t-1, t), N = s*Cout phase-major = the time-major output; Linear: taps = 1.
+ * epi = (+bias[n]) -> GELU(act_out = 1) -> (*scale[n]) -> (+residual[b][t][n]); the result goes to y32 (fp32) and / or, after
+ * an optional ELU (plane_act = 1: the activation the CONSUMING conv applies), to the bf16 planes y_hi / y_lo.
+ * a_*: [a_rows][lda] bf16 (row b*rpb + t + j of the plane is A[b][t + j]); w_*: [w_rows >= N rounded up to 16][ldw], rows
+ * beyond N zero.  taps > 1 needs C % 64 == 0; lda, ldw % 8 == 0; all plane bases 16-byte aligned.
+ * err_flag: DEVICE int zeroed once by its owner; set (sticky) if a bounded wait inside the kernel timed out. */
+typedef struct {
+  const uint16_t *a_hi, *a_lo;
+  long long a_rows;
+  int lda, rpb, C, taps;
+  const uint16_t *w_hi, *w_lo;
+  int w_rows, ldw;
+  float* y32;
+  long long y_batch;
+  int ldy;
+  uint16_t *y_hi, *y_lo;
+  long long p_batch;
+  int ldp, plane_act;
+  const float *bias, *scale, *residual;
+  long long r_batch;
+  int ldr;
+  int B, T, N, act_out;
+  int* err_flag;
+} csmb_tc3;
+int csmb_gemm_tc3(const csmb_tc3* g /*host*/, int device, void* stream);
+
+/* fp32 [B][T][C] (batch stride x_batch, row stride ldx) -> bf16 hi/lo planes (p_batch, ldp); act = 1 applies ELU first. */
+int csmb_split_planes(const float* x, long long x_batch, int ldx, uint16_t* hi, uint16_t* lo, long long p_batch, int ldp,
+                      int B, int T, int C, int act, int device, void* stream);
+/* csmb_layernorm writing dense [B*T][d] bf16 hi/lo planes (the operand of the next tensor-core Linear). */
+int csmb_layernorm_planes(const float* x, long long x_batch, const float* w, const float* b, uint16_t* hi, uint16_t* lo, int B,
+                          int T, int d, float eps, int device, void* stream);
+/* First SEANet encoder layer, Conv1d(1 -> C, k) + bias: x [B][(k-1) + N] fp32 (left-padded, batch stride x_batch) ->
+ * y fp32 and ELU(y) planes, both [B][..][C] with batch stride y_batch (pointers already at the first output row). */
+int csmb_conv_in_planes(const float* x, long long x_batch, const float* w, const float* bias, float* y, uint16_t* hi,
+                        uint16_t* lo, long long y_batch, int B, int N, int C, int k, int device, void* stream);
+/* csmb_rvq_argmin_update that also writes the updated residual as planes (operand of the next codebook's search). */
+int csmb_rvq_argmin_update_planes(const float* dots, const float* c2, const float* codebook, float* r, uint16_t* r_hi,
+                                  uint16_t* r_lo, int32_t* codes, int M, int bins, int D, int K, int k, int F, int device,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,6 +189,43 @@ def encode(audio: Tensor, W: Dict[str, Tensor], n_q: int = 32) -> Tensor:
     return rvq_encode(h, W, n_q)
 
 
+def encode_latent(audio: Tensor, W: Dict[str, Tensor]) -> Tensor:
+    """(B,1,N) fp32 → (B,512,F): the 12.5 Hz latent the quantiser sees (``encode`` without ``rvq_encode``)."""
+    h = seanet_encoder(audio.to(torch.float32), W)
+    h = transformer(h.transpose(1, 2), W, "encoder_transformer").transpose(1, 2)
+    return conv1d(h, W["downsample.conv.conv.conv.weight"], None, stride=2, pad_mode="replicate")
+
+
+def rvq_disagreement_margins(latent: Tensor, W: Dict[str, Tensor], ref: Tensor, other: Tensor) -> List[tuple]:
+    """Referee for two code tensors (B,K,F) of the same latent (B,512,F).  A nearest-neighbour search is index work, but
+    its input is floating point: an implementation that sums in another order may pick the other of two (almost)
+    equidistant codewords, after which the rest of that frame's residual chain legitimately differs.  For every frame and
+    chain (semantic: codebook 0; acoustic: codebooks 1..K-1) this walks the chain in float64 along ``ref``'s codes to the
+    FIRST codebook where ``other`` differs and returns (b, f, k, |d_ref - d_other| / |r|^2) there: the relative distance gap
+    of the two candidates, which the caller bounds (a genuine near-tie) — disagreements past that point are not examined."""
+    out = []
+    B, K, F_ = ref.shape
+    lat = latent.to(torch.float64)
+    for group, k0, n in (("rvq_first", 0, 1), ("rvq_rest", 1, K - 1)):
+        if n <= 0:
+            continue
+        wp = W[f"quantizer.{group}.input_proj.weight"].to(torch.float64)[:, :, 0]         # (256,512)
+        cbs = [codebook(W, group, i).to(torch.float64) for i in range(n)]
+        for b in range(B):
+            for f in range(F_):
+                if bool((ref[b, k0:k0 + n, f] == other[b, k0:k0 + n, f]).all()):
+                    continue
+                r = wp @ lat[b, :, f]
+                for i in range(n):
+                    a_, o_ = int(ref[b, k0 + i, f]), int(other[b, k0 + i, f])
+                    if a_ != o_:
+                        da, do = (r - cbs[i][a_]).pow(2).sum(), (r - cbs[i][o_]).pow(2).sum()
+                        out.append((b, f, k0 + i, float((da - do).abs() / r.pow(2).sum().clamp_min(1e-300))))
+                        break
+                    r = r - cbs[i][a_]
+    return out
+
+
 def decode_latent(codes: Tensor, W: Dict[str, Tensor]) -> Tensor:
     """codes → (B,512,2F) transformer input (after RVQ decode and the depthwise ×2 upsample)."""
     z = rvq_decode(codes, W)
