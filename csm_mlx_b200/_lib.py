@@ -126,6 +126,7 @@ _SIGS = {
     "csmb_gemm_tc3": (C.c_int, [C.POINTER(Tc3), _I, _P]),
     "csmb_split_planes": (C.c_int, [_P, _LL, _I, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_layernorm_planes": (C.c_int, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
+    "csmb_mimi_attention_planes": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "csmb_conv_in_planes": (C.c_int, [_P, _LL, _P, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _P]),
     "csmb_rvq_argmin_update_planes": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_layernorm": (C.c_int, [_P, _LL, _P, _P, _P, _I, _I, _I, C.c_float, _I, _P]),

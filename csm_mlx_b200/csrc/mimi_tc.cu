@@ -31,13 +31,20 @@
 namespace csmb {
 
 constexpr int T3_MAX_STAGES = 6;
-constexpr size_t T3_SMEM_BUDGET = 200 * 1024;
 constexpr int T3_BM = 128;
 // Epilogue warps: T3_EPI_WARPS / 4 per TMEM lane quarter, sharing a tile's 16-column chunks.  The epilogue is a chain of
 // dependent ALU work (ELU, hi/lo split) and global loads / stores per row: one warp per scheduler cannot hide its own
 // latencies (measured: 5.4 us per 128 x 32 tile with 4 warps), several can.
-constexpr int T3_EPI_WARPS = 16;
+constexpr int T3_EPI_WARPS = 8;
 constexpr int T3_THREADS = 64 + 32 * T3_EPI_WARPS;
+// Per-warp staging buffer of the epilogue: a 32-row x 16-column chunk is transposed through shared memory so that every
+// global store instruction writes whole 32-byte sectors (a row-per-lane store of 8 or 16 bytes per lane costs a full L2
+// sector transaction each: measured 32 sectors per request and an L2-transaction-bound kernel).  fp32: [32][20] floats
+// (row pitch 80 B, conflict-free for 16-byte accesses); planes: hi [32] x 48 B then lo [32] x 48 B.
+constexpr int T3_STG_BYTES = 3072;
+constexpr int T3_STG_F32_PITCH = 20;   // floats
+constexpr int T3_STG_PL_PITCH = 48;    // bytes
+constexpr size_t T3_SMEM_TOTAL = 225 * 1024;
 
 struct T3Args {
   int T, rpb, B, N, C, taps, NT, colstride;
@@ -155,88 +162,144 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ 
     constexpr int NSUB = T3_EPI_WARPS / 4;
     const int q = warp & 3, sub = (warp - 2) >> 2;
     const int nchunks = a.NT / 16;
+    unsigned char* stg = smem + (size_t)NS * stage_bytes + (size_t)(warp - 2) * T3_STG_BYTES;
+    float* stg_f = reinterpret_cast<float*>(stg);
+    // coalesced mappings of a 32 x 16 chunk: fp32 -> 4 instructions of (row = lane % 8 + 8 i, columns (lane / 8) * 4 ..+3);
+    // planes -> 2 instructions of (row = lane % 16 + 16 i, columns (lane / 16) * 8 ..+7)
+    const int fr = lane & 7, fc = (lane >> 3) * 4, pr = lane & 15, pc = (lane >> 4) * 8;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1u, u = tl >> 1;
       const int nt = tile % a.n_tiles, rest = tile / a.n_tiles, mt = rest % a.m_tiles, b = rest / a.m_tiles;
-      const int n0 = nt * a.NT, t = mt * T3_BM + q * 32 + lane;
+      const int n0 = nt * a.NT, tw = mt * T3_BM + q * 32;   // first row of this warp's 32 rows
+      const int t = tw + lane;
       const bool rowok = t < a.T;
-      float* yrow = a.y32 ? a.y32 + (long long)b * a.y_batch + (long long)t * a.ldy : nullptr;
-      const float* rrow = (a.res && rowok) ? a.res + (long long)b * a.r_batch + (long long)t * a.ldr : nullptr;
-      uint16_t* hrow = a.yhi ? a.yhi + (long long)b * a.p_batch + (long long)t * a.ldp : nullptr;
-      uint16_t* lrow = a.yhi ? a.ylo + (long long)b * a.p_batch + (long long)t * a.ldp : nullptr;
-      // the residual does not depend on the accumulator: its loads for the first chunk go out before the wait, those of the
-      // next chunk before the current chunk's stores (in place: every element is read before the same thread overwrites it)
-      float4 rv[4];
-      auto load_res = [&](int ci, float4 (&dst)[4]) {
+      if (!a.vec) {
+        // ---- generic path (N not a multiple of 16: the 1-channel output conv): row per lane, scalar
+        if (!tc_mbar_wait(&tfull[acc], u & 1u, a.err)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ci = sub; ci < nchunks; ci += NSUB) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.colstride + (uint32_t)(ci * 16), v);
+          if (!rowok) continue;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const int n = n0 + ci * 16 + j4 * 4;
-          dst[j4] = (rrow && a.vec && n + 3 < a.N) ? *reinterpret_cast<const float4*>(rrow + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      if (sub < nchunks) load_res(sub, rv);
-      if (!tc_mbar_wait(&tfull[acc], u & 1u, a.err)) break;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int ci = sub; ci < nchunks; ci += NSUB) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.colstride + (uint32_t)(ci * 16), v);
-        float4 rnext[4];
-        if (ci + NSUB < nchunks) load_res(ci + NSUB, rnext);
-        if (rowok) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int n = n0 + ci * 16 + j4 * 4;
-            if (n >= a.N) continue;
-            float x[4] = {__uint_as_float(v[j4 * 4]), __uint_as_float(v[j4 * 4 + 1]), __uint_as_float(v[j4 * 4 + 2]),
-                          __uint_as_float(v[j4 * 4 + 3])};
-            if (a.vec && n + 3 < a.N) {
-              if (a.bias) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                x[0] += bv.x; x[1] += bv.y; x[2] += bv.z; x[3] += bv.w;
-              }
-              if (a.act_out == 1) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = t3_gelu(x[e]);
-              }
-              if (a.scale) {
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(a.scale + n));
-                x[0] *= sv.x; x[1] *= sv.y; x[2] *= sv.z; x[3] *= sv.w;
-              }
-              if (rrow) {
-                x[0] += rv[j4].x; x[1] += rv[j4].y; x[2] += rv[j4].z; x[3] += rv[j4].w;
-              }
-              if (yrow) *reinterpret_cast<float4*>(yrow + n) = make_float4(x[0], x[1], x[2], x[3]);
-              if (hrow) {
-                if (a.plane_act == 1) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) x[e] = t3_elu(x[e]);
-                }
-                store_split4_cvt(hrow + n, lrow + n, x[0], x[1], x[2], x[3]);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e >= a.N) break;
-                float xv = x[e];
-                if (a.bias) xv += __ldg(a.bias + n + e);
-                if (a.act_out == 1) xv = t3_gelu(xv);
-                if (a.scale) xv *= __ldg(a.scale + n + e);
-                if (rrow) xv += rrow[n + e];
-                if (yrow) yrow[n + e] = xv;
-                if (hrow) {
-                  if (a.plane_act == 1) xv = t3_elu(xv);
-                  uint16_t hh, ll;
-                  split_bf16(xv, hh, ll);
-                  hrow[n + e] = hh;
-                  lrow[n + e] = ll;
-                }
-              }
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + ci * 16 + e;
+            if (n >= a.N) break;
+            float xv = __uint_as_float(v[e]);
+            if (a.bias) xv += __ldg(a.bias + n);
+            if (a.act_out == 1) xv = t3_gelu(xv);
+            if (a.scale) xv *= __ldg(a.scale + n);
+            if (a.res) xv += a.res[(long long)b * a.r_batch + (long long)t * a.ldr + n];
+            if (a.y32) a.y32[(long long)b * a.y_batch + (long long)t * a.ldy + n] = xv;
+            if (a.yhi) {
+              if (a.plane_act == 1) xv = t3_elu(xv);
+              uint16_t hh, ll;
+              split_bf16(xv, hh, ll);
+              a.yhi[(long long)b * a.p_batch + (long long)t * a.ldp + n] = hh;
+              a.ylo[(long long)b * a.p_batch + (long long)t * a.ldp + n] = ll;
             }
           }
         }
+      } else {
+        // ---- coalesced path.  The residual does not depend on the accumulator: its (coalesced) loads for the first chunk
+        // go out before the wait, those of the next chunk before the current chunk's stores (in place: every element is
+        // read before the same warp overwrites it, and no other warp touches it).
+        float4 rres[4];
+        auto load_res = [&](int ci) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) rv[j4] = rnext[j4];
+          for (int i = 0; i < 4; ++i) {
+            const int tr = tw + fr + 8 * i, n = n0 + ci * 16 + fc;
+            rres[i] = (tr < a.T && n < a.N)
+                          ? *reinterpret_cast<const float4*>(a.res + (long long)b * a.r_batch + (long long)tr * a.ldr + n)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        if (a.res && sub < nchunks) load_res(sub);
+        if (!tc_mbar_wait(&tfull[acc], u & 1u, a.err)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ci = sub; ci < nchunks; ci += NSUB) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.colstride + (uint32_t)(ci * 16), v);
+          const int nc = n0 + ci * 16;   // first column of the chunk
+          float x[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) x[e] = __uint_as_float(v[e]);
+          if (a.bias) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = (nc + j4 * 4 < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + nc + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[j4 * 4] += bv.x; x[j4 * 4 + 1] += bv.y; x[j4 * 4 + 2] += bv.z; x[j4 * 4 + 3] += bv.w;
+            }
+          }
+          if (a.act_out == 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) x[e] = t3_gelu(x[e]);
+          }
+          if (a.scale) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 sv = (nc + j4 * 4 < a.N) ? __ldg(reinterpret_cast<const float4*>(a.scale + nc + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[j4 * 4] *= sv.x; x[j4 * 4 + 1] *= sv.y; x[j4 * 4 + 2] *= sv.z; x[j4 * 4 + 3] *= sv.w;
+            }
+          }
+          if (a.res) {
+            // residual: coalesced registers -> staging -> this lane's row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg_f + (fr + 8 * i) * T3_STG_F32_PITCH + fc) = rres[i];
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 rv = *reinterpret_cast<const float4*>(stg_f + lane * T3_STG_F32_PITCH + j4 * 4);
+              x[j4 * 4] += rv.x; x[j4 * 4 + 1] += rv.y; x[j4 * 4 + 2] += rv.z; x[j4 * 4 + 3] += rv.w;
+            }
+            __syncwarp();
+            if (ci + NSUB < nchunks) load_res(ci + NSUB);
+          }
+          if (a.y32) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<float4*>(stg_f + lane * T3_STG_F32_PITCH + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int tr = tw + fr + 8 * i, n = nc + fc;
+              if (tr < a.T && n < a.N)
+                *reinterpret_cast<float4*>(a.y32 + (long long)b * a.y_batch + (long long)tr * a.ldy + n) =
+                    *reinterpret_cast<const float4*>(stg_f + (fr + 8 * i) * T3_STG_F32_PITCH + fc);
+            }
+            __syncwarp();
+          }
+          if (a.yhi) {
+            if (a.plane_act == 1) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) x[e] = t3_elu(x[e]);
+            }
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int p2 = 0; p2 < 8; ++p2) {
+              h[p2] = pack_bf16x2_rn(x[2 * p2], x[2 * p2 + 1]);
+              l[p2] = pack_bf16x2_rn(x[2 * p2] - __uint_as_float(h[p2] << 16), x[2 * p2 + 1] - __uint_as_float(h[p2] & 0xffff0000u));
+            }
+            unsigned char* hs = stg + lane * T3_STG_PL_PITCH;
+            unsigned char* ls = stg + 32 * T3_STG_PL_PITCH + lane * T3_STG_PL_PITCH;
+            *reinterpret_cast<uint4*>(hs) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(hs + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(ls) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(ls + 16) = make_uint4(l[4], l[5], l[6], l[7]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int row = pr + 16 * i, tr = tw + row, n = nc + pc;
+              if (tr < a.T && n < a.N) {
+                const long long o = (long long)b * a.p_batch + (long long)tr * a.ldp + n;
+                *reinterpret_cast<uint4*>(a.yhi + o) = *reinterpret_cast<const uint4*>(stg + row * T3_STG_PL_PITCH + pc * 2);
+                *reinterpret_cast<uint4*>(a.ylo + o) = *reinterpret_cast<const uint4*>(stg + 32 * T3_STG_PL_PITCH + row * T3_STG_PL_PITCH + pc * 2);
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -303,6 +366,106 @@ __global__ void __launch_bounds__(256) k_layernorm_planes(const float* __restric
       store_split4(hi + o, lo + o, (v[j].x - mean) * rstd * g.x + bb.x, (v[j].y - mean) * rstd * g.y + bb.y,
                    (v[j].z - mean) * rstd * g.z + bb.z, (v[j].w - mean) * rstd * g.w + bb.w);
     }
+}
+
+// ---- whole-clip attention of the codec transformers ---------------------------------------------------------------------
+// RoPE (adjacent pairs, angle = position * freqs[i]; position = row index: whole clips start at 0) on q and k, in place in
+// qkv [B][T][3][H][64].
+__global__ void __launch_bounds__(256) k_mimi_rope_inplace(float* __restrict__ qkv, const float* __restrict__ freqs, int T, int H) {
+  const int bt = blockIdx.x, t = bt % T;
+  float* row = qkv + (size_t)bt * 3 * H * 64;
+  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) {
+    const int h = i >> 5, p = i & 31;
+    float sn, cs;
+    sincosf((float)t * freqs[p], &sn, &cs);
+    const float2 qv = *reinterpret_cast<float2*>(row + h * 64 + 2 * p);
+    *reinterpret_cast<float2*>(row + h * 64 + 2 * p) = make_float2(qv.x * cs - qv.y * sn, qv.x * sn + qv.y * cs);
+    const float2 kv = *reinterpret_cast<float2*>(row + (H + h) * 64 + 2 * p);
+    *reinterpret_cast<float2*>(row + (H + h) * 64 + 2 * p) = make_float2(kv.x * cs - kv.y * sn, kv.x * sn + kv.y * cs);
+  }
+}
+
+// Causal attention over the last `ctx` positions, one block per (32 queries, head, clip): the <= ctx + 31 key and value rows
+// the block's queries share are staged ONCE in shared memory (the per-query kernel of the streaming path re-reads them from
+// L2 for every query: 128 KB per query, L2-bandwidth-bound at batch scale).  Same arithmetic and summation order as
+// k_mimi_attention; the output goes straight to the bf16 hi/lo planes of the out-projection's operand.
+constexpr int AT_QT = 32, AT_PITCH = 68, AT_WARPS = 8;
+__global__ void __launch_bounds__(AT_WARPS * 32) k_mimi_attn_tile(const float* __restrict__ qkv, uint16_t* __restrict__ out_hi,
+                                                                  uint16_t* __restrict__ out_lo, int T, int H, int ctx) {
+  extern __shared__ float at_sm[];
+  const int kt_max = AT_QT + ctx - 1;
+  float* sK = at_sm;
+  float* sV = sK + (size_t)kt_max * AT_PITCH;
+  float* sQ = sV + (size_t)kt_max * AT_PITCH;
+  float* sS = sQ + AT_WARPS * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * AT_QT, h = blockIdx.y, b = blockIdx.z;
+  const int k_first = t0 - ctx + 1 > 0 ? t0 - ctx + 1 : 0;
+  const int k_last = t0 + AT_QT - 1 < T - 1 ? t0 + AT_QT - 1 : T - 1;
+  const int nk = k_last - k_first + 1;
+  const size_t rs = (size_t)3 * H * 64;
+  const float* base = qkv + (size_t)b * T * rs;
+  for (int idx = threadIdx.x; idx < nk * 16; idx += AT_WARPS * 32) {
+    const int row = idx >> 4, c4 = (idx & 15) * 4;
+    const float* src = base + (size_t)(k_first + row) * rs + (size_t)h * 64 + c4;
+    *reinterpret_cast<float4*>(sK + (size_t)row * AT_PITCH + c4) = *reinterpret_cast<const float4*>(src + (size_t)H * 64);
+    *reinterpret_cast<float4*>(sV + (size_t)row * AT_PITCH + c4) = *reinterpret_cast<const float4*>(src + (size_t)2 * H * 64);
+  }
+  __syncthreads();
+  float* sq = sQ + warp * 64;
+  float* sc = sS + (size_t)warp * ctx;
+  for (int i = 0; i < AT_QT / AT_WARPS; ++i) {
+    const int t = t0 + warp * (AT_QT / AT_WARPS) + i;
+    if (t >= T) break;
+    const float* q = base + (size_t)t * rs + (size_t)h * 64;
+    sq[lane] = q[lane];
+    sq[lane + 32] = q[lane + 32];
+    __syncwarp();
+    const int first = t - ctx + 1 > 0 ? t - ctx + 1 : 0;
+    const int S = t - first + 1, off = first - k_first;
+    float m = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      const float* kp = sK + (size_t)(off + j) * AT_PITCH;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+        dot = fmaf(kv.x, sq[c], dot);
+        dot = fmaf(kv.y, sq[c + 1], dot);
+        dot = fmaf(kv.z, sq[c + 2], dot);
+        dot = fmaf(kv.w, sq[c + 3], dot);
+      }
+      dot *= 0.125f;
+      sc[j] = dot;
+      m = fmaxf(m, dot);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(sc[j] - m);
+      sc[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = sc[j];
+      const float* vp = sV + (size_t)(off + j) * AT_PITCH;
+      a0 = fmaf(pj, vp[lane], a0);
+      a1 = fmaf(pj, vp[lane + 32], a1);
+    }
+    const float inv = 1.f / sum;
+    const size_t o = ((size_t)b * T + t) * H * 64 + (size_t)h * 64;
+    uint16_t hh, ll;
+    split_bf16(a0 * inv, hh, ll);
+    out_hi[o + lane] = hh;
+    out_lo[o + lane] = ll;
+    split_bf16(a1 * inv, hh, ll);
+    out_hi[o + lane + 32] = hh;
+    out_lo[o + lane + 32] = ll;
+    __syncwarp();  // sq / sc are reused by this warp's next query
+  }
 }
 
 // First SEANet encoder conv, Conv1d(1 -> C, k): x [B][(k-1) + N] fp32 (left-padded) -> y [B][ypad + N][C] fp32 and
@@ -403,7 +566,8 @@ int csmb_gemm_tc3(const csmb_tc3* g, int device, void* stream) {
   a.total_tiles = (int)total;
   a.nk = cdiv(K, TC_BK);
   const size_t stage = (size_t)2 * T3_BM * TC_BK * 2 + (size_t)2 * a.NT * TC_BK * 2;
-  int nstages = (int)(T3_SMEM_BUDGET / stage);
+  const size_t epi_smem = (size_t)T3_EPI_WARPS * T3_STG_BYTES;
+  int nstages = (int)((T3_SMEM_TOTAL - 1024 - epi_smem) / stage);
   nstages = nstages > T3_MAX_STAGES ? T3_MAX_STAGES : nstages;
   CSMB_REQUIRE(nstages >= 2);
   a.nstages = nstages;
@@ -413,16 +577,16 @@ int csmb_gemm_tc3(const csmb_tc3* g, int device, void* stream) {
   a.act_out = g->act_out;
   a.err = g->err_flag;
   auto al = [](const void* p, uintptr_t m) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & m) == 0; };
-  a.vec = (g->N % 4 == 0) && al(g->bias, 15) && al(g->scale, 15) &&
+  a.vec = (g->N % 16 == 0) && al(g->bias, 15) && al(g->scale, 15) &&
           (!g->y32 || (al(g->y32, 15) && g->ldy % 4 == 0 && g->y_batch % 4 == 0)) &&
           (!g->residual || (al(g->residual, 15) && g->ldr % 4 == 0 && g->r_batch % 4 == 0)) &&
-          (!g->y_hi || (al(g->y_hi, 7) && al(g->y_lo, 7) && g->ldp % 4 == 0 && g->p_batch % 4 == 0));
+          (!g->y_hi || (al(g->y_hi, 15) && al(g->y_lo, 15) && g->ldp % 8 == 0 && g->p_batch % 8 == 0));
   CUtensorMap mahi, malo, mwhi, mwlo;
   if (!tc_make_map_ld(&mahi, g->a_hi, g->a_rows, g->C, g->lda, T3_BM) || !tc_make_map_ld(&malo, g->a_lo, g->a_rows, g->C, g->lda, T3_BM) ||
       !tc_make_map_ld(&mwhi, g->w_hi, g->w_rows, K, g->ldw, a.NT) || !tc_make_map_ld(&mwlo, g->w_lo, g->w_rows, K, g->ldw, a.NT))
     return CSMB_ERR_UNSUPPORTED;
-  const size_t smem = stage * nstages + 1024;
-  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T3_SMEM_BUDGET + 1024)));
+  const size_t smem = stage * nstages + epi_smem + 1024;
+  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM_TOTAL));
   int sms = 0;
   CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
@@ -450,6 +614,21 @@ int csmb_layernorm_planes(const float* x, long long x_batch, const float* w, con
   if (R == 0) return CSMB_OK;
   CSMB_REQUIRE(d % 128 == 0 && d <= 1024 && x_batch % 4 == 0);
   k_layernorm_planes<<<cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(x, x_batch, w, b, hi, lo, R, T, d, eps);
+  CSMB_LAUNCH_CHECK();
+  return CSMB_OK;
+}
+
+int csmb_mimi_attention_planes(float* qkv, const float* freqs, uint16_t* out_hi, uint16_t* out_lo, int B, int T, int H, int ctx,
+                               int device, void* stream) {
+  CSMB_ENTER(device);
+  CSMB_REQUIRE(qkv && freqs && out_hi && out_lo && B > 0 && T > 0 && H > 0 && ctx > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_mimi_rope_inplace<<<B * T, 256, 0, st>>>(qkv, freqs, T, H);
+  CSMB_LAUNCH_CHECK();
+  const size_t smem = ((size_t)2 * (AT_QT + ctx - 1) * AT_PITCH + AT_WARPS * 64 + (size_t)AT_WARPS * ctx) * sizeof(float);
+  CSMB_REQUIRE(smem <= 220 * 1024);
+  CSMB_CUDA(cudaFuncSetAttribute(k_mimi_attn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mimi_attn_tile<<<dim3(cdiv(T, AT_QT), H, B), AT_WARPS * 32, smem, st>>>(qkv, out_hi, out_lo, T, H, ctx);
   CSMB_LAUNCH_CHECK();
   return CSMB_OK;
 }

@@ -145,17 +145,13 @@ class MimiTC:
         att_p = _Act(B, T, DIM, dev)
         ffp = _Act(B, T, FF, dev)
         qkv = torch.empty((B, T, 3 * DIM), device=dev, dtype=torch.float32)
-        att = torch.empty((B, T, DIM), device=dev, dtype=torch.float32)
-        cache = torch.zeros((B, CONTEXT + T, 2, HEADS, 64), device=dev, dtype=torch.float32)
         layers = self.tr[side]
         for li, (w_in, w_out, w1, w2, t) in enumerate(layers):
             _lib.check(lib.csmb_layernorm_planes(x.data_ptr(), xb, t.n1w.data_ptr(), t.n1b.data_ptr(), h.hi.data_ptr(),
                                                  h.lo.data_ptr(), B, T, DIM, LN_EPS, m.dev_idx, m._st()))
             self.gemm(h, 1, w_in, B, T, y32_ptr=qkv.data_ptr(), y_batch=T * 3 * DIM, ldy=3 * DIM)
-            _lib.check(lib.csmb_mimi_attention(qkv.data_ptr(), cache.data_ptr(), m.freqs.data_ptr(), m._zero_pos.data_ptr(),
-                                               att.data_ptr(), B, T, HEADS, CONTEXT + T, CONTEXT, m.dev_idx, m._st()))
-            _lib.check(lib.csmb_split_planes(att.data_ptr(), T * DIM, DIM, att_p.hi.data_ptr(), att_p.lo.data_ptr(), T * DIM, DIM,
-                                             B, T, DIM, 0, m.dev_idx, m._st()))
+            _lib.check(lib.csmb_mimi_attention_planes(qkv.data_ptr(), m.freqs.data_ptr(), att_p.hi.data_ptr(), att_p.lo.data_ptr(),
+                                                      B, T, HEADS, CONTEXT, m.dev_idx, m._st()))
             self.gemm(att_p, 1, w_out, B, T, y32_ptr=x.data_ptr(), y_batch=xb, ldy=DIM, res_ptr=x.data_ptr(), r_batch=xb,
                       ldr=DIM, scale=t.ls1)
             _lib.check(lib.csmb_layernorm_planes(x.data_ptr(), xb, t.n2w.data_ptr(), t.n2b.data_ptr(), h.hi.data_ptr(),

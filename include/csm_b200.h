@@ -372,6 +372,12 @@ int csmb_split_planes(const float* x, long long x_batch, int ldx, uint16_t* hi, 
 /* csmb_layernorm writing dense [B*T][d] bf16 hi/lo planes (the operand of the next tensor-core Linear). */
 int csmb_layernorm_planes(const float* x, long long x_batch, const float* w, const float* b, uint16_t* hi, uint16_t* lo, int B,
                           int T, int d, float eps, int device, void* stream);
+/* Whole-clip attention of the codec transformers (moshi StreamingMultiheadAttention with context 250, RoPE base 10 000 on
+ * adjacent pairs): qkv [B][T][3][H][64] fp32 from the in-projection; q and k are rotated IN PLACE (position = row index), then
+ * every position attends causally to the last `ctx` positions; out_hi / out_lo [B][T][H*64] are the bf16 planes the
+ * out-projection reads.  One block per (32 queries, head, clip) with the shared keys / values staged in shared memory. */
+int csmb_mimi_attention_planes(float* qkv, const float* freqs, uint16_t* out_hi, uint16_t* out_lo, int B, int T, int H, int ctx,
+                               int device, void* stream);
 /* First SEANet encoder layer, Conv1d(1 -> C, k) + bias: x [B][(k-1) + N] fp32 (left-padded, batch stride x_batch) ->
  * y fp32 and ELU(y) planes, both [B][..][C] with batch stride y_batch (pointers already at the first output row). */
 int csmb_conv_in_planes(const float* x, long long x_batch, const float* w, const float* bias, float* y, uint16_t* hi,
