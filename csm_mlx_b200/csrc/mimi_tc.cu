@@ -62,6 +62,12 @@ __device__ __forceinline__ void t3_mbar_arrive(uint64_t* b) {
 // ELU for the bf16 planes: exp(v) - 1 with the fast exponential (absolute error ~1e-7, far below the 2^-17 relative step of
 // the hi/lo planes it is written to); the fp32 path keeps expm1f
 __device__ __forceinline__ float t3_elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// 16-byte global load that does not allocate an L1 line (plain ld.global, coherent: the residual may alias the output)
+__device__ __forceinline__ float4 ld_noalloc_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ float t3_gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
 
 __global__ void __launch_bounds__(T3_THREADS, 1)
@@ -176,7 +182,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ 
       const bool rowok = t < a.T;
       if (!a.vec) {
         // ---- generic path (N not a multiple of 16: the 1-channel output conv): row per lane, scalar
-        if (!tc_mbar_wait(&tfull[acc], u & 1u, a.err)) break;
+        if (!tc_mbar_wait_warp(&tfull[acc], u & 1u, a.err)) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ci = sub; ci < nchunks; ci += NSUB) {
           uint32_t v[16];
@@ -205,20 +211,32 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ 
         // ---- coalesced path.  The residual does not depend on the accumulator: its (coalesced) loads for the first chunk
         // go out before the wait, those of the next chunk before the current chunk's stores (in place: every element is
         // read before the same warp overwrites it, and no other warp touches it).
-        float4 rres[4];
-        auto load_res = [&](int ci) {
+        // ALL of this warp's chunks of the tile (at most MAXC) have their residual in flight before the wait, each in its
+        // own registers (a rotating buffer stalls on the copy of a load still in flight); streaming loads: with 225 KB of
+        // shared memory the L1 has almost no lines left to allocate, and allocating loads serialise on them
+        constexpr int MAXC = 8 / NSUB;   // NT <= 128: 8 chunks shared by NSUB sub-warps
+        float4 rres_all[MAXC][4];
+        if (a.res) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int tr = tw + fr + 8 * i, n = n0 + ci * 16 + fc;
-            rres[i] = (tr < a.T && n < a.N)
-                          ? *reinterpret_cast<const float4*>(a.res + (long long)b * a.r_batch + (long long)tr * a.ldr + n)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < MAXC; ++k) {
+            const int ci = sub + k * NSUB;
+            if (ci < nchunks) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int tr = tw + fr + 8 * i, n = n0 + ci * 16 + fc;
+                rres_all[k][i] = (tr < a.T && n < a.N) ? ld_noalloc_f4(a.res + (long long)b * a.r_batch + (long long)tr * a.ldr + n)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
           }
-        };
-        if (a.res && sub < nchunks) load_res(sub);
-        if (!tc_mbar_wait(&tfull[acc], u & 1u, a.err)) break;
+        }
+        if (!tc_mbar_wait_warp(&tfull[acc], u & 1u, a.err)) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int ci = sub; ci < nchunks; ci += NSUB) {
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+          const int ci = sub + k * NSUB;
+          if (ci >= nchunks) break;
+          const float4 (&rres)[4] = rres_all[k];
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.colstride + (uint32_t)(ci * 16), v);
           const int nc = n0 + ci * 16;   // first column of the chunk
@@ -254,7 +272,6 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ 
               x[j4 * 4] += rv.x; x[j4 * 4 + 1] += rv.y; x[j4 * 4 + 2] += rv.z; x[j4 * 4 + 3] += rv.w;
             }
             __syncwarp();
-            if (ci + NSUB < nchunks) load_res(ci + NSUB);
           }
           if (a.y32) {
 #pragma unroll
@@ -387,17 +404,20 @@ __global__ void __launch_bounds__(256) k_mimi_rope_inplace(float* __restrict__ q
 
 // Causal attention over the last `ctx` positions, one block per (32 queries, head, clip): the <= ctx + 31 key and value rows
 // the block's queries share are staged ONCE in shared memory (the per-query kernel of the streaming path re-reads them from
-// L2 for every query: 128 KB per query, L2-bandwidth-bound at batch scale).  Same arithmetic and summation order as
-// k_mimi_attention; the output goes straight to the bf16 hi/lo planes of the out-projection's operand.
-constexpr int AT_QT = 32, AT_PITCH = 68, AT_WARPS = 8;
+// L2 for every query: 128 KB per query, L2-bandwidth-bound at batch scale), and every warp works on FOUR consecutive queries
+// at a time so that a key / value row read from shared memory is used four times (the kernel is shared-memory-bandwidth
+// bound).  Per (query, key) the dot product runs over the 64 dims in ascending order and P.V over the keys in ascending
+// order, as in k_mimi_attention; the output goes straight to the bf16 hi/lo planes of the out-projection's operand.
+constexpr int AT_QT = 32, AT_PITCH = 68, AT_WARPS = 8, AT_QW = AT_QT / AT_WARPS;
+static_assert(AT_QW == 4, "the warp body is written for four queries");
 __global__ void __launch_bounds__(AT_WARPS * 32) k_mimi_attn_tile(const float* __restrict__ qkv, uint16_t* __restrict__ out_hi,
                                                                   uint16_t* __restrict__ out_lo, int T, int H, int ctx) {
   extern __shared__ float at_sm[];
-  const int kt_max = AT_QT + ctx - 1;
+  const int kt_max = AT_QT + ctx - 1, sc_len = ctx + AT_QW - 1;
   float* sK = at_sm;
   float* sV = sK + (size_t)kt_max * AT_PITCH;
-  float* sQ = sV + (size_t)kt_max * AT_PITCH;
-  float* sS = sQ + AT_WARPS * 64;
+  float* sQ = sV + (size_t)kt_max * AT_PITCH;          // [warp][4 queries][64]
+  float* sS = sQ + AT_WARPS * AT_QW * 64;              // [warp][key][4 queries]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * AT_QT, h = blockIdx.y, b = blockIdx.z;
   const int k_first = t0 - ctx + 1 > 0 ? t0 - ctx + 1 : 0;
@@ -405,66 +425,142 @@ __global__ void __launch_bounds__(AT_WARPS * 32) k_mimi_attn_tile(const float* _
   const int nk = k_last - k_first + 1;
   const size_t rs = (size_t)3 * H * 64;
   const float* base = qkv + (size_t)b * T * rs;
-  for (int idx = threadIdx.x; idx < nk * 16; idx += AT_WARPS * 32) {
-    const int row = idx >> 4, c4 = (idx & 15) * 4;
-    const float* src = base + (size_t)(k_first + row) * rs + (size_t)h * 64 + c4;
-    *reinterpret_cast<float4*>(sK + (size_t)row * AT_PITCH + c4) = *reinterpret_cast<const float4*>(src + (size_t)H * 64);
-    *reinterpret_cast<float4*>(sV + (size_t)row * AT_PITCH + c4) = *reinterpret_cast<const float4*>(src + (size_t)2 * H * 64);
+  // four rows per thread and iteration: eight independent 16-byte loads in flight
+  for (int idx0 = threadIdx.x; idx0 < nk * 16; idx0 += 4 * AT_WARPS * 32) {
+    float4 kv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * AT_WARPS * 32;
+      if (idx < nk * 16) {
+        const float* src = base + (size_t)(k_first + (idx >> 4)) * rs + (size_t)h * 64 + (idx & 15) * 4;
+        kv[u] = *reinterpret_cast<const float4*>(src + (size_t)H * 64);
+        vv[u] = *reinterpret_cast<const float4*>(src + (size_t)2 * H * 64);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * AT_WARPS * 32;
+      if (idx < nk * 16) {
+        *reinterpret_cast<float4*>(sK + (size_t)(idx >> 4) * AT_PITCH + (idx & 15) * 4) = kv[u];
+        *reinterpret_cast<float4*>(sV + (size_t)(idx >> 4) * AT_PITCH + (idx & 15) * 4) = vv[u];
+      }
+    }
+  }
+  const int tq0 = t0 + warp * AT_QW;
+  float* sq = sQ + warp * AT_QW * 64;
+  float* sc = sS + (size_t)warp * sc_len * AT_QW;
+  const int nq = tq0 < T ? (T - tq0 < AT_QW ? T - tq0 : AT_QW) : 0;
+  for (int i = 0; i < AT_QW; ++i) {   // this warp's query vectors (zeros past the end of the clip)
+    const int t = tq0 + i;
+    sq[i * 64 + lane] = t < T ? base[(size_t)t * rs + (size_t)h * 64 + lane] : 0.f;
+    sq[i * 64 + lane + 32] = t < T ? base[(size_t)t * rs + (size_t)h * 64 + lane + 32] : 0.f;
   }
   __syncthreads();
-  float* sq = sQ + warp * 64;
-  float* sc = sS + (size_t)warp * ctx;
-  for (int i = 0; i < AT_QT / AT_WARPS; ++i) {
-    const int t = t0 + warp * (AT_QT / AT_WARPS) + i;
-    if (t >= T) break;
-    const float* q = base + (size_t)t * rs + (size_t)h * 64;
-    sq[lane] = q[lane];
-    sq[lane + 32] = q[lane + 32];
-    __syncwarp();
-    const int first = t - ctx + 1 > 0 ? t - ctx + 1 : 0;
-    const int S = t - first + 1, off = first - k_first;
-    float m = -INFINITY;
-    for (int j = lane; j < S; j += 32) {
-      const float* kp = sK + (size_t)(off + j) * AT_PITCH;
-      float dot = 0.f;
+  if (nq == 0) return;
+  // union key window of the warp's queries: positions first0 .. tq0 + nq - 1
+  const int first0 = tq0 - ctx + 1 > 0 ? tq0 - ctx + 1 : 0;
+  const int Su = tq0 + nq - first0, off = first0 - k_first;
+  float mx[AT_QW];
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
-        dot = fmaf(kv.x, sq[c], dot);
-        dot = fmaf(kv.y, sq[c + 1], dot);
-        dot = fmaf(kv.z, sq[c + 2], dot);
-        dot = fmaf(kv.w, sq[c + 3], dot);
+  for (int i = 0; i < AT_QW; ++i) mx[i] = -INFINITY;
+  for (int j = lane; j < Su; j += 64) {   // two keys per lane at a time x four queries: eight independent fma chains
+    const float* kp[2];
+    float dot[2][AT_QW];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      kp[u] = sK + (size_t)(off + (j + 32 * u < Su ? j + 32 * u : j)) * AT_PITCH;
+#pragma unroll
+      for (int i = 0; i < AT_QW; ++i) dot[u][i] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+      float4 qv[AT_QW];
+#pragma unroll
+      for (int i = 0; i < AT_QW; ++i) qv[i] = *reinterpret_cast<const float4*>(sq + i * 64 + c);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp[u] + c);
+#pragma unroll
+        for (int i = 0; i < AT_QW; ++i) {
+          dot[u][i] = fmaf(kv.x, qv[i].x, dot[u][i]);
+          dot[u][i] = fmaf(kv.y, qv[i].y, dot[u][i]);
+          dot[u][i] = fmaf(kv.z, qv[i].z, dot[u][i]);
+          dot[u][i] = fmaf(kv.w, qv[i].w, dot[u][i]);
+        }
       }
-      dot *= 0.125f;
-      sc[j] = dot;
-      m = fmaxf(m, dot);
     }
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < S; j += 32) {
-      const float e = expf(sc[j] - m);
-      sc[j] = e;
-      sum += e;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int jj = j + 32 * u;
+      if (jj < Su) {
+        const int pos = first0 + jj;
+        float d[AT_QW];
+#pragma unroll
+        for (int i = 0; i < AT_QW; ++i) {
+          const int t = tq0 + i;
+          const bool valid = i < nq && pos <= t && pos > t - ctx;
+          d[i] = valid ? dot[u][i] * 0.125f : -INFINITY;
+          mx[i] = fmaxf(mx[i], d[i]);
+        }
+        *reinterpret_cast<float4*>(sc + (size_t)jj * AT_QW) = make_float4(d[0], d[1], d[2], d[3]);
+      }
     }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < S; ++j) {
-      const float pj = sc[j];
-      const float* vp = sV + (size_t)(off + j) * AT_PITCH;
-      a0 = fmaf(pj, vp[lane], a0);
-      a1 = fmaf(pj, vp[lane + 32], a1);
+  }
+  float sum[AT_QW];
+#pragma unroll
+  for (int i = 0; i < AT_QW; ++i) {
+    mx[i] = warp_max(mx[i]);
+    sum[i] = 0.f;
+  }
+  __syncwarp();
+  for (int j = lane; j < Su; j += 32) {
+    float4 e = *reinterpret_cast<const float4*>(sc + (size_t)j * AT_QW);
+    e.x = expf(e.x - mx[0]);   // masked entries: exp(-inf) = 0
+    e.y = nq > 1 ? expf(e.y - mx[1]) : 0.f;
+    e.z = nq > 2 ? expf(e.z - mx[2]) : 0.f;
+    e.w = nq > 3 ? expf(e.w - mx[3]) : 0.f;
+    *reinterpret_cast<float4*>(sc + (size_t)j * AT_QW) = e;
+    sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+  }
+#pragma unroll
+  for (int i = 0; i < AT_QW; ++i) sum[i] = warp_sum(sum[i]);
+  __syncwarp();
+  float a0[AT_QW], a1[AT_QW];
+#pragma unroll
+  for (int i = 0; i < AT_QW; ++i) a0[i] = a1[i] = 0.f;
+  // keys in groups of 4: the loads of a group are independent; accumulation order stays j ascending per query
+  for (int j0 = 0; j0 < Su; j0 += 4) {
+    float4 pj[4];
+    float v0[4], v1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j0 + u < Su ? j0 + u : Su - 1;
+      const float* vp = sV + (size_t)(off + jj) * AT_PITCH;
+      pj[u] = *reinterpret_cast<const float4*>(sc + (size_t)jj * AT_QW);
+      v0[u] = vp[lane];
+      v1[u] = vp[lane + 32];
     }
-    const float inv = 1.f / sum;
-    const size_t o = ((size_t)b * T + t) * H * 64 + (size_t)h * 64;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u < Su) {
+        a0[0] = fmaf(pj[u].x, v0[u], a0[0]); a1[0] = fmaf(pj[u].x, v1[u], a1[0]);
+        a0[1] = fmaf(pj[u].y, v0[u], a0[1]); a1[1] = fmaf(pj[u].y, v1[u], a1[1]);
+        a0[2] = fmaf(pj[u].z, v0[u], a0[2]); a1[2] = fmaf(pj[u].z, v1[u], a1[2]);
+        a0[3] = fmaf(pj[u].w, v0[u], a0[3]); a1[3] = fmaf(pj[u].w, v1[u], a1[3]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < AT_QW; ++i) {
+    if (i >= nq) break;
+    const float inv = 1.f / sum[i];
+    const size_t o = ((size_t)b * T + tq0 + i) * H * 64 + (size_t)h * 64;
     uint16_t hh, ll;
-    split_bf16(a0 * inv, hh, ll);
+    split_bf16(a0[i] * inv, hh, ll);
     out_hi[o + lane] = hh;
     out_lo[o + lane] = ll;
-    split_bf16(a1 * inv, hh, ll);
+    split_bf16(a1[i] * inv, hh, ll);
     out_hi[o + lane + 32] = hh;
     out_lo[o + lane + 32] = ll;
-    __syncwarp();  // sq / sc are reused by this warp's next query
   }
 }
 
@@ -625,7 +721,7 @@ int csmb_mimi_attention_planes(float* qkv, const float* freqs, uint16_t* out_hi,
   cudaStream_t st = (cudaStream_t)stream;
   k_mimi_rope_inplace<<<B * T, 256, 0, st>>>(qkv, freqs, T, H);
   CSMB_LAUNCH_CHECK();
-  const size_t smem = ((size_t)2 * (AT_QT + ctx - 1) * AT_PITCH + AT_WARPS * 64 + (size_t)AT_WARPS * ctx) * sizeof(float);
+  const size_t smem = ((size_t)2 * (AT_QT + ctx - 1) * AT_PITCH + AT_WARPS * AT_QW * 64 + (size_t)AT_WARPS * (ctx + AT_QW - 1) * AT_QW) * sizeof(float);
   CSMB_REQUIRE(smem <= 220 * 1024);
   CSMB_CUDA(cudaFuncSetAttribute(k_mimi_attn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_mimi_attn_tile<<<dim3(cdiv(T, AT_QT), H, B), AT_WARPS * 32, smem, st>>>(qkv, out_hi, out_lo, T, H, ctx);

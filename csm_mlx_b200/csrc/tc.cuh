@@ -76,6 +76,13 @@ __device__ __forceinline__ bool tc_mbar_wait(uint64_t* b, uint32_t parity, int* 
   }
   return true;
 }
+// Warp-collective form: lane 0 polls, the result is broadcast (a whole warp spinning on mbarrier.try_wait floods the shared
+// memory pipe that the TMA writes and the epilogue's staging traffic also need).  All 32 lanes must call it.
+__device__ __forceinline__ bool tc_mbar_wait_warp(uint64_t* b, uint32_t parity, int* err) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = tc_mbar_wait(b, parity, err) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
