@@ -4,14 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one process per GPU
     python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port on the host cores
 
-Workload at every N: BASELINE.json configs[1] — csm_1b bf16, batch 1, streaming generation of 10 s of audio
-(10 prompt rows + 125 frames), greedy, seeded random-init weights, one independent stream per GPU (weak scaling;
-utterances share nothing, so there is no data-path collective — NCCL only gathers the tokens and timings).
-A "step" = one whole utterance: prefill + 125 x (backbone step, 31-step depth loop, Mimi streaming decode).
+Workload at every N: BASELINE.json configs[3] — csm_1b bf16, 64 independent utterances of 10 s (8-16 prompt rows + 125
+frames each), greedy, seeded random-init weights, request-sharded over the N GPUs (utterance i -> rank i mod N; 64 / N per
+GPU; utterances share nothing, so there is no data-path collective — NCCL only gathers the tokens and timings).  A "step" =
+the whole 64-utterance job: continuous-batching engine (admission prefill + 125 frame-steps of the fused tcgen05 chain) +
+batched Mimi decode of every utterance.  The job is fixed, so the scaling is STRONG.
 
-  value  device-timed (CUDA events) with the prompt already resident in HBM and the audio left on the device
-  e2e    the same utterance through the public API (`stream_generate`), prompt rows in host memory, every frame's
-         1920 samples + 32 tokens copied back to pinned host memory inside the timed region
+  value  device-timed (CUDA events, max over ranks): prompts staged in HBM before the timed region, audio left on the device
+  e2e    the same job through the public serving API with host buffers: prompt rows submitted from host memory, every
+         frame's tokens copied to pinned host memory, the decoded audio copied back to the host, inside the timed region
+  roofline        the frame-step of the chain (the dominant kernel group: one CUDA-graph replay = 1 047 launches of this
+                  library) at this rank's batch: algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
+  other_configs   latency path (configs[1]: batch 1 streaming through the persistent frame kernel, with its own roofline,
+                  p50 / p90 inter-chunk latency and time to first chunk), configs[2] (context prefill), configs[4] (codec,
+                  128 x 60 s sharded over the ranks), batch sweep of the chain
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -50,16 +56,27 @@ import torch  # noqa: E402
 
 FRAME_S = 0.08
 SECONDS = 10.0
-WORKLOAD = "configs[1]: csm_1b bf16 batch=1 streaming generation, 10 s audio, single B200 (latency path)"
+N_REQ = 64
+WORKLOAD = "configs[3]: csm_1b bf16, 64 independent utterances x 10 s, request-sharded across the GPUs (continuous batching + Mimi decode)"
+LATENCY_WORKLOAD = "configs[1]: csm_1b bf16 batch=1 streaming generation, 10 s audio, single B200 (latency path)"
+# Sum of all 64 x 125 x 32 greedy tokens of the job.  The engine's numeric path does not depend on the batch size or on the
+# sharding (csm_mlx_b200/serving.py, "Batch invariance"), so this constant holds at every --gpus N; a different value means the
+# tokens changed.
+CFG4_TOKENS_CHECKSUM = 261764619  # profiles/r02_bench_1gpu.json; identical at --gpus 1, 2, 4, 8
 
 
-def lm_algorithmic_bytes(prompt_rows: int, frames: int) -> float:
-    """SURVEY.md §8(d) / BASELINE.md §4: bf16 weight bytes streamed per frame-step (independent of batch) plus the
-    per-sequence KV / embedding terms, averaged over the frames of this utterance."""
+def weight_bytes(proj_table: bool = False) -> float:
+    """SURVEY.md §8(d) / BASELINE.md §4: bf16 weight bytes streamed per frame-step (independent of the batch).  With the
+    projected-embedding table the chain no longer streams the projection matrix for depth steps 2..31 (30 x 4 194 304 B)."""
     w = 1_946_292_224 + 8_400_896 + 31 * 230_711_296
+    return w - (30 * 4_194_304 if proj_table else 0)
+
+
+def lm_algorithmic_bytes(prompt_rows: float, frames: int, batch: int = 1, proj_table: bool = False) -> float:
+    """Weights once per step for the whole batch + per-sequence KV / embedding terms, averaged over the utterance."""
     s_avg = prompt_rows + (frames - 1) / 2.0
     per_seq = 32_768 * 2 * s_avg + 32_768 * 2 + 63 * 4096  # fp32 KV here: 64 KiB per token read + one token written
-    return w + per_seq
+    return weight_bytes(proj_table) + batch * per_seq
 
 
 class ClockSampler:
@@ -109,6 +126,14 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def cfg4_prompt(i: int):
+    """Utterance i of configs[3]: BOS + (8 + i mod 9) seeded ids + EOS, speaker 0."""
+    from csm_mlx_b200 import tokenizers
+    from tests.workloads import prompt_ids
+
+    return tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0)
+
+
 # ------------------------------------------------------------------------------------------------- CPU arm
 def cpu_model() -> str:
     try:
@@ -120,42 +145,48 @@ def cpu_model() -> str:
     return "unknown"
 
 
-def oracle_sample(orc, mimi_w, prompt, frames: int) -> float:
-    """Seconds for prefill + `frames` greedy frames + streaming Mimi decode of them with the CPU oracle."""
+def oracle_utterance(orc, mimi_w, tok, mask, frames: int) -> float:
+    """Seconds for prefill + `frames` greedy frames + Mimi decode of them with the CPU oracle (one utterance of the job)."""
     from oracle import lm as olm, mimi as omimi
 
-    tok, mask = olm.text_rows(prompt)
     t0 = time.perf_counter()
-    toks = olm.generate_tokens(orc, tok, mask, frames)
-    sd = omimi.StreamingDecoder(mimi_w)
-    for f in range(toks.shape[0]):
-        sd.decode_step(toks[f].clamp(max=2047).reshape(1, 32, 1))
+    toks = olm.generate_tokens(orc, tok.long(), mask, frames)
+    omimi.decode(toks.t()[None].clamp(max=2047), mimi_w)
     return time.perf_counter() - t0
+
+
+def cpu_sample(frames: int, warm: bool = True):
+    """(audio-s/s, seconds, description) of the oracle port on all host cores over utterance 0 of the job."""
+    from csm_mlx_b200.random_init import random_csm_weights, random_mimi_weights
+    from oracle import lm as olm
+
+    torch.set_num_threads(os.cpu_count())
+    orc = olm.OracleCSM(olm.CSM_1B, random_csm_weights())
+    mimi_w = random_mimi_weights()
+    tok, mask = cfg4_prompt(0)
+    if warm:
+        oracle_utterance(orc, mimi_w, tok, mask, 1)
+    return orc, mimi_w, tok, mask
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from csm_mlx_b200.random_init import random_csm_weights, random_mimi_weights
-    from oracle import lm as olm
-    from tests.workloads import cfg1_prompt_ids
-
-    torch.set_num_threads(os.cpu_count())
-    orc = olm.OracleCSM(olm.CSM_1B, random_csm_weights())
-    mimi_w = random_mimi_weights()
     frames = args.ref_frames
+    orc, mimi_w, tok, mask = cpu_sample(frames, warm=False)
     for _ in range(args.warmup):
-        oracle_sample(orc, mimi_w, cfg1_prompt_ids(), 1)
-    times = [oracle_sample(orc, mimi_w, cfg1_prompt_ids(), frames) for _ in range(args.steps)]
+        oracle_utterance(orc, mimi_w, tok, mask, 1)
+    times = [oracle_utterance(orc, mimi_w, tok, mask, frames) for _ in range(args.steps)]
     t = statistics.mean(times)
     v = frames * FRAME_S / t
-    sample = f"prefill(10 rows) + {frames} greedy frames + Mimi streaming decode per step (of the 125-frame utterance)"
+    sample = (f"one utterance of the 64 (utterance 0: prefill of {int(tok.shape[0])} rows + {frames} greedy frames + Mimi decode) per "
+              f"step; the job is 64 such independent utterances, so its CPU throughput is this number")
     line = {
         "impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "sampling": "greedy",
+        "config": {"workload": WORKLOAD, "sample": sample, "sampling": "greedy", "frames_per_utterance": frames,
                    "note": "reference dependencies (mlx, mlx_lm, moshi_mlx) are not installable here; this is the "
                            "oracle port of the reference path in PyTorch CPU fp32 on all host cores"},
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": torch.get_num_threads(), "cpu_model": cpu_model(), "kind": "port", "sample": sample},
@@ -165,66 +196,129 @@ def run_reference(args):
     emit(line)
 
 
-# ------------------------------------------------------------------------------------------------- other configs
-def other_configs(model, mimi, dev):
-    """Informational, single GPU, short runs: BASELINE.json configs[2] (context), [3] (batch 64), [4] (codec)."""
+# ------------------------------------------------------------------------------------------------- helpers (GPU arm)
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def timed(dev, fn, n=1):
+    torch.cuda.synchronize(dev)
+    a, b = ev(), ev()
+    a.record()
+    r = None
+    for _ in range(n):
+        r = fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / n, r
+
+
+def chain_step_ms(model, dev, B: int, n: int = 10):
+    """CUDA-event time of one frame-step of the fused chain (graph replay) for B sequences in lock-step."""
+    from csm_mlx_b200.runtime import LMState, SamplerSpec
+
+    spec = SamplerSpec(temperature=0.0)
+    prompts = [cfg4_prompt(i) for i in range(B)]
+    st = LMState(model, B, max_len=64, row_invariant=True)
+    t_pre, _ = timed(dev, lambda: st.prefill([p[0] for p in prompts], [p[1] for p in prompts]))
+    frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
+    st.sample_c0(frame, spec)
+    st.depth_decode(frame, spec)
+    state = {"f": frame}
+    for _ in range(3):
+        state["f"] = st.decode_frame_graphed(state["f"], spec)
+
+    def step():
+        state["f"] = st.decode_frame_graphed(state["f"], spec)
+    t_step, _ = timed(dev, step, n)
+    st.check_status()
+    launches = st.graph_launches
+    del st
+    return t_step, t_pre, launches
+
+
+def latency_path(model, mimi, dev, lib, steps: int):
+    """BASELINE.json configs[1]: batch 1, 10 s, streaming, through the persistent frame kernel (round 1's headline)."""
+    from csm_mlx_b200 import generation, tokenizers
+    from csm_mlx_b200.runtime import LMState, SamplerSpec
+    from tests.workloads import cfg1_prompt_ids
+
+    ids = cfg1_prompt_ids()
+    tok, mask = tokenizers.tokenize_text_segment(ids, 0)
+    frames = int(SECONDS / FRAME_S)
+    spec = SamplerSpec(temperature=0.0)
+    st = LMState(model, 1, max_len=tok.shape[0] + frames + 1)
+    fused = st.fused_supported(spec) and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"
+    next_frame = (lambda fr: st.decode_frame_fused(fr, spec)) if fused else (lambda fr: st.decode_frame_graphed(fr, spec))
+
+    def e2e_step():
+        lat = []
+        t0 = time.perf_counter()
+        last = t0
+        n = 0
+        for _chunk in generation.stream_generate(model, ids, 0, [], max_audio_length_ms=SECONDS * 1000, temperature=0.0):
+            now = time.perf_counter()
+            lat.append(now - last)
+            last = now
+            n += 1
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, lat, n
+
+    for _ in range(2):
+        e2e_step()
+    times, lats, firsts = [], [], []
+    for _ in range(steps):
+        t, lat, n = e2e_step()
+        assert n == frames, n
+        times.append(t)
+        firsts.append(lat[0])
+        lats += lat[1:]
+    # the frame kernel alone
+    st.prefill([tok], [mask])
+    fr = torch.zeros((1, 32), device=dev, dtype=torch.int32)
+    st.sample_c0(fr, spec)
+    st.depth_decode(fr, spec)
+    state = {"f": fr}
+    for _ in range(3):
+        state["f"] = next_frame(state["f"])
+
+    def one():
+        state["f"] = next_frame(state["f"])
+    frame_ms, _ = timed(dev, one, 60)
+    st.check_status()
+    alg = lm_algorithmic_bytes(int(tok.shape[0]), frames)
+    lats_ms = sorted(1e3 * x for x in lats)
+    pct = lambda p: lats_ms[min(len(lats_ms) - 1, int(p * len(lats_ms)))] if lats_ms else None
+    t_e2e = statistics.mean(times)
+    return {"workload": LATENCY_WORKLOAD, "e2e_audio_s_per_s": frames * FRAME_S / t_e2e, "e2e_ms": 1e3 * t_e2e,
+            "api": "csm_mlx.stream_generate (host prompt, every chunk + tokens copied to pinned host memory)",
+            "latency_ms": {"p50": pct(0.5), "p90": pct(0.9), "first_chunk": 1e3 * statistics.median(firsts),
+                           "what": "time between successive stream_generate chunks on the host; first_chunk = call -> first "
+                                   "1 920 samples on the host (prompt assembly + prefill + first frame + the one-frame lookahead + codec step)"},
+            "roofline": {"bound": "hbm", "kernel": "csmb::k_frame (persistent whole-frame kernel)" if fused else "per-op graph",
+                         "ms_per_frame": frame_ms, "algorithmic_bytes_per_frame": alg, "achieved": alg / (frame_ms * 1e-3) / 1e9,
+                         "unit": "GB/s"}}
+
+
+def context_config(model, mimi, dev):
+    """BASELINE.json configs[2]: 2-segment context (2 x 5 s synthetic audio -> Mimi encode) + new text -> prefill -> frames."""
     from csm_mlx_b200 import Segment, generation, tokenizers
     from csm_mlx_b200.runtime import LMState, SamplerSpec
-    from tests.workloads import prompt_ids, synthetic_audio
+    from tests.workloads import synthetic_audio
 
-    out = {}
     spec = SamplerSpec(temperature=0.0)
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def timed(fn, n=1):
-        torch.cuda.synchronize(dev)
-        a, b = ev(), ev()
-        a.record()
-        for _ in range(n):
-            r = fn()
-        b.record()
-        torch.cuda.synchronize(dev)
-        return a.elapsed_time(b) / n, r
-
-    # configs[3]: 64 independent utterances in lock-step on one GPU (request batching; tcgen05 linears)
-    def batch_step(B):
-        prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in range(B)]
-        st = LMState(model, B, max_len=64)
-        t_pre, _ = timed(lambda: st.prefill([p[0] for p in prompts], [p[1] for p in prompts]))
-        frame = torch.zeros((B, 32), device=dev, dtype=torch.int32)
-        st.sample_c0(frame, spec)
-        st.depth_decode(frame, spec)
-        state = {"f": frame}
-        for _ in range(3):
-            state["f"] = st.decode_frame_graphed(state["f"], spec)
-
-        def step():
-            state["f"] = st.decode_frame_graphed(state["f"], spec)
-        t_step, _ = timed(step, 10)
-        st.check_status()
-        del st
-        return t_pre, t_step
-
-    B = 64
-    t_pre, t_step = batch_step(B)
-    out["batch64_one_gpu"] = {"audio_s_per_s": B * FRAME_S / (t_step / 1e3), "ms_per_frame_step": t_step, "prefill_ms": t_pre,
-                              "roofline_frac": lm_algorithmic_bytes(12, 20) / (t_step / 1e3) / 1e9 / 6557.8,
-                              "note": "LM frames only: CUDA graph of the fused kernel chain (csrc/batch_frame.cu: one tcgen05 launch per Linear, SwiGLU in the gate|up epilogue, fused partial-sum kernels, programmatic dependent launch); 64 frames per step"}
-    # the same chain at other batch sizes: every kernel is latency-bound, so a step costs almost the same from 2 to 256 sequences
-    sweep = {}
-    for Bs in (2, 8, 128, 256):
-        _, t = batch_step(Bs)
-        sweep[str(Bs)] = {"ms_per_frame_step": t, "audio_s_per_s": Bs * FRAME_S / (t / 1e3)}
-    out["batch_sweep_one_gpu"] = sweep
-    # configs[2]: 2-segment context (2 x 5 s synthetic audio -> Mimi encode) + new text -> 164-row prefill -> frames
     tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
     try:
         clips = [synthetic_audio(11, 5.0), synthetic_audio(12, 5.0)]
-        t_enc, _ = timed(lambda: [mimi.encode(c[None, None].to(dev)) for c in clips])
+        [mimi.encode(c[None, None].to(dev)) for c in clips]
+        t_enc, _ = timed(dev, lambda: [mimi.encode(c[None, None].to(dev)) for c in clips])
         segs = [Segment(i, "context sentence number %d" % i, clips[i]) for i in range(2)]
         prompt = generation._build_prompt(model, "and now the answer", 0, segs)
-        st = LMState(model, 1, max_len=int(prompt[0].shape[0]) + 40)
-        t_pre, _ = timed(lambda: st.prefill([prompt[0]], [prompt[1]]))
+        rows = int(prompt[0].shape[0])
+        st = LMState(model, 1, max_len=rows + 40)
+        st.prefill([prompt[0]], [prompt[1]])
+        st.reset()
+        t_pre, _ = timed(dev, lambda: st.prefill([prompt[0]], [prompt[1]]))
         frame = torch.zeros((1, 32), device=dev, dtype=torch.int32)
         st.sample_c0(frame, spec)
         st.depth_decode(frame, spec)
@@ -234,71 +328,51 @@ def other_configs(model, mimi, dev):
             state["f"] = st.decode_frame_fused(state["f"], spec)
         for _ in range(3):
             step1()
-        t_f, _ = timed(step1, 20)
+        t_f, _ = timed(dev, step1, 20)
         st.check_status()
-        out["context_2x5s"] = {"prompt_rows": int(prompt[0].shape[0]), "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
-                               "ms_per_frame": t_f, "note": "frame kernel with 2-chunk attention (S > 128)"}
+        return {"prompt_rows": rows, "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
+                "prefill_tflops": 2 * 973.1e6 * rows / (t_pre * 1e-3) / 1e12, "ms_per_frame": t_f,
+                "note": "prefill = host staging + backbone over all prompt rows (tcgen05 linears) + c0 head; frame kernel with 2-chunk attention (S > 128)"}
     finally:
         tokenizers.set_text_tokenizer(None)
-    # configs[4] scaled down: 4 clips x 60 s through the codec (encode -> codes -> decode)
-    clips = torch.stack([synthetic_audio(100 + i, 60.0) for i in range(4)])[:, None].to(dev)
-    mimi.decode(mimi.encode(clips))  # warm-up at the measured shapes: the buffers come from the caching allocator afterwards
-    t_e, codes = timed(lambda: mimi.encode(clips), 2)
-    t_d, audio = timed(lambda: mimi.decode(codes), 2)
-    out["mimi_codec_4x60s"] = {"encode_audio_s_per_s": 240.0 / (t_e / 1e3), "decode_audio_s_per_s": 240.0 / (t_d / 1e3),
-                               "frames": int(codes.shape[2]), "note": "fp32 CUDA-core strided-row GEMMs, one GPU"}
-    return out
 
 
-def cfg4_sharded(model, dev, world, rank, barrier, max_over_ranks):
-    """BASELINE.json configs[3]: 64 independent 10 s utterances; request i -> rank i mod N (no collective on the data
-    path), continuous batching over the rank's slots (csm_mlx_b200/serving.py), Mimi decode of every utterance, then
-    one NCCL gather of the ragged token tensors to rank 0.  Called by every rank; returns the record on rank 0."""
-    from csm_mlx_b200 import serving, tokenizers
-    from csm_mlx_b200.sharding import gather_ragged, shard_indices
-    from tests.workloads import prompt_ids
+def codec_config(mimi, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: 128 clips x 60 s through the codec (encode -> codes -> decode), clip i -> rank i mod N."""
+    from csm_mlx_b200.sharding import shard_indices
+    from tests.workloads import synthetic_audio
 
-    n_req = 64
-    mine = shard_indices(n_req, rank, world)
-    frames = int(SECONDS / FRAME_S)
-    prompts = {i: tokenizers.tokenize_text_segment(prompt_ids(21 + i, 8 + i % 9), 0) for i in mine}
-    eng = serving.Engine(model, max_batch=len(mine), max_len=32 + frames + 2)
-
-    def run():
-        rids = [eng.submit_prompt(prompts[i][0], prompts[i][1], frames) for i in mine]
-        eng.run()
-        toks = [eng.tokens(r) for r in rids]
-        audio = eng.audio(rids)
-        torch.cuda.synchronize(dev)
-        return toks, audio
-
-    run()  # warm-up: graph capture, codec buffers
+    n_clips, secs = 128, 60.0
+    mine = shard_indices(n_clips, rank, world)
+    clips = torch.stack([synthetic_audio(100 + i, secs) for i in mine])[:, None].to(dev)
+    warm = clips[:2]
+    mimi.decode(mimi.encode(warm))   # warm-up at the measured pass shape: buffers come from the caching allocator afterwards
     barrier()
-    t0 = time.perf_counter()
-    toks, audio = run()
-    t = max_over_ranks(time.perf_counter() - t0)
-    steps = eng.steps
-    gathered = gather_ragged([x.to(dev) for x in toks], n_req, device=dev)
+    t_e, codes = timed(dev, lambda: mimi.encode(clips))
+    t_d, audio = timed(dev, lambda: mimi.decode(codes))
+    t_e, t_d = max_over_ranks(t_e / 1e3), max_over_ranks(t_d / 1e3)
+    total = n_clips * secs
+    frames = int(codes.shape[2])
+    csum = int(codes.long().sum())
+    del clips, audio
     if rank != 0:
         return None
-    total_frames = sum(int(x.shape[0]) for x in gathered)
-    return {"requests": n_req, "per_gpu": len(mine), "frames_total": total_frames,
-            "audio_s_per_s": total_frames * FRAME_S / t, "seconds": t,
-            "tokens_checksum": int(sum(int(x.long().sum()) for x in gathered)),
-            "note": "wall clock over submit -> continuous-batching LM frames -> batched Mimi decode, max over ranks; "
-                    f"{steps} engine steps on rank 0 since start; strong scaling of a fixed 64-utterance job (latency-bound per step)"}
+    return {"clips": n_clips, "seconds_per_clip": secs, "clips_per_gpu": len(mine), "frames": frames,
+            "encode_audio_s_per_s": total / t_e, "decode_audio_s_per_s": total / t_d,
+            "encode_tflops": 0.46e9 * 12.5 * total / t_e / 1e12, "decode_tflops": 0.43e9 * 12.5 * total / t_d / 1e12,
+            "rank0_codes_checksum": csum,
+            "note": "tensor-core path (csrc/mimi_tc.cu: persistent tcgen05 GEMM on bf16 hi+lo planes, three MMAs per K step); "
+                    "TFLOP/s = algorithmic fp32-equivalent FLOPs (BASELINE.md §4) / time; max over ranks"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
 
-    from csm_mlx_b200 import CSM, _lib, csm_1b, generation, tokenizers
+    from csm_mlx_b200 import CSM, _lib, csm_1b, serving, tokenizers
     from csm_mlx_b200.mimi import Mimi
     from csm_mlx_b200.random_init import random_csm_weights, random_mimi_weights
-    from csm_mlx_b200.runtime import LMState, SamplerSpec
-    from csm_mlx_b200.sharding import gather_ragged
-    from tests.workloads import cfg1_prompt_ids, prompt_ids
+    from csm_mlx_b200.sharding import gather_ragged, shard_indices
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -312,95 +386,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
-    model = CSM(csm_1b(), device=dev).load_weights(random_csm_weights())
-    mimi = Mimi(32, device=dev).load_pytorch_weights(random_mimi_weights())
-    tokenizers.set_audio_tokenizer(mimi)
-    ids = cfg1_prompt_ids() if rank == 0 else prompt_ids(7 + rank, 8)  # an independent utterance per GPU
-    tok, mask = tokenizers.tokenize_text_segment(ids, 0)
-    frames = int(SECONDS / FRAME_S)
-    spec = SamplerSpec(temperature=0.0)
-    ncb = 32
-
-    # ---- device-resident step ---------------------------------------------------------------------
-    audio_dev = torch.empty((frames, 1920), device=dev, dtype=torch.float32)
-    tokens_dev = torch.empty((frames, ncb), device=dev, dtype=torch.int32)
-    launches = {"step": 0}
-
-    st = LMState(model, 1, max_len=tok.shape[0] + frames + 1)
-    codec = mimi.new_decode_stream(1)
-    lane = generation._CodecLane(codec, dev)   # the product's own overlap of codec(t) with LM(t+1)
-    fused = st.fused_supported(spec) and os.environ.get("CSMB_DISABLE_FUSED", "0") != "1"
-    next_frame = (lambda fr: st.decode_frame_fused(fr, spec)) if fused else (lambda fr: st.decode_frame_graphed(fr, spec))
-
-    def device_step(timed: bool):
-        st.reset()
-        codec.reset()
-        staged = st.stage_prefill([tok], [mask])          # prompt resident in HBM before the timed region
-        frame = torch.zeros((1, ncb), device=dev, dtype=torch.int32)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0 = lib.csmb_debug_launch_count()
-        e0.record()
-        st.run_prefill(staged)
-        if fused:
-            frame = st.first_frame_fused(spec)
-        else:
-            st.sample_c0(frame, spec)
-            st.depth_decode(frame, spec)
-        for f in range(frames):
-            audio = lane.step(frame)
-            with torch.cuda.stream(lane.stream):
-                tokens_dev[f].copy_(frame[0])
-                audio_dev[f].copy_(audio.reshape(-1))
-            if f + 1 < frames:
-                frame = next_frame(frame)
-        lane.join()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        launches["eager"] = lib.csmb_debug_launch_count() - c0
-        return e0.elapsed_time(e1) / 1e3, st, codec
-
-    # ---- e2e step (public API, host buffers) --------------------------------------------------------
-    def e2e_step():
-        lat = []
-        t0 = time.perf_counter()
-        last = t0
-        n = 0
-        for chunk in generation.stream_generate(model, ids, 0, [], max_audio_length_ms=SECONDS * 1000, temperature=0.0):
-            now = time.perf_counter()
-            lat.append(now - last)
-            last = now
-            n += 1
-        torch.cuda.synchronize(dev)
-        return time.perf_counter() - t0, lat, n
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        device_step(False)
-    barrier()
-    clocks = ClockSampler(local).start()
-    dev_times = []
-    for _ in range(args.steps):
-        barrier()
-        t, _, _ = device_step(True)
-        dev_times.append(t)
-    barrier()
-    clk = clocks.stop()
-
-    for _ in range(max(1, args.warmup - 1)):
-        e2e_step()
-    e2e_times, lats = [], []
-    for _ in range(args.steps):
-        barrier()
-        t, lat, n = e2e_step()
-        assert n == frames, n
-        e2e_times.append(t)
-        lats += lat[1:]  # the first chunk carries the prefill
-    barrier()
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -409,92 +398,138 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
+    model = CSM(csm_1b(), device=dev).load_weights(random_csm_weights())
+    mimi = Mimi(32, device=dev).load_pytorch_weights(random_mimi_weights())
+    tokenizers.set_audio_tokenizer(mimi)
+    frames = int(SECONDS / FRAME_S)
+    mine = shard_indices(N_REQ, rank, world)
+    prompts = {i: cfg4_prompt(i) for i in mine}
+    eng = serving.Engine(model, max_batch=max(1, len(mine)), max_len=32 + frames + 2)
+    has_table = model.proj_table() is not None and os.environ.get("CSMB_NO_PROJ_TABLE", "0") != "1"
+
+    # ---- one job.  device=True: CUDA-event timed, audio stays in HBM; device=False: wall clock, host buffers in and out
+    def job(device: bool):
+        torch.cuda.synchronize(dev)
+        c0 = lib.csmb_debug_launch_count()
+        e0, e1 = ev(), ev()
+        t0 = time.perf_counter()
+        e0.record()
+        rids = [eng.submit_prompt(prompts[i][0], prompts[i][1], frames) for i in mine]
+        steps0 = eng.steps
+        eng.run()
+        audio = eng.audio(rids, to_host=not device)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        toks = [eng.tokens(r) for r in rids]
+        eager = int(lib.csmb_debug_launch_count() - c0)
+        n_steps = eng.steps - steps0
+        return {"event_s": e0.elapsed_time(e1) / 1e3, "wall_s": wall, "tokens": toks, "audio": audio, "eager_launches": eager,
+                "engine_steps": n_steps}
+
+    for _ in range(max(1, args.warmup)):
+        job(True)
+    barrier()
+    clocks = ClockSampler(local).start()
+    dev_times, last = [], None
+    for _ in range(args.steps):
+        barrier()
+        last = job(True)
+        dev_times.append(last["event_s"])
+    barrier()
+    clk = clocks.stop()
+    job(False)
+    e2e_times = []
+    for _ in range(args.steps):
+        barrier()
+        r = job(False)
+        e2e_times.append(r["wall_s"])
+        last_e2e = r
+    barrier()
     t_dev = max_over_ranks(statistics.mean(dev_times))
     t_e2e = max_over_ranks(statistics.mean(e2e_times))
-    # gather every rank's tokens to rank 0 over NCCL (the only use of the interconnect on this path)
-    all_tokens = gather_ragged([tokens_dev.clone()], world, device=dev)
+    # the only use of the interconnect on this path: gather every rank's tokens to rank 0 over NCCL
+    gathered = gather_ragged([x.to(dev) for x in last["tokens"]], N_REQ, device=dev)
+    d2h_local = sum(int(t.numel()) * 4 for t in last_e2e["tokens"]) + sum(int(a.numel()) * 4 for a in last_e2e["audio"])
+    h2d_local = sum(int(prompts[i][0].numel()) * 4 + int(prompts[i][1].numel()) + 4 * (2 * int(prompts[i][0].shape[0]) + 3) for i in mine) \
+        + sum(int(t.numel()) * 4 for t in last_e2e["tokens"])   # prompt rows + maps at admission; codes of the batched Mimi decode
+    io = torch.tensor([float(h2d_local), float(d2h_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(io)
 
-    cfg4 = None
+    # ---- the dominant kernel group alone: one frame-step of the chain at this rank's batch (CUDA events, graph replay)
+    B_rank = max(1, len(mine))
+    step_ms, _, graph_launches = chain_step_ms(model, dev, B_rank)
+    step_ms = max_over_ranks(step_ms)
+
+    other = None
     if not args.no_extras:
-        cfg4 = cfg4_sharded(model, dev, world, rank, barrier, max_over_ranks)
+        other = {}
+        other["cfg5_codec_128x60s_sharded"] = codec_config(mimi, dev, world, rank, barrier, max_over_ranks)
+        if rank == 0 and world == 1:
+            other["latency_path"] = latency_path(model, mimi, dev, lib, args.steps)
+            other["context_2x5s"] = context_config(model, mimi, dev)
+            sweep = {}
+            for Bs in (1, 8, 16, 32, 128, 256):
+                t, _, _ = chain_step_ms(model, dev, Bs, 6)
+                sweep[str(Bs)] = {"ms_per_frame_step": t, "audio_s_per_s": Bs * FRAME_S / (t / 1e3),
+                                  "roofline_frac": lm_algorithmic_bytes(12, 20, Bs, has_table) / (t / 1e3) / 1e9 / 6557.8}
+            other["chain_batch_sweep_one_gpu"] = sweep
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    audio_s = frames * FRAME_S * world
-    alg = lm_algorithmic_bytes(int(tok.shape[0]), frames)
+    total_frames = sum(int(x.shape[0]) for x in gathered)
+    audio_s = total_frames * FRAME_S
+    checksum = int(sum(int(x.long().sum()) for x in gathered))
+    if CFG4_TOKENS_CHECKSUM is not None and os.environ.get("CSMB_BENCH_NO_CHECKSUM", "0") != "1":
+        assert checksum == CFG4_TOKENS_CHECKSUM, (checksum, CFG4_TOKENS_CHECKSUM, "greedy tokens of the job changed")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel(s): the LM frame (backbone step + depth loop).  Time it alone, device events, graph replay.
-    st.reset()
-    st.prefill([tok], [mask])
-    fr = torch.zeros((1, ncb), device=dev, dtype=torch.int32)
-    st.sample_c0(fr, spec)
-    st.depth_decode(fr, spec)
-    for _ in range(3):
-        fr = next_frame(fr)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nf = 60
-    e0.record()
-    for _ in range(nf):
-        fr = next_frame(fr)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    frame_ms = e0.elapsed_time(e1) / nf
-    achieved = alg / (frame_ms * 1e-3) / 1e9
+    alg = lm_algorithmic_bytes(12.0, frames, B_rank, has_table)
+    achieved = alg / (step_ms * 1e-3) / 1e9
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import lm as olm
-
-        torch.set_num_threads(os.cpu_count())
-        orc = olm.OracleCSM(olm.CSM_1B, random_csm_weights())
-        mw = random_mimi_weights()
-        oracle_sample(orc, mw, cfg1_prompt_ids(), 1)
-        nfr = args.ref_frames
-        tc = oracle_sample(orc, mw, cfg1_prompt_ids(), nfr)
+        orc, mimi_w, tok0, mask0 = cpu_sample(args.ref_frames)
+        nfr = args.cpu_frames
+        tc = oracle_utterance(orc, mimi_w, tok0, mask0, nfr)
         cpu = {"value": nfr * FRAME_S / tc, "unit": "audio-s/s", "cores": torch.get_num_threads(), "cpu_model": cpu_model(), "kind": "port",
-               "sample": f"prefill(10 rows) + {nfr} greedy frames + Mimi streaming decode, oracle PyTorch-CPU fp32 "
-                         f"({tc:.2f} s)"}
+               "sample": f"utterance 0 of the 64: prefill ({int(tok0.shape[0])} rows) + {nfr} greedy frames + Mimi decode, oracle PyTorch-CPU fp32 "
+                         f"on all host cores ({tc:.1f} s); `--impl reference` runs the full 125 frames"}
 
-    other = None
-    if not args.no_extras:
-        other = other_configs(model, mimi, dev) if world == 1 else {}
-        other["cfg4_64x10s_request_sharded"] = cfg4
-
-    lats_ms = sorted(1e3 * x for x in lats)
-    pct = lambda p: lats_ms[min(len(lats_ms) - 1, int(p * len(lats_ms)))] if lats_ms else None
-    d2h = frames * (1920 * 4 + ncb * 4)
-    h2d = int(tok.numel() * 4 + mask.numel() + 4 * (3 * tok.shape[0] + 2))
     line = {
         "metric": "audio_seconds_per_second", "value": audio_s / t_dev, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames": frames, "prompt_rows": int(tok.shape[0]), "sampling": "greedy",
-                   "weights": "bf16 in HBM (seeded random init, 3.1 GB)", "activations": "fp32, fp32 accumulation",
-                   "parallelism": f"replicas: 1 independent stream per GPU x {world}",
-                   "l2": "inputs larger than L2: 9.1 GB of weights streamed per frame-step vs 126 MB L2"},
-        "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * t_e2e, "api": "csm_mlx.stream_generate"},
-        "latency_ms": {"p50": pct(0.5), "p90": pct(0.9), "what": "time between successive stream_generate chunks on the host"},
-        "gpu_launches": int(launches.get("eager", 0)) + 0,
-        "gpu_launches_note": "kernels of libcsm_b200 enqueued per device step: prefill + first frame per-op, then 1 persistent k_frame per frame; "
-                             "the Mimi streaming step replays a CUDA graph of ~110 captured kernels per frame on top",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "requests": N_REQ, "per_gpu": len(mine), "frames_per_utterance": frames,
+                   "frames_total": total_frames, "prompt_rows": "10..18 (8 + i mod 9 ids + BOS + EOS)", "sampling": "greedy",
+                   "weights": "bf16 in HBM (seeded random init, 3.1 GB per GPU, replicated)", "activations": "fp32 accumulation (bf16 hi+lo operand planes on the tensor cores)",
+                   "parallelism": f"request sharding: utterance i -> rank i mod {world}, one continuous-batching engine per GPU, no data-path collective",
+                   "l2": "inputs larger than L2: 9.0 GB of weights streamed per frame-step vs 126 MB L2",
+                   "engine_steps_per_job_rank0": last["engine_steps"]},
+        "e2e": {"value": audio_s / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
+                "ms_per_step": 1e3 * t_e2e, "api": "csm_mlx_b200.serving.Engine.submit_prompt / run / tokens / audio (host tensors in, host tensors out)"},
+        "gpu_launches": int(last["eager_launches"] + last["engine_steps"] * graph_launches),
+        "gpu_launches_note": f"rank 0, one job: {last['engine_steps']} engine steps x {graph_launches} kernels of libcsm_b200 per CUDA-graph replay of the "
+                             f"chain + {last['eager_launches']} eagerly launched (admission prefill, Mimi decode)",
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 9.1205e9 if fused else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_frame, profiles/r01_frame_kernel_ncu.md" if fused else None,
-                     "kernel": "csmb::k_frame (persistent whole-frame kernel)" if fused else "LM frame as a CUDA graph of per-op kernels",
-                     "ms_per_frame": frame_ms,
-                     "algorithmic_bytes_per_frame": alg, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+                     "traffic": None,
+                     "kernel": f"frame-step of the fused chain (csrc/batch_frame.cu) at {B_rank} sequences: one CUDA-graph replay = {graph_launches} launches "
+                               "(csmb::k_gemm_part_t tcgen05 linears + fused element-wise kernels)",
+                     "ms_per_frame_step": step_ms, "algorithmic_bytes_per_frame_step": alg,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "note": "bytes = bf16 weights streamed once per step for the whole batch (projection matrix only in depth step 1: "
+                             "projected-embedding table) + per-sequence KV / embedding terms; traffic: see profiles/r02_chain_ncu.md"},
         "cpu_baseline": cpu,
-        "tokens_checksum": int(sum(int(t.long().sum()) for t in all_tokens)) if all_tokens else None,
+        "tokens_checksum": checksum,
+        "tokens_checksum_expected": CFG4_TOKENS_CHECKSUM,
         "other_configs": other,
     }
     emit(line)
@@ -508,7 +543,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=125, help="frames per step of the CPU arm (125 = the job's full utterance)")
+    ap.add_argument("--cpu-frames", type=int, default=25, help="frames of the cpu_baseline sample inside the CUDA arm's run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational measurements of the other BASELINE configs")
     args = ap.parse_args()

@@ -81,6 +81,7 @@ class LMState:
         self.frame_status: Optional[torch.Tensor] = None
         self._frame_opts: Optional[_lib.FrameOpts] = None
         self._graph_key = None
+        self.graph_launches = 0
         if self._chain_possible():
             self._prepare_chain()
 
@@ -343,8 +344,10 @@ class LMState:
             pos_save, host_save = self.pos.clone(), list(self.pos_host)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().csmb_debug_launch_count()
             with torch.cuda.graph(g):
                 self.decode_frame(self._g_prev, self._g_out, sampler)
+            self.graph_launches = int(_lib.lib().csmb_debug_launch_count() - n0)   # kernels of this library per replay
             self.pos.copy_(pos_save)  # capture does not execute, but keep host/device views in lock-step
             self.pos_host = host_save
             self._graph, self._graph_key = g, key

@@ -286,8 +286,9 @@ class Engine:
         r = self.finished[rid]
         return torch.stack(r.frames) if r.frames else torch.zeros((0, self.ncb), dtype=torch.int32)
 
-    def audio(self, rids: Sequence[int]) -> List[torch.Tensor]:
-        """Mimi decode (tokenizers.py:148-150) of finished requests, batched; 1-D float32 CPU tensors."""
+    def audio(self, rids: Sequence[int], to_host: bool = True) -> List[torch.Tensor]:
+        """Mimi decode (tokenizers.py:148-150) of finished requests, batched; 1-D float32 tensors (on the host by default,
+        views of one device tensor with ``to_host=False``)."""
         mimi = get_audio_tokenizer(self.ncb)
         toks = [self.tokens(r) for r in rids]
         fmax = max((int(t.shape[0]) for t in toks), default=0)
@@ -296,5 +297,8 @@ class Engine:
         codes = torch.zeros((len(toks), self.ncb, fmax), dtype=torch.int32)
         for i, t in enumerate(toks):
             codes[i, :, : t.shape[0]] = t.t()
-        audio = mimi.decode(codes.to(self.model.device)).to("cpu")
-        return [audio[i, 0, : 1920 * int(t.shape[0])].clone() for i, t in enumerate(toks)]
+        audio = mimi.decode(codes.to(self.model.device))
+        if to_host:
+            audio = audio.to("cpu")
+            return [audio[i, 0, : 1920 * int(t.shape[0])].clone() for i, t in enumerate(toks)]
+        return [audio[i, 0, : 1920 * int(t.shape[0])] for i, t in enumerate(toks)]

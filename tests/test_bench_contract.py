@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_exactly_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-frames", "2"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.splitlines()
@@ -18,7 +19,8 @@ def test_reference_arm_prints_exactly_one_json_line():
     assert rec["impl"] == "reference" and rec["metric"] == "audio_seconds_per_second" and rec["unit"] == "audio-s/s"
     assert rec["higher_is_better"] is True and rec["n_gpus"] == 1 and rec["steps"] == 1 and rec["warmup"] == 0
     assert rec["value"] > 0 and rec["ms_per_step"] > 0 and rec["vs_baseline"] is None
-    assert rec["config"]["workload"].startswith("configs[1]")
+    assert rec["config"]["workload"].startswith("configs[3]") and rec["scaling"] == "strong"
+    assert rec["config"]["frames_per_utterance"] == 2
     cb = rec["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == rec["value"] and cb["sample"]
     e2e = rec["e2e"]
@@ -30,7 +32,7 @@ def test_reference_arm_under_torchrun_prints_on_rank0_only():
     other ranks exit 0 without work."""
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--steps", "1", "--warmup", "0", "--ref-frames", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.splitlines()
     assert len(lines) == 1, lines[:3]
