@@ -67,8 +67,8 @@ def time_graph_steps(st, prev, n=10):
 def _chain():
     """Frame-step of the fused chain (CUDA-graph replay) over batch size x {projected-embedding table} x {smem budget}."""
     base = {}
-    for B in (1, 2, 8, 16, 32, 64, 128):
-        for tab, smem in ((0, 0), (1, 0), (1, 96), (1, 64)):
+    for B in (int(x) for x in os.environ.get("R2_BATCHES", "1,2,8,16,32,64,128").split(",")):
+        for tab, smem in (((0, 0), (1, 0), (1, 96)) if os.environ.get("R2_FULL") else ((1, 0),)):
             setenv(CSMB_NO_PROJ_TABLE=None if tab else 1, CSMB_CHAIN_SMEM_KB=smem or None)
             st, frame = warm_state(B, row_invariant=(B == 1))
             ms, last = time_graph_steps(st, frame)
