@@ -330,9 +330,31 @@ def context_config(model, mimi, dev):
             step1()
         t_f, _ = timed(dev, step1, 20)
         st.check_status()
+        del st
+        # near-maximum context: a 2 030-row prompt (text + audio rows), GPU time of the prompt pass with staged inputs
+        from oracle import lm as olm
+        from tests.workloads import prompt_ids
+
+        gen = torch.Generator().manual_seed(77)
+        t1 = olm.text_rows(prompt_ids(9, 10))
+        a1 = olm.audio_rows(torch.randint(0, 2048, (32, 2017), generator=gen))
+        tok_l, mask_l = torch.cat([t1[0], a1[0]]).int(), torch.cat([t1[1], a1[1]])
+        stl = LMState(model, 1, max_len=int(tok_l.shape[0]) + 8)
+        staged = stl.stage_prefill([tok_l], [mask_l])
+        stl.run_prefill(staged)
+
+        def long_pass():
+            stl.reset()
+            stl.run_prefill(staged)
+        t_long, _ = timed(dev, long_pass, 2)
+        stl.check_status()
+        rows_l = int(tok_l.shape[0])
         return {"prompt_rows": rows, "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
                 "prefill_tflops": 2 * 973.1e6 * rows / (t_pre * 1e-3) / 1e12, "ms_per_frame": t_f,
-                "note": "prefill = host staging + backbone over all prompt rows (tcgen05 linears) + c0 head; frame kernel with 2-chunk attention (S > 128)"}
+                "prefill_long": {"prompt_rows": rows_l, "ms": t_long, "tflops": 2 * 973.1e6 * rows_l / (t_long * 1e-3) / 1e12},
+                "note": "prefill = host staging + backbone over all prompt rows on the chain's kernels (csmb_prefill_fast: one tcgen05 launch per "
+                        "Linear, fused norms, tiled attention) + c0 head; TFLOP/s = 2 x 973.1 M x rows / time (fp32-equivalent: every "
+                        "product runs twice, bf16 hi + lo); frame kernel with 2-chunk attention (S > 128)"}
     finally:
         tokenizers.set_text_tokenizer(None)
 

@@ -20,6 +20,7 @@
 // Arithmetic is that of the per-op path (fp32 accumulation, fixed summation orders): parity tests compare both with
 // the batch-1 kernels and the oracle token for token.
 #include <math.h>
+#include <stdlib.h>
 
 #include <utility>
 
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(256) k_prefill_embed_norm(const int32_t* __res
 
 // One block per prompt row: sum the qkv partials, rotate q and k (attention.py:119-177) at the row's position, keep q
 // (fp32, [R][H*HD]) and append k / v to the paged cache of the row's sequence (attention.py:236-237).
-__global__ void __launch_bounds__(256) k_prefill_rope_append(PartIn qkv, const float* __restrict__ rope, float* __restrict__ pool,
+__global__ void __launch_bounds__(512) k_prefill_rope_append(PartIn qkv, const float* __restrict__ rope, float* __restrict__ pool,
                                                              const int32_t* __restrict__ block_table, int max_pages,
                                                              const int32_t* __restrict__ row_seq,
                                                              const int32_t* __restrict__ row_pos, int H, int Hkv, int HD,
@@ -573,7 +574,10 @@ __global__ void __launch_bounds__(256) k_prefill_rope_append(PartIn qkv, const f
   const int page = block_table[(size_t)seq * max_pages + pos / CSMB_PAGE];
   float* kbase = pool + (size_t)page * page_stride + (size_t)(pos % CSMB_PAGE) * HD;
   const int total = (H + 2 * Hkv) * half;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+  // one (head, pair) per thread (gridDim.y blocks per row): a row's partial loads are all in flight at once
+  {
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
     const int head = idx / half, pr = idx % half;
     const float2 v = part_sum2(qkv, (size_t)r * qkv.ld + (size_t)head * HD + 2 * pr);
     if (head < H + Hkv) {
@@ -665,6 +669,200 @@ __global__ void __launch_bounds__(256) k_prefill_attn(const float* __restrict__ 
     split_bf16(acc[ii] * inv, hh, ll);
     out_hi[o + lane + 32 * ii] = hh;
     out_lo[o + lane + 32 * ii] = ll;
+  }
+}
+
+// Prompt attention (attention.py:242-249 with T > 1), one block per (tile of PA_QT consecutive prompt rows, kv head).  The G
+// query heads that share the kv head are handled together (GQA: mx.repeat, attention.py:242-245): a warp takes a row and
+// computes its G heads at once, so a staged key / value row is used G times.  Keys and values of the tile's sequence are staged
+// in shared memory in chunks of PA_KC positions (the per-row kernel re-read them from L2 for every row: O(T^2) traffic) with
+// an online softmax across chunks (running max / sum / accumulator per (row, head)).  A tile that spans two sequences
+// processes them one after the other.  Output: bf16 hi/lo planes of the o-projection's operand.
+constexpr int PA_QT = 32, PA_KC = 256, PA_WARPS = 8, PA_G = 4;
+template <int HD>
+__global__ void __launch_bounds__(PA_WARPS * 32) k_prefill_attn_tile(const float* __restrict__ q, const float* __restrict__ pool,
+                                                                     const int32_t* __restrict__ block_table, int max_pages,
+                                                                     const int32_t* __restrict__ row_seq,
+                                                                     const int32_t* __restrict__ row_pos, int R, int H, int Hkv,
+                                                                     uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  static_assert(HD == 64, "two output dims per lane");
+  constexpr int PITCH = HD + 4;
+  extern __shared__ float pa_sm[];
+  float* sK = pa_sm;
+  float* sV = sK + (size_t)PA_KC * PITCH;
+  float* sQ = sV + (size_t)PA_KC * PITCH;           // [warp][G][HD]
+  float* sS = sQ + PA_WARPS * PA_G * HD;            // [warp][PA_KC][G]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * PA_QT, kvh = blockIdx.y;
+  const int r1 = r0 + PA_QT < R ? r0 + PA_QT : R;
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
+  const float scale = rsqrtf((float)HD);
+  float* sq = sQ + warp * PA_G * HD;
+  float* sc = sS + (size_t)warp * PA_KC * PA_G;
+  for (int seg0 = r0; seg0 < r1;) {
+    // segment: consecutive rows of the tile that belong to one sequence
+    const int seq = row_seq[seg0];
+    int seg1 = seg0 + 1, pmax = row_pos[seg0];
+    while (seg1 < r1 && row_seq[seg1] == seq) {
+      pmax = row_pos[seg1] > pmax ? row_pos[seg1] : pmax;
+      ++seg1;
+    }
+    const int32_t* bt = block_table + (size_t)seq * max_pages;
+    // this warp's rows of the segment: seg0 + warp, + PA_WARPS, ... (at most PA_QT / PA_WARPS = 4); running softmax state in registers
+    constexpr int RPW = PA_QT / PA_WARPS;
+    float m_run[RPW][PA_G], l_run[RPW][PA_G], a0[RPW][PA_G], a1[RPW][PA_G];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int g = 0; g < PA_G; ++g) {
+        m_run[i][g] = -INFINITY;
+        l_run[i][g] = a0[i][g] = a1[i][g] = 0.f;
+      }
+    for (int k0 = 0; k0 <= pmax; k0 += PA_KC) {
+      const int nk = pmax + 1 - k0 < PA_KC ? pmax + 1 - k0 : PA_KC;
+      __syncthreads();   // the previous chunk (or segment) is fully consumed
+      for (int idx0 = threadIdx.x; idx0 < nk * (HD / 4); idx0 += 4 * PA_WARPS * 32) {
+        float4 kv[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = idx0 + u * PA_WARPS * 32;
+          if (idx < nk * (HD / 4)) {
+            const int j = k0 + idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
+            const float* src = pool + (size_t)bt[j / CSMB_PAGE] * page_stride + head_off + (size_t)(j % CSMB_PAGE) * HD + c4;
+            kv[u] = *reinterpret_cast<const float4*>(src);
+            vv[u] = *reinterpret_cast<const float4*>(src + (size_t)Hkv * CSMB_PAGE * HD);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = idx0 + u * PA_WARPS * 32;
+          if (idx < nk * (HD / 4)) {
+            *reinterpret_cast<float4*>(sK + (size_t)(idx / (HD / 4)) * PITCH + (idx % (HD / 4)) * 4) = kv[u];
+            *reinterpret_cast<float4*>(sV + (size_t)(idx / (HD / 4)) * PITCH + (idx % (HD / 4)) * 4) = vv[u];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = seg0 + warp + i * PA_WARPS;
+        if (r >= seg1) break;
+        const int pos = row_pos[r];
+        if (pos < k0) continue;                                   // causal: nothing of this chunk is visible to the row
+        const int S = pos - k0 + 1 < nk ? pos - k0 + 1 : nk;      // visible keys of the chunk
+        __syncwarp();
+        for (int g = 0; g < PA_G; ++g) {
+          const float* qp = q + (size_t)r * H * HD + (size_t)(kvh * PA_G + g) * HD;
+          sq[g * HD + lane] = qp[lane];
+          sq[g * HD + lane + 32] = qp[lane + 32];
+        }
+        __syncwarp();
+        float mx[PA_G];
+#pragma unroll
+        for (int g = 0; g < PA_G; ++g) mx[g] = -INFINITY;
+        for (int j = lane; j < S; j += 64) {   // two keys per lane x G heads: 2 G independent fma chains
+          const float* kp[2];
+          float dot[2][PA_G];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            kp[u] = sK + (size_t)(j + 32 * u < S ? j + 32 * u : j) * PITCH;
+#pragma unroll
+            for (int g = 0; g < PA_G; ++g) dot[u][g] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < HD; c += 4) {
+            float4 qv[PA_G];
+#pragma unroll
+            for (int g = 0; g < PA_G; ++g) qv[g] = *reinterpret_cast<const float4*>(sq + g * HD + c);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 kv = *reinterpret_cast<const float4*>(kp[u] + c);
+#pragma unroll
+              for (int g = 0; g < PA_G; ++g) {
+                dot[u][g] = fmaf(kv.x, qv[g].x, dot[u][g]);
+                dot[u][g] = fmaf(kv.y, qv[g].y, dot[u][g]);
+                dot[u][g] = fmaf(kv.z, qv[g].z, dot[u][g]);
+                dot[u][g] = fmaf(kv.w, qv[g].w, dot[u][g]);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (j + 32 * u < S) {
+              float d[PA_G];
+#pragma unroll
+              for (int g = 0; g < PA_G; ++g) {
+                d[g] = dot[u][g] * scale;
+                mx[g] = fmaxf(mx[g], d[g]);
+              }
+              *reinterpret_cast<float4*>(sc + (size_t)(j + 32 * u) * PA_G) = make_float4(d[0], d[1], d[2], d[3]);
+            }
+        }
+        float corr[PA_G], sum[PA_G];
+#pragma unroll
+        for (int g = 0; g < PA_G; ++g) {
+          const float mnew = fmaxf(m_run[i][g], warp_max(mx[g]));
+          corr[g] = expf(m_run[i][g] - mnew);   // exp(-inf) = 0 on the first chunk
+          m_run[i][g] = mnew;
+          sum[g] = 0.f;
+        }
+        __syncwarp();
+        for (int j = lane; j < S; j += 32) {
+          float4 e = *reinterpret_cast<const float4*>(sc + (size_t)j * PA_G);
+          e.x = expf(e.x - m_run[i][0]); e.y = expf(e.y - m_run[i][1]); e.z = expf(e.z - m_run[i][2]); e.w = expf(e.w - m_run[i][3]);
+          *reinterpret_cast<float4*>(sc + (size_t)j * PA_G) = e;
+          sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+        }
+#pragma unroll
+        for (int g = 0; g < PA_G; ++g) {
+          l_run[i][g] = l_run[i][g] * corr[g] + warp_sum(sum[g]);
+          a0[i][g] *= corr[g];
+          a1[i][g] *= corr[g];
+        }
+        __syncwarp();
+        for (int j0 = 0; j0 < S; j0 += 4) {
+          float4 pj[4];
+          float v0[4], v1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int jj = j0 + u < S ? j0 + u : S - 1;
+            const float* vp = sV + (size_t)jj * PITCH;
+            pj[u] = *reinterpret_cast<const float4*>(sc + (size_t)jj * PA_G);
+            v0[u] = vp[lane];
+            v1[u] = vp[lane + 32];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (j0 + u < S) {
+              a0[i][0] = fmaf(pj[u].x, v0[u], a0[i][0]); a1[i][0] = fmaf(pj[u].x, v1[u], a1[i][0]);
+              a0[i][1] = fmaf(pj[u].y, v0[u], a0[i][1]); a1[i][1] = fmaf(pj[u].y, v1[u], a1[i][1]);
+              a0[i][2] = fmaf(pj[u].z, v0[u], a0[i][2]); a1[i][2] = fmaf(pj[u].z, v1[u], a1[i][2]);
+              a0[i][3] = fmaf(pj[u].w, v0[u], a0[i][3]); a1[i][3] = fmaf(pj[u].w, v1[u], a1[i][3]);
+            }
+        }
+      }
+    }
+    // write this segment's rows
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = seg0 + warp + i * PA_WARPS;
+      if (r >= seg1) break;
+#pragma unroll
+      for (int g = 0; g < PA_G; ++g) {
+        const float inv = 1.f / l_run[i][g];
+        const size_t o = (size_t)r * H * HD + (size_t)(kvh * PA_G + g) * HD;
+        uint16_t hh, ll;
+        split_bf16(a0[i][g] * inv, hh, ll);
+        out_hi[o + lane] = hh;
+        out_lo[o + lane] = ll;
+        split_bf16(a1[i][g] * inv, hh, ll);
+        out_hi[o + lane + 32] = hh;
+        out_lo[o + lane + 32] = ll;
+      }
+    }
+    seg0 = seg1;
   }
 }
 
@@ -1137,14 +1335,21 @@ int csmb_prefill_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   PartIn part;
+  const char* pf_env = getenv("CSMB_PREFILL_FLAGS");   // developer A/B: bit 0 = per-row attention kernel instead of the tiled one
+  const int opts_flags = pf_env ? atoi(pf_env) : 0;
   CSMB_CUDA(bf_launch(w.cc, k_prefill_embed_norm, dim3(R), dim3(256), 0, st, tokens, mask, m->text_emb, m->audio_emb, m->n_codebooks,
                       V, d, w.x, L.norm_in[0], L.eps, w.hi, w.lo));
   for (int l = 0; l < L.n_layers; ++l) {
     float* pool = bt->kv_pool + (size_t)l * bt->kv_layer_stride;
     if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st))) return rc;
-    CSMB_CUDA(bf_launch(w.cc, k_prefill_rope_append, dim3(R), dim3(256), 0, st, part, L.rope, pool, bt->block_table, bt->max_pages,
-                        row_seq, row_pos, H, Hkv, HD, qbuf));
-    if (HD == 64)
+    CSMB_CUDA(bf_launch(w.cc, k_prefill_rope_append, dim3(R, cdiv(nqkv / 2, 512)), dim3(512), 0, st, part, L.rope, pool,
+                        bt->block_table, bt->max_pages, row_seq, row_pos, H, Hkv, HD, qbuf));
+    if (HD == 64 && G == PA_G && !(opts_flags & 1)) {
+      const size_t tile_smem = ((size_t)2 * PA_KC * (HD + 4) + PA_WARPS * PA_G * HD + (size_t)PA_WARPS * PA_KC * PA_G) * sizeof(float);
+      CSMB_CUDA(cudaFuncSetAttribute(k_prefill_attn_tile<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      CSMB_CUDA(bf_launch(w.cc, k_prefill_attn_tile<64>, dim3(cdiv(R, PA_QT), Hkv), dim3(PA_WARPS * 32), tile_smem, st, (const float*)qbuf,
+                          (const float*)pool, bt->block_table, bt->max_pages, row_seq, row_pos, R, H, Hkv, w.hi, w.lo));
+    } else if (HD == 64)
       CSMB_CUDA(bf_launch(w.cc, k_prefill_attn<64>, dim3(R * Hkv), dim3(32 * G), at_smem, st, (const float*)qbuf, (const float*)pool,
                           bt->block_table, bt->max_pages, row_seq, row_pos, H, Hkv, w.hi, w.lo, max_pos));
     else
