@@ -1,0 +1,80 @@
+// Micro-benchmark: how fast can ONE thread issue small tcgen05.mma instructions (M = 128, K = 16, N = 16 .. 256, bf16, operands in
+// shared memory), into one accumulator (a dependent chain, what a GEMM's K loop is) or round-robin into several, and from one or
+// two issuing warps?  The decode-batch Linears (N = tokens <= 64) and the codec's narrow convolutions (N = 16 .. 64 channels) are
+// made of exactly such instructions.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I csm_mlx_b200/csrc -o mma_issue
+// scripts/micro/mma_issue.cu csm_mlx_b200/csrc/gemm_tc.cu (tc.cuh helpers); run on a B200.
+#include <cstdio>
+#include <cstdlib>
+
+#include "tc.cuh"
+
+using namespace csmb;
+
+__global__ void __launch_bounds__(128, 1) k_mma_issue(int N, int count, int nacc, int issuers, unsigned long long* out) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t done[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    tc_mbar_init(&done[0], 1);
+    tc_mbar_init(&done[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  int err = 0;
+  if (lane == 0 && warp >= 1 && warp <= issuers) {
+    const uint32_t idesc = umma_idesc(N);
+    const uint64_t da = umma_desc(s32(smem)), db = umma_desc(s32(smem + 16384));
+    const int w = warp - 1;
+    const uint32_t colstride = N < 32 ? 32 : N;
+    const long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      const uint32_t acc = (uint32_t)(w * nacc + (i % nacc));
+      const uint64_t koff = (uint64_t)(((i & 3) * 32) >> 4);
+      umma_f16(tmem_base + acc * colstride, da + koff, db + koff, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    umma_commit(&done[w]);
+    tc_mbar_wait(&done[w], 0, &err);
+    const long long t2 = clock64();
+    if (blockIdx.x == 0) {
+      out[w * 2] = (unsigned long long)(t1 - t0);
+      out[w * 2 + 1] = (unsigned long long)(t2 - t0);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+int main() {
+  unsigned long long* d;
+  cudaMalloc(&d, 64);
+  cudaFuncSetAttribute(k_mma_issue, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int count = 4096;
+  printf("M=128 K=16 bf16, %d MMAs per issuer, 148 CTAs; cycles per MMA: issue loop only / until all complete\n", count);
+  for (int N : {16, 32, 64, 128, 256}) {
+    for (int issuers : {1, 2}) {
+      for (int nacc : {1, 2, 4}) {
+        if ((N < 32 ? 32 : N) * nacc * issuers > 512) continue;
+        cudaMemset(d, 0, 64);
+        k_mma_issue<<<148, 128, 64 * 1024>>>(N, count, nacc, issuers, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        unsigned long long h[4];
+        cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+        printf("N=%3d issuers=%d accumulators/issuer=%d : issue %.1f  complete %.1f  (per issuer; tensor work = %.0f cycles)  %s\n", N, issuers,
+               nacc, (double)h[0] / count, (double)h[1] / count, 128.0 * N / 256.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
+    }
+  }
+  return 0;
+}
