@@ -87,8 +87,12 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   const int nk_total = a.K / TC_BK, NS = a.nstages;
   const int kb0 = (int)(((long long)nk_total * blockIdx.z) / a.S), kb1 = (int)(((long long)nk_total * (blockIdx.z + 1)) / a.S);
   const int nk = kb1 - kb0;
-  uint32_t ncols = 32;
-  while ((int)ncols < RN) ncols <<= 1;
+  // The token rows' hi and lo planes sit one after the other in a stage and are ONE operand of 2 RN rows: a single
+  // tcgen05.mma per K step leaves W.hi in accumulator columns [0, RN) and W.lo in [RN, 2 RN); the epilogue adds the halves.
+  // (One thread issues one tcgen05.mma per ~150 cycles whatever its N — profiles/r02_mma_issue_microbench.log — and two
+  // instructions per K step made these Linears issue-bound below the HBM stream rate.)
+  uint32_t ncols = 64;
+  while ((int)ncols < 2 * RN + 32) ncols <<= 1;
   auto load_w = [&](unsigned char* dst, int kb, uint64_t* bar) {
     if (GU) {
       tma_load_2d(dst, &map_w, kb * TC_BK, n0 / 2, bar);                                  // gate rows f0 .. f0+63
@@ -147,7 +151,7 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(RN);
+      const uint32_t idesc = umma_idesc(2 * RN);
       bool ok = true;
       for (int kb = 0; kb < nk && ok; ++kb) {
         const int s = kb % NS;
@@ -156,12 +160,11 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = s32(smem + (size_t)s * stage_bytes);
-        const uint64_t da = umma_desc(sa), dhi = umma_desc(sa + x_off), dlo = umma_desc(sa + x_off + x_bytes);
+        const uint64_t da = umma_desc(sa), dx = umma_desc(sa + x_off);   // hi rows then lo rows: 2 RN rows, 128 B apart
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t koff = (uint64_t)((k * 32) >> 4);
-          umma_f16(tmem_base, da + koff, dhi + koff, idesc, (kb | k) != 0);
-          umma_f16(tmem_base, da + koff, dlo + koff, idesc, 1u);
+          umma_f16(tmem_base, da + koff, dx + koff, idesc, (kb | k) != 0);
         }
         umma_commit(&empty[s]);
       }
@@ -180,11 +183,12 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       if (ok) {
         float* mine = ex + (size_t)(quarter >> 1) * RN * 64 + (quarter & 1) * 32 + lane;
         for (int c0 = 0; c0 < RN; c0 += 32) {
-          uint32_t v[32];
+          uint32_t v[32], vl[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RN + c0), vl);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c0 + j < RN) mine[(size_t)(c0 + j) * 64] = __uint_as_float(v[j]);
+            if (c0 + j < RN) mine[(size_t)(c0 + j) * 64] = __uint_as_float(v[j]) + __uint_as_float(vl[j]);
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -203,18 +207,19 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     } else if (ok) {
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
       for (int c0 = 0; c0 < RN; c0 += 32) {
-        uint32_t v[32];
+        uint32_t v[32], vl[32];
         if (a.dbg & 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int j = 0; j < 32; ++j) v[j] = vl[j] = 0u;
         } else {
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RN + c0), vl);
         }
         if (n < a.N && !(a.dbg & 1)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int r = r0 + c0 + j;
-            if (c0 + j < RN && r < a.R) dst0[(size_t)r * a.N] = __uint_as_float(v[j]);
+            if (c0 + j < RN && r < a.R) dst0[(size_t)r * a.N] = __uint_as_float(v[j]) + __uint_as_float(vl[j]);
           }
         }
       }
@@ -1116,7 +1121,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int S = bf_pick_split(N, K);
   CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
-  const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
+  const int RN = R <= 128 ? ((R + 15) / 16) * 16 : 128;   // token rows per tile: 2 RN <= 256 accumulator columns (hi | lo)
   CUtensorMap mw, mhi, mlo;
   if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, xhi ? xhi : w.hi, R, K, RN) ||
       !tc_make_map(&mlo, xlo ? xlo : w.lo, R, K, RN))
@@ -1137,7 +1142,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
 // SwiGLU MLP first half in one launch: w.hi2 / w.lo2 [R][F] = split(silu(x Wg^T) * (x Wu^T)), Wgu = gate rows then up rows
 static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K, cudaStream_t st) {
   CSMB_REQUIRE(R > 0 && F % (TC_BM / 2) == 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(Wgu) & 15) == 0);
-  const int RN = R <= 256 ? ((R + 15) / 16) * 16 : 128;
+  const int RN = R <= 128 ? ((R + 15) / 16) * 16 : 128;   // token rows per tile: 2 RN <= 256 accumulator columns (hi | lo)
   CUtensorMap mw, mhi, mlo;
   if (!tc_make_map(&mw, Wgu, 2 * F, K, TC_BM / 2) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
