@@ -20,7 +20,6 @@
 // Arithmetic is that of the per-op path (fp32 accumulation, fixed summation orders): parity tests compare both with
 // the batch-1 kernels and the oracle token for token.
 #include <math.h>
-#include <stdlib.h>
 
 #include <utility>
 
@@ -1340,8 +1339,6 @@ int csmb_prefill_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   PartIn part;
-  const char* pf_env = getenv("CSMB_PREFILL_FLAGS");   // developer A/B: bit 0 = per-row attention kernel instead of the tiled one
-  const int opts_flags = pf_env ? atoi(pf_env) : 0;
   CSMB_CUDA(bf_launch(w.cc, k_prefill_embed_norm, dim3(R), dim3(256), 0, st, tokens, mask, m->text_emb, m->audio_emb, m->n_codebooks,
                       V, d, w.x, L.norm_in[0], L.eps, w.hi, w.lo));
   for (int l = 0; l < L.n_layers; ++l) {
@@ -1349,7 +1346,7 @@ int csmb_prefill_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* 
     if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st))) return rc;
     CSMB_CUDA(bf_launch(w.cc, k_prefill_rope_append, dim3(R, cdiv(nqkv / 2, 512)), dim3(512), 0, st, part, L.rope, pool,
                         bt->block_table, bt->max_pages, row_seq, row_pos, H, Hkv, HD, qbuf));
-    if (HD == 64 && G == PA_G && !(opts_flags & 1)) {
+    if (HD == 64 && G == PA_G) {
       const size_t tile_smem = ((size_t)2 * PA_KC * (HD + 4) + PA_WARPS * PA_G * HD + (size_t)PA_WARPS * PA_KC * PA_G) * sizeof(float);
       CSMB_CUDA(cudaFuncSetAttribute(k_prefill_attn_tile<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
       CSMB_CUDA(bf_launch(w.cc, k_prefill_attn_tile<64>, dim3(cdiv(R, PA_QT), Hkv), dim3(PA_WARPS * 32), tile_smem, st, (const float*)qbuf,
