@@ -50,6 +50,33 @@ static ChainCfg chain_cfg(const csmb_chain_opts* o) {
   return c;
 }
 
+// ---------------------------------------------------------------------------------------------- timeline (debug builds)
+// -DCSMB_TIMELINE (scripts/chain_timeline.py builds a second .so with it; never the shipped library): block (0,0,0) of every
+// chain kernel records %globaltimer at entry, after griddepcontrol.wait, (Linears: accumulator complete) and at its end.
+#ifdef CSMB_TIMELINE
+constexpr int TL_SLOTS = 16384, TL_WORDS = 6;
+__device__ unsigned long long g_tl[TL_SLOTS * TL_WORDS];
+__device__ unsigned g_tl_n;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool tl_block0() { return (blockIdx.x | blockIdx.y | blockIdx.z) == 0; }
+__device__ __forceinline__ unsigned tl_enter(unsigned kind) {
+  const unsigned slot = atomicAdd(&g_tl_n, 1u) % TL_SLOTS;
+  g_tl[slot * TL_WORDS + 0] = kind | ((unsigned long long)(gridDim.x * gridDim.y * gridDim.z) << 8);
+  g_tl[slot * TL_WORDS + 1] = tl_now();
+  return slot;
+}
+__device__ __forceinline__ void tl_mark(unsigned slot, int i) { g_tl[slot * TL_WORDS + i] = tl_now(); }
+#define TL_ENTER(kind) unsigned tl_slot = 0; if (tl_block0() && threadIdx.x == 0) tl_slot = tl_enter(kind);
+#define TL_MARK(i) if (tl_block0() && threadIdx.x == 0) tl_mark(tl_slot, i);
+#else
+#define TL_ENTER(kind)
+#define TL_MARK(i)
+#endif
+
 // ---------------------------------------------------------------------------------------------- GEMM
 struct GpArgs {
   float* part;  // [S][R][N] fp32 partials
@@ -78,6 +105,10 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   __shared__ __align__(8) uint64_t full[BF_MAX_STAGES], empty[BF_MAX_STAGES], acc_full;
   __shared__ uint32_t tmem_base_s;
   pdl_launch_dependents();
+#ifdef CSMB_TIMELINE
+  __shared__ unsigned tl_slot_s;
+  if (tl_block0() && threadIdx.x == 0) tl_slot_s = tl_enter(GU ? 2u : 1u);
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TC_BM, r0 = blockIdx.y * a.RN;
   const int RN = a.RN;
@@ -131,6 +162,9 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         load_w(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
       }
       pdl_wait();
+#ifdef CSMB_TIMELINE
+      if (tl_block0()) tl_mark(tl_slot_s, 2);
+#endif
       for (int kb = 0; kb < pre; ++kb) {
         unsigned char* st = smem + (size_t)kb * stage_bytes;
         tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[kb]);
@@ -175,6 +209,9 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     const int quarter = warp & 3;
     const bool ok = tc_mbar_wait(&acc_full, 0, a.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef CSMB_TIMELINE
+    if (tl_block0() && threadIdx.x == 64) tl_mark(tl_slot_s, 3);
+#endif
     const int n = n0 + quarter * 32 + lane;
     if (GU) {
       // park gate (quarters 0, 1) and up (quarters 2, 3) values as [2][RN][64] fp32 in the drained stages
@@ -224,6 +261,9 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#ifdef CSMB_TIMELINE
+    if (tl_block0() && threadIdx.x == 64) tl_mark(tl_slot_s, 4);
+#endif
   }
   __syncthreads();
   if (warp == 2) {
@@ -250,6 +290,23 @@ struct PartIn {
   size_t stride;   // R * ld
   int ld;
 };
+// Asynchronous global -> shared copies (LDGSTS): no register destination, so a thread can have any number of them in flight —
+// ptxas pipelines ordinary loads feeding a sum three to five at a time, which turned "sum S partials" into S / 4 dependent
+// L2 round trips (profiles/r02_chain_timeline.md).  A thread that reads back only what it copied itself needs
+// cp_async_wait_all() and no block barrier.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // Fixed-order sums over the S split-K partials.  Loads go out in independent batches of 8 through the read-only path
 // (one L2 round trip per batch instead of one per partial: these kernels are pure latency chains).
 __device__ __forceinline__ float part_sum1(const PartIn& pi, size_t off) {
@@ -346,7 +403,9 @@ __global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restr
                                                           const uint8_t* __restrict__ use_override) {
   __shared__ float red[8];
   pdl_launch_dependents();
+  TL_ENTER(6u)
   pdl_wait();
+  TL_MARK(2)
   const int b = blockIdx.x, c = threadIdx.x * 8;
   float acc[8];
 #pragma unroll
@@ -377,6 +436,7 @@ __global__ void __launch_bounds__(256) k_frame_embed_norm(const int32_t* __restr
                acc[2] * scale * g0.z, acc[3] * scale * g0.w);
   store_split4(hi + (size_t)b * d + c + 4, lo + (size_t)b * d + c + 4, acc[4] * scale * g1.x, acc[5] * scale * g1.y,
                acc[6] * scale * g1.z, acc[7] * scale * g1.w);
+  TL_MARK(4)
 }
 
 // Row rin = blockIdx.x * row_mul + row_add (or row_idx[blockIdx.x] if given) of the residual stream:  mode 1: x = sum(part);  mode 2: x += sum(part);
@@ -386,33 +446,60 @@ __global__ void __launch_bounds__(256) k_resid_norm_split(float* __restrict__ x,
                                                           const float* __restrict__ w, float eps,
                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                                           float* __restrict__ y32, int row_mul, int row_add,
-                                                          const int32_t* __restrict__ row_idx) {
+                                                          const int32_t* __restrict__ row_idx, int staged) {
+  extern __shared__ __align__(16) float pst[];   // staged: [S][d] partials of this row
   __shared__ float red[8];
   pdl_launch_dependents();
+  TL_ENTER(3u)
   pdl_wait();
+  TL_MARK(2)
   constexpr int d = NV * 1024;
   const int rin = row_idx ? row_idx[blockIdx.x] : blockIdx.x * row_mul + row_add, rout = blockIdx.x;
+  if (staged && mode != 0) {
+    // all S x NV 16-byte pieces of this thread's columns in flight at once
+    for (int z = 0; z < part.S; ++z)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = threadIdx.x * 4 + j * 1024;
+        cp_async16(pst + (size_t)z * d + c, part.p + (size_t)z * part.stride + (size_t)rin * part.ld + c);
+      }
+  }
   float4 v[NV];
   float ss = 0.f;
+  float4 xo[NV];
+  if (mode != 1) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) xo[j] = *reinterpret_cast<const float4*>(x + (size_t)rin * ldx + threadIdx.x * 4 + j * 1024);
+  }
+  if (staged && mode != 0) cp_async_wait_all();
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c = threadIdx.x * 4 + j * 1024;
     float* xp = x + (size_t)rin * ldx + c;
     float4 s;
     if (mode == 0) {
-      s = *reinterpret_cast<const float4*>(xp);
+      s = xo[j];
     } else {
-      s = part_sum4(part, (size_t)rin * part.ld + c);
-      if (mode == 2) {
-        const float4 o = *reinterpret_cast<const float4*>(xp);
-        s = make_float4(o.x + s.x, o.y + s.y, o.z + s.z, o.w + s.w);
+      if (staged) {
+        s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < part.S; ++z) {
+          const float4 t = *reinterpret_cast<const float4*>(pst + (size_t)z * d + c);
+          s.x += t.x;
+          s.y += t.y;
+          s.z += t.z;
+          s.w += t.w;
+        }
+      } else {
+        s = part_sum4(part, (size_t)rin * part.ld + c);
       }
+      if (mode == 2) s = make_float4(xo[j].x + s.x, xo[j].y + s.y, xo[j].z + s.z, xo[j].w + s.w);
       *reinterpret_cast<float4*>(xp) = s;
     }
     v[j] = s;
     ss = sumsq4(s, ss);
   }
   norm_split_row<NV>(v, ss, w, eps, hi + (size_t)rout * d, lo + (size_t)rout * d, y32 ? y32 + (size_t)rout * d : nullptr, red);
+  TL_MARK(4)
 }
 
 // One block per (sequence b, kv head), warp g = query head kvh*G + g.  Stage 0 (all threads): sum the qkv partials of the
@@ -427,7 +514,9 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
                                                            uint16_t* __restrict__ out_lo, int max_pos) {
   extern __shared__ float smem[];
   pdl_launch_dependents();
+  TL_ENTER(4u)
   pdl_wait();
+  TL_MARK(2)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
   const int G = H / Hkv, h = kvh * G + warp;
@@ -459,6 +548,7 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
     }
   }
   __syncthreads();  // this block's k/v rows are in the cache, all queries are in shared memory
+  TL_MARK(3)
   const int32_t* bt = block_table ? block_table + (size_t)b * max_pages : nullptr;
   for (int i = 0; i < rps; ++i) {
     const int r = b * rps + i, pos = posb + i, S = pos + 1;
@@ -523,6 +613,139 @@ __global__ void __launch_bounds__(256) k_attn_decode_fused(PartIn qkv, const flo
     }
     __syncwarp();  // sc is reused by this warp's next row
   }
+  TL_MARK(4)
+}
+
+// The same block for caches of at most AS_MAXPOS positions (the depth decoder: 32 codebook positions, re-created every
+// frame, generation.py:70).  k_attn_decode_fused walks the cache through dependent L2 round trips (scores, then values in
+// groups of 8 keys: 8.4 us per launch for 17 positions on average, the largest item of the decoder's frame-step,
+// profiles/r02_chain_timeline.md); here every cached K / V row of the kv head is requested at once with cp.async straight
+// into shared memory while the block sums the qkv partials of the new rows, and the attention itself runs out of shared
+// memory.  Same sums in the same order as k_attn_decode_fused: bit-identical output planes.
+constexpr int AS_MAXPOS = 32;
+template <int HD>
+__global__ void __launch_bounds__(256) k_attn_decode_small(PartIn qkv, const float* __restrict__ rope, float* pool,
+                                                           const int32_t* __restrict__ block_table, int max_pages,
+                                                           const int32_t* __restrict__ pos_arr, int pos0, int rps, int H,
+                                                           int Hkv, uint16_t* __restrict__ out_hi,
+                                                           uint16_t* __restrict__ out_lo) {
+  constexpr int PITCH = HD + 4, half = HD / 2;
+  extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  TL_ENTER(4u)
+  pdl_wait();
+  TL_MARK(2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
+  const int G = H / Hkv, h = kvh * G + warp;
+  float* sK = smem;                                  // [AS_MAXPOS][PITCH]
+  float* sV = sK + AS_MAXPOS * PITCH;
+  float* sq_all = sV + AS_MAXPOS * PITCH;            // [rps][G][HD] rotated queries
+  float* sc = sq_all + (size_t)rps * G * HD + warp * AS_MAXPOS;   // this warp's scores
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
+  const size_t v_off = (size_t)Hkv * CSMB_PAGE * HD;
+  const float scale = rsqrtf((float)HD);
+  const int posb = pos_arr ? pos_arr[b] : pos0;
+  // positions 0 .. posb-1 are in the cache (written by earlier launches): all of them in flight at once
+  for (int idx = threadIdx.x; idx < posb * (HD / 4); idx += blockDim.x) {
+    const int j = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
+    const int page = block_table ? block_table[(size_t)b * max_pages + j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
+    const float* src = pool + (size_t)page * page_stride + head_off + (size_t)(j % CSMB_PAGE) * HD + c4;
+    cp_async16(sK + j * PITCH + c4, src);
+    cp_async16(sV + j * PITCH + c4, src + v_off);
+  }
+  // the new rows' qkv partials (this block's G query heads, its k head, its v head) and their RoPE rows: also asynchronous
+  const int per_row = (G + 2) * half, total = rps * per_row;
+  float2* stg = reinterpret_cast<float2*>(sq_all + (size_t)rps * G * HD + (size_t)G * AS_MAXPOS);   // [S][total]
+  float2* srope = stg + (size_t)qkv.S * total;                                                      // [rps][half]
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int i = idx / per_row, rem = idx % per_row, slot = rem / half, pr = rem % half;
+    const int col = (slot < G ? (kvh * G + slot) : (slot == G ? H + kvh : H + Hkv + kvh)) * HD + 2 * pr;
+    const float* src = qkv.p + (size_t)(b * rps + i) * qkv.ld + col;
+    for (int z = 0; z < qkv.S; ++z) cp_async8(stg + (size_t)z * total + idx, src + (size_t)z * qkv.stride);
+  }
+  for (int idx = threadIdx.x; idx < rps * half; idx += blockDim.x)
+    cp_async8(srope + idx, rope + ((size_t)(posb + idx / half) * half + idx % half) * 2);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int i = idx / per_row, rem = idx % per_row, slot = rem / half, pr = rem % half;
+    const int pos = posb + i;
+    float2 v = make_float2(0.f, 0.f);
+    for (int z = 0; z < qkv.S; ++z) {   // part_sum2's order
+      const float2 t = stg[(size_t)z * total + idx];
+      v.x += t.x;
+      v.y += t.y;
+    }
+    const float2 cs = srope[i * half + pr];
+    const float2 rot = make_float2(v.x * cs.x - v.y * cs.y, v.y * cs.x + v.x * cs.y);
+    if (slot < G) {
+      *reinterpret_cast<float2*>(sq_all + ((size_t)i * G + slot) * HD + 2 * pr) = rot;
+    } else {
+      const int lp = pos / CSMB_PAGE;
+      const int page = block_table ? block_table[(size_t)b * max_pages + lp] : b * max_pages + lp;
+      float* kdst = pool + (size_t)page * page_stride + head_off + (size_t)(pos % CSMB_PAGE) * HD;
+      if (slot == G) {
+        *reinterpret_cast<float2*>(kdst + 2 * pr) = rot;
+        *reinterpret_cast<float2*>(sK + pos * PITCH + 2 * pr) = rot;
+      } else {
+        *reinterpret_cast<float2*>(kdst + v_off + 2 * pr) = v;
+        *reinterpret_cast<float2*>(sV + pos * PITCH + 2 * pr) = v;
+      }
+    }
+  }
+  __syncthreads();  // the kv head's whole cache and all queries are in shared memory
+  TL_MARK(3)
+  for (int i = 0; i < rps; ++i) {
+    const int r = b * rps + i, S = posb + i + 1;
+    const float* sq = sq_all + ((size_t)i * G + warp) * HD;
+    float m = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      const float* kp = sK + j * PITCH;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+        dot = fmaf(kv.x, sq[c], dot);
+        dot = fmaf(kv.y, sq[c + 1], dot);
+        dot = fmaf(kv.z, sq[c + 2], dot);
+        dot = fmaf(kv.w, sq[c + 3], dot);
+      }
+      dot *= scale;
+      sc[j] = dot;
+      m = fmaxf(m, dot);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(sc[j] - m);
+      sc[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    constexpr int PER = HD / 32;
+    float acc[PER];
+#pragma unroll
+    for (int ii = 0; ii < PER; ++ii) acc[ii] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < S; ++j) {
+      const float pj = sc[j];
+#pragma unroll
+      for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(pj, sV[j * PITCH + lane + 32 * ii], acc[ii]);
+    }
+    const size_t o = (size_t)r * H * HD + (size_t)h * HD;
+#pragma unroll
+    for (int ii = 0; ii < PER; ++ii) {
+      uint16_t hh, ll;
+      split_bf16(acc[ii] * inv, hh, ll);
+      out_hi[o + lane + 32 * ii] = hh;
+      out_lo[o + lane + 32 * ii] = ll;
+    }
+    __syncwarp();  // sc is reused by this warp's next row
+  }
+  TL_MARK(4)
 }
 
 // ---- prompt rows (T > 1) through the chain's kernels: generation.py:34-42 with many rows per sequence --------------------
@@ -911,16 +1134,34 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
                                                       int cb, int32_t* __restrict__ frame, int ncb,
                                                       const uint16_t* __restrict__ audio_emb, int d, int embed,
                                                       const float* __restrict__ h_last, uint16_t* __restrict__ hi,
-                                                      uint16_t* __restrict__ lo, int out_mul, ProjIn pj) {
+                                                      uint16_t* __restrict__ lo, int out_mul, ProjIn pj, int staged) {
   extern __shared__ float sl[];
   __shared__ float red_v[8];
   __shared__ int red_i[8];
   __shared__ unsigned long long red_q[8];
   pdl_launch_dependents();
+  TL_ENTER(5u)
   pdl_wait();
+  TL_MARK(2)
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < V; i += 256) sl[i] = part_sum1(lg, (size_t)b * lg.ld + i);
+  if (staged) {
+    // logits = sum of the head's split-K partials in part_sum1's order; every partial of this thread's vocabulary entries is
+    // requested at once (cp.async into sl[V ..]), one L2 round trip instead of one per entry
+    float* stg = sl + V;
+    const float* lp = lg.p + (size_t)b * lg.ld;
+    for (int z = 0; z < lg.S; ++z)
+      for (int i = threadIdx.x; i < V; i += 256) cp_async4(stg + (size_t)z * V + i, lp + (size_t)z * lg.stride + i);
+    cp_async_wait_all();
+    for (int i = threadIdx.x; i < V; i += 256) {
+      float v = 0.f;
+      for (int z = 0; z < lg.S; ++z) v += stg[(size_t)z * V + i];
+      sl[i] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += 256) sl[i] = part_sum1(lg, (size_t)b * lg.ld + i);
+  }
   __syncthreads();
+  TL_MARK(3)
   int tok;
   if (a.inv_temp == 0.f) {
     tok = block_argmax(V, [&](int i) { return sl[i]; }, red_v, red_i);
@@ -994,6 +1235,7 @@ __global__ void __launch_bounds__(256) k_sample_embed(PartIn lg, int V, BfSample
         red_v, red_i);
   }
   if (threadIdx.x == 0) frame[(size_t)b * ncb + cb] = tok;
+  TL_MARK(4)
   if (!embed) return;
   const int t = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
   if (pj.ptab != nullptr) {
@@ -1159,11 +1401,17 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
 
 static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, const float* nw, float eps, float* y32, int rows,
                    int row_mul, int row_add, cudaStream_t st, const int32_t* row_idx = nullptr) {
-  if (d == 1024)
-    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<1>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx));
-  else if (d == 2048)
-    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<2>, dim3(rows), dim3(256), 0, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx));
-  else
+  // the row's S partials staged in shared memory with cp.async when they fit (S * d * 4 bytes)
+  size_t smem = mode != 0 ? (size_t)part.S * d * sizeof(float) : 0;
+  const int staged = (smem > 0 && smem <= 96 * 1024 && !(w.cc.dbg & 16)) ? 1 : 0;
+  if (!staged) smem = 0;
+  if (d == 1024) {
+    if (smem > 48 * 1024) CSMB_CUDA(cudaFuncSetAttribute(k_resid_norm_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<1>, dim3(rows), dim3(256), smem, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx, staged));
+  } else if (d == 2048) {
+    if (smem > 48 * 1024) CSMB_CUDA(cudaFuncSetAttribute(k_resid_norm_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CSMB_CUDA(bf_launch(w.cc, k_resid_norm_split<2>, dim3(rows), dim3(256), smem, st, x, d, part, mode, nw, eps, w.hi, w.lo, y32, row_mul, row_add, row_idx, staged));
+  } else
     return CSMB_ERR_UNSUPPORTED;
   return CSMB_OK;
 }
@@ -1171,9 +1419,27 @@ static int bf_norm(const FastWs& w, float* x, int d, PartIn part, int mode, cons
 static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool, const int32_t* block_table, int max_pages,
                    const int32_t* pos_arr, int pos0, int rps, int B, cudaStream_t st) {
   const int G = L.n_heads / L.n_kv_heads, max_pos = max_pages * CSMB_PAGE;
-  const size_t smem = ((size_t)rps * G * L.head_dim + (size_t)G * max_pos) * sizeof(float);
-  CSMB_REQUIRE(smem <= 48 * 1024 && G >= 1 && G <= 8);
+  CSMB_REQUIRE(G >= 1 && G <= 8);
   const dim3 grid(B * L.n_kv_heads), block(32 * G);
+  if (max_pos <= AS_MAXPOS && !(w.cc.dbg & 8)) {
+    // short caches (the depth decoder): everything staged in shared memory at once
+    const size_t smem = ((size_t)2 * AS_MAXPOS * (L.head_dim + 4) + (size_t)rps * G * L.head_dim + (size_t)G * AS_MAXPOS) * sizeof(float) +
+                        ((size_t)qkv.S * rps * (G + 2) * (L.head_dim / 2) + (size_t)rps * (L.head_dim / 2)) * sizeof(float2);
+    CSMB_REQUIRE(smem <= 160 * 1024);
+    if (L.head_dim == 64) CSMB_CUDA(cudaFuncSetAttribute(k_attn_decode_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (L.head_dim == 128) CSMB_CUDA(cudaFuncSetAttribute(k_attn_decode_small<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (L.head_dim == 64)
+      CSMB_CUDA(bf_launch(w.cc, k_attn_decode_small<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                          rps, L.n_heads, L.n_kv_heads, w.hi, w.lo));
+    else if (L.head_dim == 128)
+      CSMB_CUDA(bf_launch(w.cc, k_attn_decode_small<128>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                          rps, L.n_heads, L.n_kv_heads, w.hi, w.lo));
+    else
+      return CSMB_ERR_UNSUPPORTED;
+    return CSMB_OK;
+  }
+  const size_t smem = ((size_t)rps * G * L.head_dim + (size_t)G * max_pos) * sizeof(float);
+  CSMB_REQUIRE(smem <= 48 * 1024);
   if (L.head_dim == 64)
     CSMB_CUDA(bf_launch(w.cc, k_attn_decode_fused<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
                         rps, L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
@@ -1277,7 +1543,15 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   sa.draw_pos_mul = (uint32_t)ncb;
   int rc;
   PartIn part;
-  const size_t lg_smem = (size_t)V * sizeof(float);
+  // logits row + (staged) the head's split-K partials of the row: (1 + S) * V floats
+  auto lg_smem_of = [&](int K, int* staged) {
+    const size_t full = (size_t)(1 + bf_pick_split(V, K)) * V * sizeof(float);
+    *staged = (full <= 96 * 1024 && !(w.cc.dbg & 16)) ? 1 : 0;
+    return *staged ? full : (size_t)V * sizeof(float);
+  };
+  CSMB_CUDA(cudaFuncSetAttribute(k_sample_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  int lg_staged = 0;
+  size_t lg_smem = lg_smem_of(db, &lg_staged);
   const ProjIn no_proj{nullptr, nullptr, nullptr, 0.f, 0};
 
   // ---- backbone step (generation.py:34-42 with T = 1)
@@ -1288,7 +1562,8 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   if ((rc = bf_gemm(w, m->c0_head, B, V, db, &part, st))) return rc;
   sa.draw_base = draw_base;
   CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, 0, frame, ncb, m->audio_emb, db, 1,
-                      (const float*)w.h_last, w.hi, w.lo, 2, no_proj));
+                      (const float*)w.h_last, w.hi, w.lo, 2, no_proj, lg_staged));
+  lg_smem = lg_smem_of(dd, &lg_staged);
   // ---- depth decoder (generation.py:56-90)
   for (int i = 1; i < ncb; ++i) {
     const int rps = (i == 1) ? 2 : 1, R = B * rps;
@@ -1305,7 +1580,7 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
     const int embed = i + 1 < ncb ? 1 : 0;
     const ProjIn pj = (ptab && embed) ? ProjIn{ptab + (size_t)i * V * dd, w.dx, D.norm_in[0], D.eps, dd} : no_proj;
     CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, i, frame, ncb, m->audio_emb, db,
-                        embed, (const float*)nullptr, w.hi, w.lo, 1, pj));
+                        embed, (const float*)nullptr, w.hi, w.lo, 1, pj, lg_staged));
   }
   return CSMB_OK;
 }
@@ -1376,6 +1651,22 @@ int csmb_prefill_fast(const csmb_model* m, const csmb_batch* bt, const int32_t* 
   }
   return CSMB_OK;
 }
+
+#ifdef CSMB_TIMELINE
+// debug builds only: copies the recorded slots ([n][TL_WORDS] words) to `out`, returns the number recorded, optionally resets
+int csmb_debug_timeline_read(unsigned long long* out, int max_slots, int reset) {
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(n));
+  const int m = (int)(n < (unsigned)max_slots ? n : (unsigned)max_slots);
+  if (out && m > 0) cudaMemcpyFromSymbol(out, g_tl, (size_t)m * TL_WORDS * sizeof(unsigned long long));
+  if (reset) {
+    n = 0;
+    cudaMemcpyToSymbol(g_tl_n, &n, sizeof(n));
+  }
+  return m;
+}
+#endif
 
 // ---- projected-embedding table -------------------------------------------------------------------------------------
 size_t csmb_proj_table_bytes(const csmb_model* m) {

@@ -10,16 +10,15 @@
 
 using namespace csmb;
 
-__global__ void __launch_bounds__(128, 1) k_mma_issue(int N, int count, int nacc, int issuers, unsigned long long* out) {
+__global__ void __launch_bounds__(192, 1) k_mma_issue(int N, int count, int nacc, int issuers, unsigned long long* out) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t done[2];
+  __shared__ __align__(8) uint64_t done[4];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
-    tc_mbar_init(&done[0], 1);
-    tc_mbar_init(&done[1], 1);
+    for (int i = 0; i < 4; ++i) tc_mbar_init(&done[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -63,11 +62,11 @@ int main() {
   const int count = 4096;
   printf("M=128 K=16 bf16, %d MMAs per issuer, 148 CTAs; cycles per MMA: issue loop only / until all complete\n", count);
   for (int N : {16, 32, 64, 128, 256}) {
-    for (int issuers : {1, 2}) {
-      for (int nacc : {1, 2, 4}) {
+    for (int issuers : {1, 2, 4}) {
+      for (int nacc : {1, 2}) {
         if ((N < 32 ? 32 : N) * nacc * issuers > 512) continue;
         cudaMemset(d, 0, 64);
-        k_mma_issue<<<148, 128, 64 * 1024>>>(N, count, nacc, issuers, d);
+        k_mma_issue<<<148, 192, 64 * 1024>>>(N, count, nacc, issuers, d);
         cudaError_t e = cudaDeviceSynchronize();
         unsigned long long h[4];
         cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);

@@ -69,17 +69,18 @@ def _chain():
     base = {}
     for B in (int(x) for x in os.environ.get("R2_BATCHES", "1,2,8,16,32,64,128").split(",")):
         for tab, smem in (((0, 0), (1, 0), (1, 96)) if os.environ.get("R2_FULL") else ((1, 0),)):
-            setenv(CSMB_NO_PROJ_TABLE=None if tab else 1, CSMB_CHAIN_SMEM_KB=smem or None)
-            st, frame = warm_state(B, row_invariant=(B == 1))
-            ms, last = time_graph_steps(st, frame)
-            key = (B,)
-            if key not in base:
-                base[key] = last.clone()
-            same = bool(torch.equal(base[key], last))
-            print(f"chain B={B:3d} table={tab} smem_kb={smem or 200}: {ms:.3f} ms/step  {B * 0.08 / (ms / 1e3):7.0f} audio-s/s  "
-                  f"frac {9.107e9 / (ms * 1e-3) / 6557.8e9:.3f}  tokens_same_as_first_variant={same}", flush=True)
-            del st
-    setenv(CSMB_NO_PROJ_TABLE=None, CSMB_CHAIN_SMEM_KB=None)
+            for flags in (int(x) for x in os.environ.get("R2_FLAGS", "0").split(",")):
+                setenv(CSMB_NO_PROJ_TABLE=None if tab else 1, CSMB_CHAIN_SMEM_KB=smem or None, CSMB_CHAIN_FLAGS=flags or None)
+                st, frame = warm_state(B, row_invariant=(B == 1))
+                ms, last = time_graph_steps(st, frame)
+                key = (B,)
+                if key not in base:
+                    base[key] = last.clone()
+                same = bool(torch.equal(base[key], last))
+                print(f"chain B={B:3d} table={tab} smem_kb={smem or 200} flags={flags}: {ms:.3f} ms/step  {B * 0.08 / (ms / 1e3):7.0f} audio-s/s  "
+                      f"frac {8.981e9 / (ms * 1e-3) / 6557.8e9:.3f}  tokens_same_as_first_variant={same}", flush=True)
+                del st
+    setenv(CSMB_NO_PROJ_TABLE=None, CSMB_CHAIN_SMEM_KB=None, CSMB_CHAIN_FLAGS=None)
 
 
 @section("lanes")
