@@ -28,6 +28,12 @@
 namespace csmb {
 
 constexpr int BF_MAX_STAGES = 6;
+#ifndef CSMB_BF_NI
+#define CSMB_BF_NI 2
+#endif
+constexpr int BF_NI = CSMB_BF_NI;                 // MMA-issuing warps (= fp32 accumulators) per Linear CTA: 1 or 2
+constexpr int BF_THREADS = 32 * (1 + BF_NI + 4);  // warp 0: TMA producer; warps 1 .. BF_NI: MMA issuers; then 4 epilogue warps
+static_assert(BF_MAX_STAGES % BF_NI == 0, "a pipeline stage must always be consumed by the same issuer");
 constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
 
 // Split-K geometry is a constant of the library (see bf_pick_split): at least BF_MIN_KBLOCKS 64-wide K blocks per CTA and
@@ -86,6 +92,9 @@ struct GpArgs {
   // GU variant only: the matrix is gate rows [0, F) then up rows [F, 2F); output planes [R][F]
   int F;
   uint16_t *out_hi, *out_lo;
+  // L2 prefetch hint: bytes [pf, pf + pf_bytes) are weights a LATER Linear of the chain streams; CTA c of n asks L2 for slice c
+  const char* pf;
+  unsigned pf_bytes;
 };
 
 // dynamic smem: [stage][ W 128x64 | Xhi RNx64 | Xlo RNx64 ] bf16, 1024-byte aligned tiles
@@ -96,8 +105,17 @@ struct GpArgs {
 // quarters (gate: lanes 0..63, up: lanes 64..127) in the drained pipeline stages, and all 128 threads then write
 // silu(gate) * up as bf16 hi + lo planes [R][F] for the down projection — the k_swiglu_split launch disappears.  Same
 // sums and the same expression as k_swiglu_split over one partial: bit-identical planes.
+//
+// MMA issue: ONE thread issues one tcgen05.mma (M = 128, K = 16) per ~152 cycles whatever its N, a second issuing warp runs at
+// the same rate beside it (scripts/micro/mma_issue.cu), and the in-kernel timeline (scripts/chain_timeline.py) showed the big
+// Linears waiting for exactly that serial issue (gate|up, K = 1024: 64 instructions = 5 us after the token planes arrive).
+// So the K blocks go alternately to BF_NI = 2 issuers, each with its own accumulator (TMEM columns [i * 2 RN, (i + 1) * 2 RN)),
+// and the epilogue adds them in fixed order: out = (hi_0 + hi_1) + (lo_0 + lo_1).  BF_NI is a constant of the library and
+// the number of stages is a multiple of it: a row's sums never depend on the row count, and a stage always belongs to the
+// same issuer (an mbarrier parity wait cannot tell the second from the third use of a stage apart, so one thread must see
+// every use of "its" stages in order).
 template <bool GU>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BF_THREADS, 1)
 k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
               const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -109,7 +127,9 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   __shared__ unsigned tl_slot_s;
   if (tl_block0() && threadIdx.x == 0) tl_slot_s = tl_enter(GU ? 2u : 1u);
 #endif
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the tcgen05.mma operands in uniform
+  // registers (otherwise every UTCHMMA sits in an ELECT / R2UR.BROADCAST loop: ~240 instead of ~150 cycles per instruction)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TC_BM, r0 = blockIdx.y * a.RN;
   const int RN = a.RN;
   const uint32_t w_bytes = TC_BM * TC_BK * 2, x_bytes = (uint32_t)RN * TC_BK * 2;
@@ -121,14 +141,23 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   // tcgen05.mma per K step leaves W.hi in accumulator columns [0, RN) and W.lo in [RN, 2 RN); the epilogue adds the halves.
   // (One thread issues one tcgen05.mma per ~150 cycles whatever its N — profiles/r02_mma_issue_microbench.log — and two
   // instructions per K step made these Linears issue-bound below the HBM stream rate.)
-  uint32_t ncols = 64;
-  while ((int)ncols < 2 * RN + 32) ncols <<= 1;
+  const int ni = nk < BF_NI ? nk : BF_NI;   // issuers with work
+  uint32_t ncols = 32;   // RN % 16 == 0 and the epilogue loads 16 columns at a time: no load reads past an accumulator
+  while ((int)ncols < BF_NI * 2 * RN) ncols <<= 1;
+  const uint64_t wpol = l2_policy_evict_first();
   auto load_w = [&](unsigned char* dst, int kb, uint64_t* bar) {
-    if (GU) {
-      tma_load_2d(dst, &map_w, kb * TC_BK, n0 / 2, bar);                                  // gate rows f0 .. f0+63
-      tma_load_2d(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, bar);  // up rows F+f0 ..
+    if (a.dbg & 32) {   // A/B: default L2 policy
+      if (GU) {
+        tma_load_2d(dst, &map_w, kb * TC_BK, n0 / 2, bar);
+        tma_load_2d(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, bar);
+      } else {
+        tma_load_2d(dst, &map_w, kb * TC_BK, n0, bar);
+      }
+    } else if (GU) {
+      tma_load_2d_hint(dst, &map_w, kb * TC_BK, n0 / 2, bar, wpol);                                  // gate rows f0 .. f0+63
+      tma_load_2d_hint(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, bar, wpol);  // up rows F+f0 ..
     } else {
-      tma_load_2d(dst, &map_w, kb * TC_BK, n0, bar);
+      tma_load_2d_hint(dst, &map_w, kb * TC_BK, n0, bar, wpol);
     }
   };
 
@@ -137,10 +166,10 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       tc_mbar_init(&full[i], 1);
       tc_mbar_init(&empty[i], 1);
     }
-    tc_mbar_init(&acc_full, 1);
+    tc_mbar_init(&acc_full, (uint32_t)ni);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -160,6 +189,30 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       for (int kb = 0; kb < pre; ++kb) {
         tc_mbar_expect_tx(&full[kb], w_bytes + 2 * x_bytes);
         load_w(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
+      }
+      // The ring holds NS of this CTA's nk weight blocks; the others would only be requested as stages drain, each refill
+      // paying the DRAM latency with at most NS x 16 KiB in flight (a latency-bound ~30 GB/s per CTA).  Ask L2 for them now
+      // (TMA tensor prefetch, same boxes) — the CTA is resident long before its producer kernel finishes and HBM idles
+      // through the small kernels in between — and for this CTA's slice of the next big Linear's matrix, whose CTAs cannot
+      // become resident before this kernel's CTAs leave.  Hints only: no result depends on them.
+      if (!(a.dbg & 64)) {
+        for (int kb = pre; kb < nk; ++kb) {
+          if (GU) {
+            tma_prefetch_2d(&map_w, (kb0 + kb) * TC_BK, n0 / 2);
+            tma_prefetch_2d(&map_w, (kb0 + kb) * TC_BK, a.F + n0 / 2);
+          } else {
+            tma_prefetch_2d(&map_w, (kb0 + kb) * TC_BK, n0);
+          }
+        }
+      }
+      if (a.pf_bytes != 0 && !(a.dbg & 128)) {
+        const unsigned nc = gridDim.x * gridDim.y * gridDim.z, c = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const unsigned chunk = (((a.pf_bytes + nc - 1) / nc) + 127u) & ~127u;
+        const unsigned long long off = (unsigned long long)c * chunk;
+        if (off < a.pf_bytes) {
+          const unsigned end = a.pf_bytes - off < chunk ? a.pf_bytes : (unsigned)(off + chunk);
+          for (unsigned o = (unsigned)off; o < end; o += 16384u) bulk_prefetch_l2(a.pf + o, (end - o < 16384u ? end - o : 16384u) & ~15u);
+        }
       }
       pdl_wait();
 #ifdef CSMB_TIMELINE
@@ -181,12 +234,14 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[s]);
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp <= BF_NI) {
+    // ===== MMA issuers: issuer i = warp - 1 takes K blocks i, i + BF_NI, ... into accumulator i =====
+    const int iss = warp - 1;
+    if (lane == 0 && iss < ni) {
       const uint32_t idesc = umma_idesc(2 * RN);
+      const uint32_t tacc = tmem_base + (uint32_t)(iss * 2 * RN);
       bool ok = true;
-      for (int kb = 0; kb < nk && ok; ++kb) {
+      for (int kb = iss; kb < nk && ok; kb += BF_NI) {
         const int s = kb % NS;
         const uint32_t par = (kb / NS) & 1;
         ok = tc_mbar_wait(&full[s], par, a.err);
@@ -197,39 +252,61 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t koff = (uint64_t)((k * 32) >> 4);
-          umma_f16(tmem_base, da + koff, dx + koff, idesc, (kb | k) != 0);
+          umma_f16(tacc, da + koff, dx + koff, idesc, (kb != iss) || (k != 0));
         }
         umma_commit(&empty[s]);
       }
       umma_commit(&acc_full);
     }
   } else {
-    // ===== epilogue: warps 2..5 -> TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: four warps -> TMEM lane quarters (warp % 4) =====
     pdl_wait();  // `part` may still be read by the previous kernel of the stream
     const int quarter = warp & 3;
     const bool ok = tc_mbar_wait(&acc_full, 0, a.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef CSMB_TIMELINE
-    if (tl_block0() && threadIdx.x == 64) tl_mark(tl_slot_s, 3);
+    if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 3);
 #endif
+    const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // 16 consecutive token columns c0 .. c0+15 of this thread's weight row: (sum of the issuers' W.hi) + (sum of their W.lo),
+    // each in issuer order; all 2 * ni TMEM loads are in flight together (one tcgen05.wait::ld)
+    auto load_cols = [&](int c0, float (&o)[16]) {
+      uint32_t vh[BF_NI][16], vl[BF_NI][16];
+#pragma unroll
+      for (int i = 0; i < BF_NI; ++i)
+        if (i < ni) {
+          tmem_ld16_nowait(tq + (uint32_t)(i * 2 * RN + c0), vh[i]);
+          tmem_ld16_nowait(tq + (uint32_t)(i * 2 * RN + RN + c0), vl[i]);
+        }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float h = __uint_as_float(vh[0][j]), l = __uint_as_float(vl[0][j]);
+#pragma unroll
+        for (int i = 1; i < BF_NI; ++i)
+          if (i < ni) {
+            h += __uint_as_float(vh[i][j]);
+            l += __uint_as_float(vl[i][j]);
+          }
+        o[j] = h + l;
+      }
+    };
     const int n = n0 + quarter * 32 + lane;
     if (GU) {
       // park gate (quarters 0, 1) and up (quarters 2, 3) values as [2][RN][64] fp32 in the drained stages
       float* ex = reinterpret_cast<float*>(smem);
       if (ok) {
         float* mine = ex + (size_t)(quarter >> 1) * RN * 64 + (quarter & 1) * 32 + lane;
-        for (int c0 = 0; c0 < RN; c0 += 32) {
-          uint32_t v[32], vl[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RN + c0), vl);
+        for (int c0 = 0; c0 < RN; c0 += 16) {
+          float o[16];
+          load_cols(c0, o);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < RN) mine[(size_t)(c0 + j) * 64] = __uint_as_float(v[j]) + __uint_as_float(vl[j]);
+          for (int j = 0; j < 16; ++j) mine[(size_t)(c0 + j) * 64] = o[j];
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (ok) {
-        const int f0 = n0 / 2, te = threadIdx.x - 64;  // 0 .. 127
+        const int f0 = n0 / 2, te = threadIdx.x - 32 * (1 + BF_NI);  // 0 .. 127
         const int rows = min(RN, a.R - r0);
         for (int idx = te; idx < rows * 16; idx += 128) {
           const int t = idx >> 4, f4 = (idx & 15) * 4;
@@ -242,31 +319,30 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       }
     } else if (ok) {
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
-      for (int c0 = 0; c0 < RN; c0 += 32) {
-        uint32_t v[32], vl[32];
+      for (int c0 = 0; c0 < RN; c0 += 16) {
+        float o[16];
         if (a.dbg & 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = vl[j] = 0u;
+          for (int j = 0; j < 16; ++j) o[j] = 0.f;
         } else {
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RN + c0), vl);
+          load_cols(c0, o);
         }
         if (n < a.N && !(a.dbg & 1)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const int r = r0 + c0 + j;
-            if (c0 + j < RN && r < a.R) dst0[(size_t)r * a.N] = __uint_as_float(v[j]) + __uint_as_float(vl[j]);
+            if (r < a.R) dst0[(size_t)r * a.N] = o[j];
           }
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #ifdef CSMB_TIMELINE
-    if (tl_block0() && threadIdx.x == 64) tl_mark(tl_slot_s, 4);
+    if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 4);
 #endif
   }
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -744,6 +820,159 @@ __global__ void __launch_bounds__(256) k_attn_decode_small(PartIn qkv, const flo
       out_lo[o + lane + 32 * ii] = ll;
     }
     __syncwarp();  // sc is reused by this warp's next row
+  }
+  TL_MARK(4)
+}
+
+// The same block for long caches (the backbone: up to max_pos positions), one new row per sequence.  The cache is walked in
+// chunks of AC_CHUNK positions staged in shared memory with cp.async (every row of a chunk in flight at once; chunk 0 —
+// keys AND values — is requested before the new row's qkv partials are summed): a cache of S positions costs about
+// 2 ceil(S / AC_CHUNK) - 1 L2 / DRAM round trips instead of ceil(S / 32) + ceil(S / 8).  Scores for all positions first,
+// softmax, then the values in position order: the sums and their order are those of k_attn_decode_fused (bit-identical).
+constexpr int AC_CHUNK = 64;
+template <int HD>
+__global__ void __launch_bounds__(256) k_attn_decode_chunked(PartIn qkv, const float* __restrict__ rope, float* pool,
+                                                             const int32_t* __restrict__ block_table, int max_pages,
+                                                             const int32_t* __restrict__ pos_arr, int pos0, int H, int Hkv,
+                                                             uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                                             int max_pos) {
+  constexpr int PITCH = HD + 4, half = HD / 2;
+  extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  TL_ENTER(4u)
+  pdl_wait();
+  TL_MARK(2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / Hkv, kvh = blockIdx.x % Hkv;
+  const int G = H / Hkv, h = kvh * G + warp;
+  float* sK = smem;                                   // [AC_CHUNK][PITCH]
+  float* sV = sK + AC_CHUNK * PITCH;                  // [AC_CHUNK][PITCH]
+  float* sq_all = sV + AC_CHUNK * PITCH;              // [G][HD] rotated queries
+  float* knew = sq_all + (size_t)G * HD;              // [HD] rotated key of the new row
+  float* vnew = knew + HD;                            // [HD]
+  float* sc = vnew + HD + (size_t)warp * max_pos;     // this warp's scores [max_pos]
+  const size_t page_stride = (size_t)2 * Hkv * CSMB_PAGE * HD, head_off = (size_t)kvh * CSMB_PAGE * HD;
+  const size_t v_off = (size_t)Hkv * CSMB_PAGE * HD;
+  const float scale = rsqrtf((float)HD);
+  const int posb = pos_arr ? pos_arr[b] : pos0, S = posb + 1;
+  const int32_t* bt = block_table ? block_table + (size_t)b * max_pages : nullptr;
+  // cached rows j0 .. min(j0 + AC_CHUNK, posb) - 1 of K (what & 1) and / or V (what & 2) -> shared memory, asynchronously
+  auto stage_chunk = [&](int j0, int what) {
+    const int n = (posb - j0 < AC_CHUNK ? posb - j0 : AC_CHUNK) * (HD / 4);
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const int jl = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4, j = j0 + jl;
+      const int page = bt ? bt[j / CSMB_PAGE] : b * max_pages + j / CSMB_PAGE;
+      const float* src = pool + (size_t)page * page_stride + head_off + (size_t)(j % CSMB_PAGE) * HD + c4;
+      if (what & 1) cp_async16(sK + jl * PITCH + c4, src);
+      if (what & 2) cp_async16(sV + jl * PITCH + c4, src + v_off);
+    }
+  };
+  stage_chunk(0, 3);
+  // the new row's qkv partials and its RoPE row
+  const int per_row = (G + 2) * half;
+  float2* stg = reinterpret_cast<float2*>(sc - (size_t)warp * max_pos + (size_t)G * max_pos);   // [S_split][per_row]
+  float2* srope = stg + (size_t)qkv.S * per_row;                                                // [half]
+  for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+    const int slot = idx / half, pr = idx % half;
+    const int col = (slot < G ? (kvh * G + slot) : (slot == G ? H + kvh : H + Hkv + kvh)) * HD + 2 * pr;
+    const float* src = qkv.p + (size_t)b * qkv.ld + col;
+    for (int z = 0; z < qkv.S; ++z) cp_async8(stg + (size_t)z * per_row + idx, src + (size_t)z * qkv.stride);
+  }
+  for (int idx = threadIdx.x; idx < half; idx += blockDim.x) cp_async8(srope + idx, rope + ((size_t)posb * half + idx) * 2);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+    const int slot = idx / half, pr = idx % half;
+    float2 v = make_float2(0.f, 0.f);
+    for (int z = 0; z < qkv.S; ++z) {   // part_sum2's order
+      const float2 t = stg[(size_t)z * per_row + idx];
+      v.x += t.x;
+      v.y += t.y;
+    }
+    const float2 cs = srope[pr];
+    const float2 rot = make_float2(v.x * cs.x - v.y * cs.y, v.y * cs.x + v.x * cs.y);
+    if (slot < G) {
+      *reinterpret_cast<float2*>(sq_all + (size_t)slot * HD + 2 * pr) = rot;
+    } else {
+      const int lp = posb / CSMB_PAGE;
+      const int page = bt ? bt[lp] : b * max_pages + lp;
+      float* kdst = pool + (size_t)page * page_stride + head_off + (size_t)(posb % CSMB_PAGE) * HD;
+      if (slot == G) {
+        *reinterpret_cast<float2*>(kdst + 2 * pr) = rot;
+        *reinterpret_cast<float2*>(knew + 2 * pr) = rot;
+      } else {
+        *reinterpret_cast<float2*>(kdst + v_off + 2 * pr) = v;
+        *reinterpret_cast<float2*>(vnew + 2 * pr) = v;
+      }
+    }
+  }
+  __syncthreads();
+  TL_MARK(3)
+  const float* sq = sq_all + (size_t)warp * HD;
+  // ---- scores, chunk by chunk (chunk 0 is already in shared memory)
+  float m = -INFINITY;
+  for (int j0 = 0; j0 < S; j0 += AC_CHUNK) {
+    if (j0 > 0) {
+      __syncthreads();   // everybody is done with the previous K chunk
+      stage_chunk(j0, 1);
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    const int j1 = j0 + AC_CHUNK < S ? j0 + AC_CHUNK : S;
+    for (int j = j0 + lane; j < j1; j += 32) {
+      const float* kp = j == posb ? knew : sK + (j - j0) * PITCH;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+        dot = fmaf(kv.x, sq[c], dot);
+        dot = fmaf(kv.y, sq[c + 1], dot);
+        dot = fmaf(kv.z, sq[c + 2], dot);
+        dot = fmaf(kv.w, sq[c + 3], dot);
+      }
+      dot *= scale;
+      sc[j] = dot;
+      m = fmaxf(m, dot);
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < S; j += 32) {
+    const float e = expf(sc[j] - m);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  constexpr int PER = HD / 32;
+  float acc[PER];
+#pragma unroll
+  for (int ii = 0; ii < PER; ++ii) acc[ii] = 0.f;
+  // ---- values in position order (chunk 0 of V was staged with chunk 0 of K)
+  for (int j0 = 0; j0 < S; j0 += AC_CHUNK) {
+    if (j0 > 0) {
+      __syncthreads();
+      stage_chunk(j0, 2);
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    const int j1 = j0 + AC_CHUNK < S ? j0 + AC_CHUNK : S;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+      const float pj = sc[j];
+      const float* vp = j == posb ? vnew : sV + (j - j0) * PITCH;
+#pragma unroll
+      for (int ii = 0; ii < PER; ++ii) acc[ii] = fmaf(pj, vp[lane + 32 * ii], acc[ii]);
+    }
+  }
+  const size_t o = (size_t)b * H * HD + (size_t)h * HD;
+#pragma unroll
+  for (int ii = 0; ii < PER; ++ii) {
+    uint16_t hh, ll;
+    split_bf16(acc[ii] * inv, hh, ll);
+    out_hi[o + lane + 32 * ii] = hh;
+    out_lo[o + lane + 32 * ii] = ll;
   }
   TL_MARK(4)
 }
@@ -1358,7 +1587,7 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base, const ChainCfg& c
 
 // y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
-                   const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr) {
+                   const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, const void* pf = nullptr, size_t pf_bytes = 0) {
   CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int S = bf_pick_split(N, K);
   CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
@@ -1370,18 +1599,20 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
+  nstages -= nstages % BF_NI;   // a stage always belongs to the same issuer
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & 3, 0, nullptr, nullptr};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
-  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   *out = PartIn{w.part, S, (size_t)R * N, N};
   return CSMB_OK;
 }
 
 // SwiGLU MLP first half in one launch: w.hi2 / w.lo2 [R][F] = split(silu(x Wg^T) * (x Wu^T)), Wgu = gate rows then up rows
-static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K, cudaStream_t st) {
+static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K, cudaStream_t st, const void* pf = nullptr,
+                      size_t pf_bytes = 0) {
   CSMB_REQUIRE(R > 0 && F % (TC_BM / 2) == 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(Wgu) & 15) == 0);
   const int RN = R <= 128 ? ((R + 15) / 16) * 16 : 128;   // token rows per tile: 2 RN <= 256 accumulator columns (hi | lo)
   CUtensorMap mw, mhi, mlo;
@@ -1390,12 +1621,13 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
   nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
+  nstages -= nstages % BF_NI;   // a stage always belongs to the same issuer
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
-  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, 0, F, w.hi2, w.lo2};
+  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
-  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true>, grid, dim3(TC_THREADS), smem, st, mw, mhi, mlo, a));
+  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   return CSMB_OK;
 }
 
@@ -1438,6 +1670,25 @@ static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool
       return CSMB_ERR_UNSUPPORTED;
     return CSMB_OK;
   }
+  if (rps == 1 && !(w.cc.dbg & 8)) {
+    // long caches, one new row per sequence (the backbone): chunks of the cache staged in shared memory
+    const size_t smem = ((size_t)2 * AC_CHUNK * (L.head_dim + 4) + (size_t)(G + 2) * L.head_dim + (size_t)G * max_pos) * sizeof(float) +
+                        ((size_t)qkv.S * (G + 2) * (L.head_dim / 2) + (size_t)(L.head_dim / 2)) * sizeof(float2);
+    if (smem <= 160 * 1024) {
+      if (L.head_dim == 64) {
+        CSMB_CUDA(cudaFuncSetAttribute(k_attn_decode_chunked<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CSMB_CUDA(bf_launch(w.cc, k_attn_decode_chunked<64>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                            L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
+        return CSMB_OK;
+      }
+      if (L.head_dim == 128) {
+        CSMB_CUDA(cudaFuncSetAttribute(k_attn_decode_chunked<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CSMB_CUDA(bf_launch(w.cc, k_attn_decode_chunked<128>, grid, block, smem, st, qkv, L.rope, pool, block_table, max_pages, pos_arr, pos0,
+                            L.n_heads, L.n_kv_heads, w.hi, w.lo, max_pos));
+        return CSMB_OK;
+      }
+    }
+  }
   const size_t smem = ((size_t)rps * G * L.head_dim + (size_t)G * max_pos) * sizeof(float);
   CSMB_REQUIRE(smem <= 48 * 1024);
   if (L.head_dim == 64)
@@ -1470,7 +1721,8 @@ static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool
       const size_t total4 = (size_t)R * F / 4;
       CSMB_CUDA(bf_launch(w.cc, k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi2, w.lo2));
     } else {
-      if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st))) return rc;
+      // its CTAs also pull the down matrix towards L2: the down Linear's CTAs only become resident as these leave
+      if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st, L.wdown[l], (size_t)d * F * 2))) return rc;
     }
     if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st, w.hi2, w.lo2))) return rc;
     if (l + 1 < L.n_layers) {

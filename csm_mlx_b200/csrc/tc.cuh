@@ -90,6 +90,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(s32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): weights are read once per frame-step — evict-first keeps them from
+// pushing the step's small, re-read data (KV rows, partials, planes, norm weights, RoPE rows) out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          s32(dst)),
+      "l"(map), "r"(s32(bar)), "r"(x), "r"(y), "l"(policy)
+      : "memory");
+}
+// L2 prefetch of a tensor-map box / of a byte range (fire and forget: no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {   // p 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -134,6 +155,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 columns without the wait: the caller issues several loads and then one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 // 32 lanes x 16 consecutive fp32 columns of the accumulator -> registers (waits for the load)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -4,6 +4,7 @@ Block (0,0,0) of every chain kernel records %globaltimer at entry, after griddep
 accumulator complete; attention: q/k/v staged; sampler: logits summed) and at its end.  Per kernel class this prints
   lead   = wait returned - entry            (how long the CTA was resident before its producer finished)
   body   = end - wait returned              (the kernel's own dependent path, block 0)
+  first  = (Linears) first pipeline stage complete - wait returned
   mid    = mid point - wait returned
   gap    = next kernel's wait returned - this kernel's end   (tail of the other CTAs + the kernel boundary)
   period = next kernel's wait returned - this kernel's wait returned
@@ -14,7 +15,7 @@ import sys
 from collections import defaultdict
 
 HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["CSMB_LIB_PATH"] = os.path.join(HERE, "csm_mlx_b200", "libcsm_b200_tl.so")
+os.environ["CSMB_LIB_PATH"] = os.environ.get("TL_LIB") or os.path.join(HERE, "csm_mlx_b200", "libcsm_b200_tl.so")
 sys.path.insert(0, HERE)
 import numpy as np
 import torch
@@ -74,9 +75,11 @@ for i in range(n - 1):
     a["body"].append(t_e - t_w)
     if t_m > 0:
         a["mid"].append(t_m - t_w)
+    if tl[i, 5] > 0:
+        a["first"].append(tl[i, 5] - t_w)
     a["gap"].append(nxt_w - t_e)
     a["period"].append(nxt_w - t_w)
-print(f"{'stack':9s} {'kernel':16s} {'grid':>5s} {'count/step':>10s} {'lead':>7s} {'mid':>7s} {'body':>7s} {'gap':>7s} {'period':>7s} {'us/step':>8s}")
+print(f"{'stack':9s} {'kernel':16s} {'grid':>5s} {'count/step':>10s} {'lead':>7s} {'first':>7s} {'mid':>7s} {'body':>7s} {'gap':>7s} {'period':>7s} {'us/step':>8s}")
 tot = 0.0
 for key in sorted(agg, key=lambda k: -np.sum(agg[k]["period"])):
     a = agg[key]
@@ -84,6 +87,6 @@ for key in sorted(agg, key=lambda k: -np.sum(agg[k]["period"])):
     mean = lambda x: float(np.mean(x)) / 1e3 if len(x) else float("nan")
     per = float(np.sum(a["period"])) / STEPS / 1e3
     tot += per
-    print(f"{key[0]:9s} {key[1]:16s} {key[2]:5d} {cnt:10.1f} {mean(a['lead']):7.2f} {mean(a['mid']):7.2f} {mean(a['body']):7.2f} "
+    print(f"{key[0]:9s} {key[1]:16s} {key[2]:5d} {cnt:10.1f} {mean(a['lead']):7.2f} {mean(a['first']):7.2f} {mean(a['mid']):7.2f} {mean(a['body']):7.2f} "
           f"{mean(a['gap']):7.2f} {mean(a['period']):7.2f} {per:8.1f}")
 print(f"sum of periods: {tot / 1e3:.3f} ms per step")
