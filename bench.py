@@ -62,7 +62,7 @@ LATENCY_WORKLOAD = "configs[1]: csm_1b bf16 batch=1 streaming generation, 10 s a
 # Sum of all 64 x 125 x 32 greedy tokens of the job.  The engine's numeric path does not depend on the batch size or on the
 # sharding (csm_mlx_b200/serving.py, "Batch invariance"), so this constant holds at every --gpus N; a different value means the
 # tokens changed.
-CFG4_TOKENS_CHECKSUM = 261741370  # profiles/r02_bench_1gpu.json; identical at --gpus 1, 2, 4, 8
+CFG4_TOKENS_CHECKSUM = 261764229  # profiles/r02_bench_1gpu.json; identical at --gpus 1, 2, 4, 8 (re-baselined with the 2-issuer Linears)
 
 
 def weight_bytes(proj_table: bool = False) -> float:

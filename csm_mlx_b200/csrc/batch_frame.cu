@@ -27,7 +27,7 @@
 
 namespace csmb {
 
-constexpr int BF_MAX_STAGES = 6;
+constexpr int BF_MAX_STAGES = 8;
 #ifndef CSMB_BF_NI
 #define CSMB_BF_NI 2
 #endif
@@ -1585,6 +1585,16 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base, const ChainCfg& c
   return w;
 }
 
+// Pipeline depth of a Linear CTA: what the shared-memory budget allows, at most BF_MAX_STAGES, a multiple of BF_NI.  (Measured
+// on the 2-issuer kernel, B = 8: 8 stages 4.30 ms per frame-step, 6 stages 4.40; shrinking the ring of a Linear with few K
+// blocks to make room for other kernels' CTAs on its SM: 4.37.  B = 64 has 32 KiB stages: 6 either way.)
+static int bf_ring_depth(int fit, int dbg) {
+  int n = fit > BF_MAX_STAGES ? BF_MAX_STAGES : fit;
+  if ((dbg & 256) && n > 6) n = 6;   // A/B: the 6-stage ring
+  n -= n % BF_NI;                    // a stage always belongs to the same issuer
+  return n;
+}
+
 // y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
                    const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, const void* pf = nullptr, size_t pf_bytes = 0) {
@@ -1598,8 +1608,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
     return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
-  nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
-  nstages -= nstages % BF_NI;   // a stage always belongs to the same issuer
+  nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2);
   GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
@@ -1620,8 +1629,7 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
     return CSMB_ERR_UNSUPPORTED;
   const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
-  nstages = nstages > BF_MAX_STAGES ? BF_MAX_STAGES : nstages;
-  nstages -= nstages % BF_NI;   // a stage always belongs to the same issuer
+  nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
   GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
