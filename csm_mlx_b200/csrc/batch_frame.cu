@@ -27,7 +27,7 @@
 
 namespace csmb {
 
-constexpr int BF_MAX_STAGES = 8;
+constexpr int BF_MAX_STAGES = 10;
 #ifndef CSMB_BF_NI
 #define CSMB_BF_NI 2
 #endif
@@ -1586,11 +1586,12 @@ static FastWs bf_carve(const csmb_model& m, int B, void* base, const ChainCfg& c
 }
 
 // Pipeline depth of a Linear CTA: what the shared-memory budget allows, at most BF_MAX_STAGES, a multiple of BF_NI.  (Measured
-// on the 2-issuer kernel, B = 8: 8 stages 4.30 ms per frame-step, 6 stages 4.40; shrinking the ring of a Linear with few K
-// blocks to make room for other kernels' CTAs on its SM: 4.37.  B = 64 has 32 KiB stages: 6 either way.)
+// on the 2-issuer kernel, B = 8: 6 stages 4.40 ms per frame-step, 8 stages 4.30, 10 stages 4.25; shrinking the ring of a
+// Linear with few K blocks to make room for other kernels' CTAs on its SM: 4.37.  B = 64 has 32 KiB stages: 6 either way.
+// profiles/r02_ring_depth.log)
 static int bf_ring_depth(int fit, int dbg) {
   int n = fit > BF_MAX_STAGES ? BF_MAX_STAGES : fit;
-  if ((dbg & 256) && n > 6) n = 6;   // A/B: the 6-stage ring
+  if ((dbg & 256) && n > 8) n = 8;   // A/B: at most 8 stages
   n -= n % BF_NI;                    // a stage always belongs to the same issuer
   return n;
 }
