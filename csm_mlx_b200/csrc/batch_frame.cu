@@ -130,7 +130,8 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the tcgen05.mma operands in uniform
   // registers (otherwise every UTCHMMA sits in an ELECT / R2UR.BROADCAST loop: ~240 instead of ~150 cycles per instruction)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TC_BM, r0 = blockIdx.y * a.RN;
+  // (timing experiment, flag 2048: token-plane boxes out of bounds -> TMA zero-fills them without reading L2; results are wrong)
+  const int n0 = blockIdx.x * TC_BM, r0 = (a.dbg & 2048) ? (1 << 20) : blockIdx.y * a.RN;
   const int RN = a.RN;
   const uint32_t w_bytes = TC_BM * TC_BK * 2, x_bytes = (uint32_t)RN * TC_BK * 2;
   const uint32_t x_off = w_bytes, stage_bytes = (w_bytes + 2 * x_bytes + 1023u) & ~1023u;
@@ -1611,7 +1612,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128 | 2048), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
@@ -1632,7 +1633,7 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
-  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes};
+  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128 | 2048), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);

@@ -201,8 +201,13 @@ int csmb_decode_frame(const csmb_model* m, const csmb_batch* b, const int32_t* p
 /* Per-call switches of the fused chain; caller-owned, read during the call only; NULL = all defaults. */
 typedef struct {
   int no_pdl;               /* 1 = plain stream order instead of programmatic dependent launch (A/B timing) */
-  int flags;                /* debug: bit 0 = Linears skip their partial stores, bit 1 = and their TMEM loads (timing
-                               experiments, results are wrong); bit 2 = SwiGLU as a separate launch (A/B: same tokens) */
+  int flags;                /* debug / A-B switches, 0 = the shipped chain.  Timing experiments whose results are WRONG: 1 = Linears
+                               skip their partial stores, 2 = and their TMEM loads, 2048 = token planes not read (zero fill).
+                               Same tokens, other kernels / hints: 4 = SwiGLU as a separate launch, 8 = the round-1 attention
+                               kernel (dependent L2 round trips) instead of the shared-memory staged ones, 16 = partial sums
+                               with plain loads instead of cp.async staging, 32 = default L2 policy for the weight stream,
+                               64 / 128 = no L2 prefetch of a Linear's own remaining / the next Linear's weights,
+                               256 = at most 8 pipeline stages */
   int smem_kb;              /* shared-memory budget of a Linear CTA in KiB (48..200, 0 = 200): <= 100 lets two Linear CTAs
                                (of this or of another stream's chain) share an SM */
   const float* proj_table;  /* optional DEVICE table of csmb_build_proj_table: depth steps >= 2 read projection(embedding)

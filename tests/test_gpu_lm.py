@@ -313,6 +313,40 @@ def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, monkeypa
     assert int((fused[1:] != fused[:-1]).sum()) > 0  # frames differ from step to step: the loop really decoded
 
 
+@pytest.mark.parametrize("flags", [8, 16, 32 | 64 | 128 | 256])
+def test_chain_staged_kernels_are_bit_identical_to_the_plain_ones(model_1b, device, monkeypatch, flags):
+    """The shared-memory staged kernels of the chain (k_attn_decode_small: the depth decoder's whole cache requested at once
+    with cp.async; k_attn_decode_chunked: the backbone's cache in 64-position chunks; cp.async staged split-K partial sums in
+    the norm / sampling kernels) and its L2 hints do the round-1 kernels' sums in the same order: identical tokens against
+    csmb_chain_opts.flags 8 (plain attention kernel), 16 (plain partial sums) and the hints switched off — for ragged
+    prompts whose caches cross the 64- and 128-position chunk boundaries while decoding (3 sequences, 6 frames)."""
+    spec = SamplerSpec(temperature=0.0)
+    lens = (58, 61, 125)   # + BOS, EOS: 60 / 63 / 127 rows -> positions 60..65, 63..68, 127..132 while decoding
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(300 + i, n), i) for i, n in enumerate(lens)]
+
+    def run(f):
+        monkeypatch.setenv("CSMB_CHAIN_FLAGS", str(f))
+        st = LMState(model_1b, len(prompts), max_len=160, row_invariant=True)
+        assert st.fast_supported(spec)
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        frame = torch.zeros((len(prompts), 32), device=device, dtype=torch.int32)
+        st.sample_c0(frame, spec)
+        st.depth_decode(frame, spec)
+        out, prev = [frame.clone()], frame
+        for _ in range(6):
+            nxt = torch.zeros_like(prev)
+            st.decode_frame(prev, nxt, spec)
+            out.append(nxt.clone())
+            prev = nxt
+        torch.cuda.synchronize()
+        st.check_status()
+        return torch.stack(out).cpu()
+
+    shipped, plain = run(0), run(flags)
+    assert torch.equal(shipped, plain)
+    assert int((shipped[1:] != shipped[:-1]).sum()) > 0
+
+
 def test_chain_projected_embedding_table_is_bit_exact(model_1b, monkeypatch):
     """csmb_build_proj_table: depth steps >= 2 read projection(embed_audio(cb, token)) rows from a table built with the
     chain's own projection Linear instead of running that Linear (60 launches less per frame-step): identical tokens,
