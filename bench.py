@@ -237,6 +237,53 @@ def chain_step_ms(model, dev, B: int, n: int = 10):
     return t_step, t_pre, launches
 
 
+def fp8_config(model, dev):
+    """Weight-only FP8 (csm_mlx_b200.quantize, the nn.quantize analogue of the reference README): a second, quantised copy of
+    the model on the row-based GEMV path, batch 1, against the bf16 model on the same per-op path and on the frame kernel."""
+    from csm_mlx_b200 import CSM, csm_1b, quantize, tokenizers
+    from csm_mlx_b200.random_init import random_csm_weights
+    from csm_mlx_b200.runtime import LMState, SamplerSpec
+    from tests.workloads import cfg1_prompt_ids
+
+    tok, mask = tokenizers.tokenize_text_segment(cfg1_prompt_ids(), 0)
+    spec = SamplerSpec(temperature=0.0)
+
+    def per_op_ms(m):
+        st = LMState(m, 1, max_len=tok.shape[0] + 64)
+        st.prefill([tok], [mask])
+        fr = torch.zeros((1, 32), device=dev, dtype=torch.int32)
+        st.sample_c0(fr, spec)
+        st.depth_decode(fr, spec)
+        state = {"f": fr}
+        os.environ["CSMB_DISABLE_FAST"] = "1"     # the bf16 model too on the row-based path (CUDA graph of csmb_decode_frame)
+        try:
+            for _ in range(3):
+                state["f"] = st.decode_frame_graphed(state["f"], spec)
+
+            def one():
+                state["f"] = st.decode_frame_graphed(state["f"], spec)
+            ms, _ = timed(dev, one, 20)
+        finally:
+            os.environ.pop("CSMB_DISABLE_FAST", None)
+        st.check_status()
+        return ms
+
+    q = quantize(CSM(csm_1b(), device=dev).load_weights(random_csm_weights()))
+    lin_bytes = lambda m: sum(t.numel() * t.element_size() for stck in (m.backbone, m.decoder)
+                              for ts in (stck.wqkv, stck.wo, stck.wgu, stck.wdown) for t in ts)
+    ms_q, ms_b = per_op_ms(q), per_op_ms(model)
+    bytes_q = lin_bytes(q)
+    alg_q = lm_algorithmic_bytes(int(tok.shape[0]), 32) - 9_106_743_296 / 2     # e4m3 bytes (+ 0.2 % fp32 scales, not counted)
+    del q
+    torch.cuda.empty_cache()
+    return {"format": "E4M3 bytes + one fp32 scale per output channel (include/csm_b200.h CSMB_WEIGHTS_E4M3); embeddings, norms bf16 / fp32",
+            "linear_weight_bytes": {"bf16": lin_bytes(model), "e4m3": bytes_q}, "path": "row-based GEMV kernels in a CUDA graph (csmb_decode_frame), batch 1",
+            "ms_per_frame_e4m3": ms_q, "ms_per_frame_bf16_same_path": ms_b,
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": alg_q, "achieved": alg_q / (ms_q * 1e-3) / 1e9, "unit": "GB/s",
+                         "frac": alg_q / (ms_q * 1e-3) / 1e9 / 6557.8},
+            "note": "parity: tests/test_quantization.py (oracle on the dequantised weights); the fused kernels decline a quantised model (DESIGN.md §8)"}
+
+
 def latency_path(model, mimi, dev, lib, steps: int):
     """BASELINE.json configs[1]: batch 1, 10 s, streaming, through the persistent frame kernel (round 1's headline)."""
     from csm_mlx_b200 import generation, tokenizers
@@ -491,6 +538,7 @@ def run_ours(args):
         if rank == 0 and world == 1:
             other["latency_path"] = latency_path(model, mimi, dev, lib, args.steps)
             other["context_2x5s"] = context_config(model, mimi, dev)
+            other["fp8_weight_only"] = fp8_config(model, dev)
             sweep = {}
             for Bs in (1, 8, 16, 32, 128, 256):
                 t, _, _ = chain_step_ms(model, dev, Bs, 6)

@@ -8,7 +8,7 @@ from csm_mlx_b200 import *  # noqa: F401,F403
 from csm_mlx_b200 import (attention, config, generation, models, sample_utils, segment, serving, tokenizers, utils)  # noqa: F401
 from csm_mlx_b200 import __all__  # noqa: F401
 from csm_mlx_b200 import generate_batch, generate_frame, make_cache, make_logits_processors, make_sampler  # noqa: F401
-from csm_mlx_b200 import ContextCache, Engine  # noqa: F401  (throughput form of the path; not in the reference)
+from csm_mlx_b200 import ContextCache, Engine, quantize  # noqa: F401  (throughput form of the path; nn.quantize analogue)
 
 for _name in ("attention", "config", "generation", "models", "sample_utils", "segment", "serving", "tokenizers", "utils"):
     _sys.modules[f"csm_mlx.{_name}"] = getattr(_impl, _name)

@@ -27,6 +27,7 @@ TrainArgs = _out_of_scope("TrainArgs")
 
 
 from .adapters import load_adapters  # noqa: E402  (inference-side half of finetune/utils.py:84-108: adapters are merged)
+from .quantization import quantize  # noqa: E402  (what README.md:92-128 does with mlx.nn.quantize(csm): weight-only FP8 here)
 
 
 __all__ = [

@@ -42,7 +42,7 @@ class Model(C.Structure):
     _fields_ = [("backbone", Llama), ("decoder", Llama), ("text_emb", C.c_void_p), ("audio_emb", C.c_void_p),
                 ("projection", C.c_void_p), ("c0_head", C.c_void_p), ("audio_head_t", C.c_void_p),
                 ("n_text_vocab", C.c_int), ("audio_vocab", C.c_int), ("n_codebooks", C.c_int),
-                ("max_pos", C.c_int)]
+                ("max_pos", C.c_int), ("weight_format", C.c_int), ("reserved", C.c_int)]
 
 
 class Batch(C.Structure):
@@ -53,7 +53,8 @@ class Batch(C.Structure):
 
 
 BATCH_ROW_INVARIANT = 1
-ABI_VERSION = 2
+WEIGHTS_BF16, WEIGHTS_E4M3 = 0, 1
+ABI_VERSION = 3
 
 
 class ChainOpts(C.Structure):
@@ -93,6 +94,8 @@ _SIGS = {
     "csmb_embed_audio": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_rmsnorm": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, C.c_float, _I, _P]),
     "csmb_linear": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "csmb_e4m3_blob_bytes": (C.c_size_t, [_I, _I]),
+    "csmb_linear_e4m3": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "csmb_linear_tc_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "csmb_linear_tc": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _I, _P]),
     "csmb_swiglu": (C.c_int, [_P, _P, _I, _I, _I, _P]),

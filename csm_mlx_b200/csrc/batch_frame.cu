@@ -1753,6 +1753,7 @@ static bool bf_supported(const csmb_model& m, const csmb_sampler& s) {
   };
   // fused samplers: greedy; temperature with optional top-k, top-p and / or min-p (min_keep 1)
   const bool filtered = s.temperature != 0.f && s.min_p > 0.f && s.min_keep > 1;
+  if (m.weight_format != CSMB_WEIGHTS_BF16) return false;   // weight-only FP8 models run on the row-based GEMV path
   return llama_ok(b) && llama_ok(d) && b.d_model == 2048 && m.audio_vocab <= 8192 && m.n_codebooks >= 2 && !filtered &&
          s.temperature >= 0.f;
 }
@@ -1944,6 +1945,7 @@ size_t csmb_proj_table_workspace_bytes(const csmb_model* m) {
 int csmb_build_proj_table(const csmb_model* m, float* table, void* workspace, size_t workspace_bytes, int device, void* stream) {
   CSMB_ENTER(device);
   CSMB_REQUIRE(m && table && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  if (m->weight_format != CSMB_WEIGHTS_BF16) return CSMB_ERR_UNSUPPORTED;
   CSMB_REQUIRE(workspace_bytes >= csmb_proj_table_workspace_bytes(m));
   const int V = m->audio_vocab, db = m->backbone.d_model, dd = m->decoder.d_model, ncb = m->n_codebooks;
   CSMB_REQUIRE(db % TC_BK == 0 && dd % 4 == 0);

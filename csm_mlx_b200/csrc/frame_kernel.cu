@@ -1390,7 +1390,7 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   const bool shape_ok = B.d_model == 2048 && B.n_heads == 32 && B.n_kv_heads == 8 && B.head_dim == 64 &&
                         D.d_model == 1024 && D.n_heads == 8 && D.n_kv_heads == 2 && D.head_dim == 128 &&
                         D.d_ff == 8192 && B.d_ff == 8192 && m->n_codebooks <= 32 && m->n_codebooks >= 3 &&
-                        m->audio_vocab <= 9 * NCT;
+                        m->audio_vocab <= 9 * NCT && m->weight_format == CSMB_WEIGHTS_BF16;   // FP8 blobs: row-based path
   if (!shape_ok) return CSMB_ERR_UNSUPPORTED;
   // fused samplers: greedy; temperature with optional top-k, top-p and / or min-p.  Only min-p with min_tokens_to_keep > 1
   // (it needs the sorted order) stays on the per-op path (csmb_decode_frame).

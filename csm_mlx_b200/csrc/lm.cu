@@ -25,6 +25,7 @@ struct Workspace {
   size_t tc_bytes;
   size_t bytes;
   bool row_invariant;                      // CSMB_BATCH_ROW_INVARIANT: every Linear on the tensor-core path, whatever R
+  bool e4m3;                               // CSMB_WEIGHTS_E4M3: the Linear matrices are weight-only FP8 blobs (GEMV kernels)
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -89,11 +90,14 @@ static Workspace carve(const csmb_model& m, int max_rows, void* base) {
   w.tc_bytes = tcb;
   w.bytes = off;
   w.row_invariant = false;
+  w.e4m3 = m.weight_format == CSMB_WEIGHTS_E4M3;
   return w;
 }
 
 static int lin(const Workspace& w, const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
                int accumulate, cudaStream_t st) {
+  // weight-only FP8: e4m3 rows widened in registers (a row's sums do not depend on the other rows of the call either)
+  if (w.e4m3) return launch_linear_e4m3(x, ldx, W, y, ldy, R, N, K, accumulate, st);
   if ((R >= TC_MIN_ROWS || w.row_invariant) && K % 64 == 0 && w.tc != nullptr && w.tc_bytes >= linear_tc_workspace_bytes(R, N, K))
     return launch_linear_tc(x, ldx, W, y, ldy, R, N, K, accumulate, w.tc, w.tc_bytes, st);
   return launch_linear(x, ldx, W, y, ldy, R, N, K, accumulate, st);
@@ -162,6 +166,10 @@ static int check_model(const csmb_model* m) {
   CSMB_REQUIRE(m->n_codebooks >= 2 && m->n_codebooks <= CSMB_MAX_CODEBOOKS);
   CSMB_REQUIRE(m->backbone.n_heads * m->backbone.head_dim == m->backbone.d_model);
   CSMB_REQUIRE(m->decoder.n_heads * m->decoder.head_dim == m->decoder.d_model);
+  CSMB_REQUIRE(m->weight_format == CSMB_WEIGHTS_BF16 || m->weight_format == CSMB_WEIGHTS_E4M3);
+  if (m->weight_format == CSMB_WEIGHTS_E4M3)
+    CSMB_REQUIRE(m->backbone.d_model % 16 == 0 && m->decoder.d_model % 16 == 0 && m->backbone.d_ff % 16 == 0 &&
+                 m->decoder.d_ff % 16 == 0);
   return CSMB_OK;
 }
 
@@ -220,7 +228,10 @@ static int depth_decode(const csmb_model& m, const csmb_batch& b, const Workspac
     if ((rc = launch_rmsnorm(last, ldlast, L.norm_final, w.hn, dd, B, dd, L.eps, nullptr, st))) return rc;
     float* lg = logits_out ? logits_out + (size_t)i * V : w.logits;
     const int ldl = logits_out ? ncb * V : V;
-    if ((rc = lin(w, w.hn, dd, m.audio_head_t + (size_t)(i - 1) * V * dd, lg, ldl, B, V, dd, 0, st))) return rc;
+    const uint16_t* head = w.e4m3 ? reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(m.audio_head_t) +
+                                                                      (size_t)(i - 1) * e4m3_blob_bytes(V, dd))
+                                  : m.audio_head_t + (size_t)(i - 1) * V * dd;
+    if ((rc = lin(w, w.hn, dd, head, lg, ldl, B, V, dd, 0, st))) return rc;
     if ((rc = launch_sample(lg, ldl, frame + i, ncb, B, V, sampler, draw_base + (uint64_t)i, pos, (uint32_t)ncb,
                             forced ? forced + i : nullptr, ncb, st)))
       return rc;

@@ -205,6 +205,92 @@ static int launch_linear_t(const float* x, int ldx, const uint16_t* W, float* y,
   return CSMB_OK;
 }
 
+// The same Linear on a weight-only FP8 blob (CSMB_WEIGHTS_E4M3): one warp per output feature and RB rows, lanes split K in
+// 16-element (16-byte) pieces, e4m3 -> f16 pairs with the hardware conversion (exact), f16 -> f32, fp32 FMA, shuffle tree,
+// then the per-output-channel scale on the finished dot product: y = scale[n] * sum_k x[k] * q[n][k].
+__device__ __forceinline__ float2 e4m3x2_to_f32(uint16_t v) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(v));
+  float2 f;
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h2));
+  return f;
+}
+template <int RB, int NB>
+__global__ void __launch_bounds__(256) k_linear_e4m3(const float* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                                     const uint8_t* __restrict__ Q, float* __restrict__ y, int ldy, int R, int N,
+                                                     int K, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * NB;
+  const int r0 = blockIdx.y * RB;
+  if (n0 >= N) return;
+  float acc[RB][NB];
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j] = 0.f;
+  const uint8_t* qrow[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) qrow[j] = Q + (size_t)min(n0 + j, N - 1) * K;
+  const float* xrow[RB];
+#pragma unroll
+  for (int i = 0; i < RB; ++i) xrow[i] = x + (size_t)min(r0 + i, R - 1) * ldx;
+#pragma unroll 2
+  for (int k = lane * 16; k < K; k += 512) {
+    uint4 q[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) q[j] = ldg_stream(qrow[j] + k);   // NB independent 16-byte loads in flight
+    float4 xv[RB][4];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xv[i][e] = __ldg(reinterpret_cast<const float4*>(xrow[i] + k + 4 * e));
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const uint32_t qw[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = e4m3x2_to_f32((uint16_t)(qw[e] & 0xffffu)), b = e4m3x2_to_f32((uint16_t)(qw[e] >> 16));
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          float s = acc[i][j];
+          s = fmaf(a.x, xv[i][e].x, s);
+          s = fmaf(a.y, xv[i][e].y, s);
+          s = fmaf(b.x, xv[i][e].z, s);
+          s = fmaf(b.y, xv[i][e].w, s);
+          acc[i][j] = s;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float v = warp_sum(acc[i][j]);
+      if (lane == i * NB + j && r0 + i < R && n0 + j < N) {
+        float* dst = y + (size_t)(r0 + i) * ldy + n0 + j;
+        const float t = v * __ldg(scale + n0 + j);
+        *dst = accumulate ? *dst + t : t;
+      }
+    }
+}
+
+int launch_linear_e4m3(const float* x, int ldx, const void* blob, float* y, int ldy, int R, int N, int K, int accumulate,
+                       cudaStream_t st) {
+  CSMB_REQUIRE(x && blob && y && R > 0 && N > 0 && K > 0 && K % 16 == 0 && ldx % 4 == 0);
+  CSMB_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const float* scale = static_cast<const float*>(blob);
+  const uint8_t* Q = static_cast<const uint8_t*>(blob) + e4m3_scale_bytes(N);
+  // the same sums for a row whatever R: one accumulation order (k ascending per lane, then the shuffle tree)
+  if (R <= 2) {
+    k_linear_e4m3<2, 4><<<dim3(cdiv(N, 32), cdiv(R, 2)), 256, 0, st>>>(x, ldx, scale, Q, y, ldy, R, N, K, accumulate);
+  } else {
+    k_linear_e4m3<4, 4><<<dim3(cdiv(N, 32), cdiv(R, 4)), 256, 0, st>>>(x, ldx, scale, Q, y, ldy, R, N, K, accumulate);
+  }
+  CSMB_LAUNCH_CHECK();
+  return CSMB_OK;
+}
+
 // Tiled variant for many rows (prefill, R > 8): 64 x 64 output tile per CTA, BK = 16, 4 x 4 outputs per thread, bf16
 // weights widened to fp32 on the way into shared memory; every weight tile is read once per 64 rows instead of once
 // per 4.  (CUDA-core fp32 FMA: prefill is ~0.3 TFLOP for a 164-row prompt; a tcgen05 path is the next step.)
@@ -656,6 +742,14 @@ int csmb_linear(const float* x, int ldx, const uint16_t* W, float* y, int ldy, i
                 int accumulate, int device, void* stream) {
   CSMB_ENTER(device);
   return launch_linear(x, ldx, W, y, ldy, R, N, K, accumulate, (cudaStream_t)stream);
+}
+
+size_t csmb_e4m3_blob_bytes(int N, int K) { return (N > 0 && K > 0) ? e4m3_blob_bytes(N, K) : 0; }
+
+int csmb_linear_e4m3(const float* x, int ldx, const void* blob, float* y, int ldy, int R, int N, int K, int accumulate,
+                     int device, void* stream) {
+  CSMB_ENTER(device);
+  return launch_linear_e4m3(x, ldx, blob, y, ldy, R, N, K, accumulate, (cudaStream_t)stream);
 }
 
 int csmb_swiglu(const float* gu, float* out, int R, int F, int device, void* stream) {

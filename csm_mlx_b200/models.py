@@ -99,6 +99,7 @@ class CSM:
         self._desc: Optional[_lib.Model] = None
         self._proj_table: Optional[torch.Tensor] = None
         self._loaded = False
+        self.quantized = False   # quantize_weights(): the Linear matrices are weight-only FP8 blobs
 
     # ------------------------------------------------------------------ reference-visible views
     @property
@@ -107,8 +108,11 @@ class CSM:
         return None if self._audio_head_t is None else self._audio_head_t.transpose(1, 2)
 
     def parameters(self) -> Dict[str, torch.Tensor]:
-        """Flat dict keyed like the reference parameter tree; views into the fused storage."""
+        """Flat dict keyed like the reference parameter tree; views into the fused storage (a quantised
+        model: the dequantised fp32 matrices, i.e. exactly the numbers its kernels multiply with)."""
         self._require_loaded()
+        if self.quantized:
+            return self._dequantized_parameters()
         out = {
             "text_embeddings.weight": self.text_embeddings.weight,
             "audio_embeddings.weight": self.audio_embeddings.weight,
@@ -177,6 +181,8 @@ class CSM:
                     + " ".join(missing[:8]))
             self._finalize(known)
         else:
+            if self.quantized:
+                raise RuntimeError("load_weights() on a quantised model: load into a fresh CSM and quantise again")
             cur = self.parameters()
             self._proj_table = None  # derived from projection / audio_embeddings: rebuilt on next use
             for k, v in known.items():
@@ -213,6 +219,69 @@ class CSM:
         self._loaded = True
         self._desc = None
 
+    # ------------------------------------------------------------------ weight-only FP8 (nn.quantize analogue)
+    def quantize_weights(self) -> "CSM":
+        """In place: every Linear matrix (q|k|v, o, gate|up, down of both stacks, projection, codebook0_head, audio_head)
+        becomes an E4M3 blob with one fp32 scale per output channel (``quantization.py``; /root/reference README.md:92-128 calls
+        ``nn.quantize(csm)`` at this point).  Embeddings and norm weights are untouched.  Halves the streamed bytes of a frame;
+        served by the row-based GEMV path (the fused kernels decline a quantised model)."""
+        from . import quantization as qz
+
+        self._require_loaded()
+        if self.quantized:
+            return self
+        self._qshapes: Dict[str, Tuple[int, int]] = {}
+
+        def blob(t: torch.Tensor, name: str) -> torch.Tensor:
+            q, s = qz.quantize_rows_e4m3(t)
+            self._qshapes[name] = (int(t.shape[0]), int(t.shape[1]))
+            return qz.pack_blob(q, s)
+
+        for name, st in (("backbone", self.backbone), ("decoder", self.decoder)):
+            for l in range(st.args.num_hidden_layers):
+                st.wqkv[l] = blob(st.wqkv[l], f"{name}.{l}.wqkv")
+                st.wo[l] = blob(st.wo[l], f"{name}.{l}.wo")
+                st.wgu[l] = blob(st.wgu[l], f"{name}.{l}.wgu")
+                st.wdown[l] = blob(st.wdown[l], f"{name}.{l}.wdown")
+        self.projection.weight = blob(self.projection.weight, "projection")
+        self.codebook0_head.weight = blob(self.codebook0_head.weight, "codebook0_head")
+        heads = [blob(self._audio_head_t[i], "audio_head") for i in range(self._audio_head_t.shape[0])]
+        self._audio_head_t = torch.cat(heads)      # n_codebooks-1 blobs back to back
+        self.quantized = True
+        self._proj_table = None
+        self._desc = None
+        return self
+
+    def _dequantized_parameters(self) -> Dict[str, torch.Tensor]:
+        from . import quantization as qz
+
+        def deq(blob: torch.Tensor, name: str) -> torch.Tensor:
+            n, k = self._qshapes[name]
+            return qz.dequantize_rows_e4m3(*qz.unpack_blob(blob, n, k))
+
+        out = {"text_embeddings.weight": self.text_embeddings.weight, "audio_embeddings.weight": self.audio_embeddings.weight,
+               "projection.weight": deq(self.projection.weight, "projection"),
+               "codebook0_head.weight": deq(self.codebook0_head.weight, "codebook0_head")}
+        v, dd = self._qshapes["audio_head"]
+        nb = qz.blob_bytes(v, dd)
+        out["audio_head"] = torch.stack([deq(self._audio_head_t[i * nb:(i + 1) * nb], "audio_head").t()
+                                         for i in range(self.n_audio_codebooks - 1)])
+        for name, st in (("backbone", self.backbone), ("decoder", self.decoder)):
+            a = st.args
+            nq, nkv = a.num_attention_heads * a.head_dim, a.num_key_value_heads * a.head_dim
+            for l in range(a.num_hidden_layers):
+                p = f"{name}.layers.{l}."
+                qkv, gu = deq(st.wqkv[l], f"{name}.{l}.wqkv"), deq(st.wgu[l], f"{name}.{l}.wgu")
+                out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"] = qkv[:nq], qkv[nq:nq + nkv]
+                out[p + "self_attn.v_proj.weight"] = qkv[nq + nkv:]
+                out[p + "self_attn.o_proj.weight"] = deq(st.wo[l], f"{name}.{l}.wo")
+                out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = gu[:a.intermediate_size], gu[a.intermediate_size:]
+                out[p + "mlp.down_proj.weight"] = deq(st.wdown[l], f"{name}.{l}.wdown")
+                out[p + "input_layernorm.weight"] = st.norm_in[l]
+                out[p + "post_attention_layernorm.weight"] = st.norm_post[l]
+            out[f"{name}.norm.weight"] = st.norm_final
+        return out
+
     def _require_loaded(self) -> None:
         if not self._loaded:
             raise RuntimeError("CSM weights are not loaded: call model.load_weights(...) first")
@@ -243,6 +312,7 @@ class CSM:
             m.audio_head_t = self._audio_head_t.data_ptr()
             m.n_text_vocab, m.audio_vocab = self.n_text_vocab, self.n_audio_vocab
             m.n_codebooks, m.max_pos = self.n_audio_codebooks, MAX_SEQ_LEN
+            m.weight_format = _lib.WEIGHTS_E4M3 if self.quantized else _lib.WEIGHTS_BF16
             self._desc = m
         return self._desc
 
@@ -251,6 +321,8 @@ class CSM:
         models.py:79-80 rows) for the batched chain's depth steps, built once on first use with the chain's own projection
         Linear (``csmb_build_proj_table``: bit-identical to running it).  None if the shapes are not the chain's."""
         self._require_loaded()
+        if self.quantized:
+            return None   # the chain declines weight-only FP8 models
         if self._proj_table is None:
             if self.n_backbone_embedding % 64 != 0 or self.n_decoder_embedding not in (1024, 2048):
                 return None

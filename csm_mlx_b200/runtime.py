@@ -396,7 +396,7 @@ class LMState:
                  d.num_attention_heads, d.num_key_value_heads, d.head_dim) == (2048, 32, 8, 64, 1024, 8, 2, 128)
         # in-kernel samplers of k_frame: greedy; temperature with top-k, top-p and / or min-p (not min-p with min_tokens_to_keep > 1)
         plain = sampler.temperature == 0 or not (sampler.min_p > 0 and sampler.min_tokens_to_keep > 1)
-        return bool(shape and plain and 3 <= self.model.n_audio_codebooks <= 32)
+        return bool(shape and plain and 3 <= self.model.n_audio_codebooks <= 32 and not self.model.quantized)
 
     def fused_supported(self, sampler: SamplerSpec) -> bool:
         return self.batch == 1 and self.slot_fused_supported(sampler)

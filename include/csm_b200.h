@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CSMB_ABI_VERSION 2
+#define CSMB_ABI_VERSION 3
 #define CSMB_PAGE 16          /* tokens per KV page */
 #define CSMB_MAX_LAYERS 16
 #define CSMB_MAX_CODEBOOKS 32
@@ -148,7 +148,24 @@ typedef struct {
   const uint16_t* c0_head;      /* [audio_vocab][d_b] */
   const uint16_t* audio_head_t; /* [n_codebooks-1][audio_vocab][d_d]: checkpoint's (in,out) transposed */
   int n_text_vocab, audio_vocab, n_codebooks, max_pos;
+  int weight_format;            /* CSMB_WEIGHTS_BF16 (0) or CSMB_WEIGHTS_E4M3: every nn.Linear matrix above (wqkv, wo, wgu, wdown,
+                                   projection, c0_head, audio_head_t — not the embedding tables) is an e4m3 blob, see below */
+  int reserved;
 } csmb_model;
+
+/* Weight-only FP8 (the analogue of mlx.nn.quantize on the reference's Linear layers, /root/reference README.md:92-128).
+ * A matrix [N][K] is stored as one blob: N fp32 per-output-channel scales, padded to 256 bytes, then N*K e4m3 bytes
+ * (OCP FP8 E4M3, finite-only "fn" variant) row-major, the whole blob padded to 256 bytes:  W[n][k] = scale[n] * e4m3[n][k].
+ * audio_head_t is n_codebooks-1 such blobs of [audio_vocab][d_d] back to back.  csmb_e4m3_blob_bytes gives the size.
+ * Served by the row-based entry points (csmb_backbone_forward, csmb_depth_decode, csmb_decode_frame: GEMV kernels that
+ * widen e4m3 -> fp32 in registers and apply the scale to the finished dot product); the fused paths (csmb_frame_b1*,
+ * csmb_decode_frame_fast*, csmb_prefill_fast, csmb_build_proj_table) return CSMB_ERR_UNSUPPORTED for such a model. */
+#define CSMB_WEIGHTS_BF16 0
+#define CSMB_WEIGHTS_E4M3 1
+size_t csmb_e4m3_blob_bytes(int N, int K);
+/* csmb_linear on an e4m3 blob: y[R][N] (+)= scale[n] * sum_k x[r][k] * e4m3[n][k]   (K % 16 == 0, blob 16-byte aligned) */
+int csmb_linear_e4m3(const float* x, int ldx, const void* blob, float* y, int ldy, int R, int N, int K, int accumulate,
+                     int device, void* stream);
 
 /* Per-call view of a batch of sequences being generated. */
 typedef struct {

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header():
     # csmb_llama: 6 ints + float + 6 arrays of 16 pointers + 2 pointers (8-byte aligned)
     assert ctypes.sizeof(_lib.Llama) == 32 + 6 * 16 * 8 + 16
     assert ctypes.sizeof(_lib.Sampler) == 32
-    assert ctypes.sizeof(_lib.Model) == 2 * ctypes.sizeof(_lib.Llama) + 5 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.Model) == 2 * ctypes.sizeof(_lib.Llama) + 5 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Batch) == 8 + 7 * 8 + 8       # + int flags, padded to the struct's 8-byte alignment
     assert ctypes.sizeof(_lib.ChainOpts) == 3 * 4 + 4 + 8 and ctypes.sizeof(_lib.FrameOpts) == 4 * 4 + 8
 
@@ -48,7 +48,7 @@ def test_header_is_plain_c():
         import pytest
 
         pytest.skip("no gcc")
-    src = '#include "csm_b200.h"\nint main(void) { csmb_sampler s; csmb_model m; csmb_batch b; csmb_chain_opts c; csmb_frame_opts f; (void)s; (void)m; (void)b; (void)c; (void)f; return CSMB_ABI_VERSION - 2; }\n'
+    src = '#include "csm_b200.h"\nint main(void) { csmb_sampler s; csmb_model m; csmb_batch b; csmb_chain_opts c; csmb_frame_opts f; (void)s; (void)m; (void)b; (void)c; (void)f; return CSMB_ABI_VERSION - 3; }\n'
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", "-I",
                         os.path.join(ROOT, "include"), "-"], input=src.encode(), capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
