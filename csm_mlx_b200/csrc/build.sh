@@ -13,7 +13,7 @@ pids=()
 for src in "$HERE"/*.cu; do
   o="$OBJ/$(basename "${src%.cu}").o"
   # rebuild when the source, any header of this directory, the public header or this script is newer than the object
-  if [ ! -f "$o" ] || [ -n "$(find "$src" "$HERE"/*.cuh "$HERE/../../include/csm_b200.h" "${BASH_SOURCE[0]}" -newer "$o" 2>/dev/null | head -1)" ] || [ $# -gt 0 ]; then
+  if [ ! -f "$o" ] || [ -n "$(find "$src" "$HERE"/frame_kernel.cu "$HERE"/*.cuh "$HERE/../../include/csm_b200.h" "${BASH_SOURCE[0]}" -newer "$o" 2>/dev/null | head -1)" ] || [ $# -gt 0 ]; then
     "$NVCC" "${FLAGS[@]}" -c -o "$o" "$src" 2> "$o.log" &
     pids+=($!)
   fi

@@ -27,8 +27,23 @@
 
 #include "ops.cuh"
 
-namespace csmb {
+// This file is compiled twice: as is (CSMB_FK_FMT = 0: bf16 weights, namespace csmb::fk_bf16, plus the C entry points) and
+// through frame_kernel_e4m3.cu (CSMB_FK_FMT = 1: weight-only FP8 blobs, namespace csmb::fk_e4m3, kernel and launcher only), so
+// that the bf16 kernel's code is exactly what it was before the FP8 mode existed (a template parameter changed ptxas'
+// inlining and cost the bf16 frame 3 %).
+#ifndef CSMB_FK_FMT
+#define CSMB_FK_FMT 0
+#endif
+#if CSMB_FK_FMT == 0
+#define FK_NS fk_bf16
+#else
+#define FK_NS fk_e4m3
+#endif
 
+namespace csmb {
+namespace FK_NS {
+
+constexpr int FMT = CSMB_FK_FMT;        // CSMB_WEIGHTS_BF16 or CSMB_WEIGHTS_E4M3
 constexpr int NCW = 8;                  // consumer warps
 constexpr int NCT = NCW * 32;           // consumer threads
 constexpr int NTHREADS = (NCW + 1) * 32;
@@ -125,6 +140,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ uint64_t make_evict_first_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// e4m3 models: the depth decoder (4 layers + projection + one head = 115 MB at one byte per weight) is streamed 31 times per
+// frame and nearly fits the 126 MB L2: its copies ask L2 to keep them (evict-last on a fraction of the lines, so that the
+// tagged activation words and KV rows still find room), the backbone stays evict-first
+__device__ __forceinline__ uint64_t make_keep_policy(float fraction) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(fraction));
   return pol;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
@@ -244,15 +267,43 @@ __device__ __forceinline__ void probe_wait(Ctx& c, const uint2* word, unsigned t
 // consumer-side sync (shared-memory results visible to all consumer warps)
 __device__ __forceinline__ void csync() { named_bar_sync(2, NCT); }
 
+// two e4m3 -> two fp32, exact (hardware e4m3x2 -> f16x2, then f16 -> f32)
+__device__ __forceinline__ float2 e4m3x2_to_f32(uint16_t v) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(v));
+  float2 f;
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h2));
+  return f;
+}
+
 // ------------------------------------------------------------------------------------------------ row partition
 struct Range {
-  const uint16_t* p;
+  const uint16_t* p;   // first weight of the range (bf16 elements; e4m3 instantiation: bytes)
   int row0, rows, K;
 };
-__device__ __forceinline__ Range cta_range(const uint16_t* W, int N, int K, int cta, int G) {
+// this CTA's rows of the sub-matrix [rbase, rbase + N) of a matrix of Ntot rows: bf16 [Ntot][K], or (FMT = CSMB_WEIGHTS_E4M3) a
+// blob of Ntot fp32 scales followed by the e4m3 bytes
+__device__ __forceinline__ Range cta_range(const uint16_t* W, int Ntot, int rbase, int N, int K, int cta, int G) {
   const int r0 = (int)(((unsigned)N * (unsigned)cta) / (unsigned)G), r1 = (int)(((unsigned)N * (unsigned)(cta + 1)) / (unsigned)G);
-  return Range{W + (size_t)r0 * K, r0, r1 - r0, K};
+  if (FMT == CSMB_WEIGHTS_E4M3) {
+    const char* q = reinterpret_cast<const char*>(W) + e4m3_scale_bytes(Ntot) + (size_t)(rbase + r0) * K;
+    return Range{reinterpret_cast<const uint16_t*>(q), r0, r1 - r0, K};
+  }
+  return Range{W + (size_t)(rbase + r0) * K, r0, r1 - r0, K};
 }
+// e4m3: the per-output-channel scales of that range's rows
+__device__ __forceinline__ const float* range_scales(const uint16_t* W, int rbase, const Range& r) {
+  return reinterpret_cast<const float*>(W) + rbase + r.row0;
+}
+// head i of audio_head_t: [V][dd] bf16, or one e4m3 blob per head
+__device__ __forceinline__ const uint16_t* audio_head_ptr(const csmb_model& m, int i) {
+  if (FMT == CSMB_WEIGHTS_E4M3)
+    return reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(m.audio_head_t) +
+                                             (size_t)i * e4m3_blob_bytes(m.audio_vocab, m.decoder.d_model));
+  return m.audio_head_t + (size_t)i * m.audio_vocab * m.decoder.d_model;
+}
+// ring stages of a range: a stage holds SUB * 8 units of 1024 weights whatever the weight format (an e4m3 stage fills the
+// first half of its 32 KiB slot), so the stage sequence — and every unit index — is the same for both formats
 __device__ __forceinline__ int n_stages(const Range& r) {
   return (int)(((size_t)r.rows * r.K * 2 + STAGE_BYTES - 1) / STAGE_BYTES);
 }
@@ -286,7 +337,31 @@ __device__ void consume(Ctx& c, const Range& r, const float (&xr)[R][32], float*
     for (int g = 0; g < GS; ++g)
 #pragma unroll
       for (int i = 0; i < R; ++i) acc[g][i][0] = acc[g][i][1] = 0.f;
-    if (math && !c.aborted) {
+    if (FMT == CSMB_WEIGHTS_E4M3 && math && !c.aborted) {
+      // weight-only FP8: the same units at one byte per weight — 8 e4m3 per lane and chunk (one 8-byte load), widened to
+      // fp32 with cvt.rn.f16x2.e4m3x2 + cvt.f32.f16 (exact); the per-channel scale is applied where the row is finalised
+      const unsigned char* b[GS];
+#pragma unroll
+      for (int g = 0; g < GS; ++g)
+        b[g] = c.ring.data + (size_t)((c.q + g / SUB) % NSTAGES) * STAGE_BYTES + (size_t)(g % SUB) * 8192 + (size_t)c.warp * UNIT +
+               c.lane * 8;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint2 w[GS];
+#pragma unroll
+        for (int g = 0; g < GS; ++g) w[g] = *reinterpret_cast<const uint2*>(b[g] + ch * 256);
+#pragma unroll
+        for (int g = 0; g < GS; ++g) {
+          const float2 f01 = e4m3x2_to_f32((uint16_t)(w[g].x & 0xffffu)), f23 = e4m3x2_to_f32((uint16_t)(w[g].x >> 16));
+          const float2 f45 = e4m3x2_to_f32((uint16_t)(w[g].y & 0xffffu)), f67 = e4m3x2_to_f32((uint16_t)(w[g].y >> 16));
+          const float f[8] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y, f67.x, f67.y};
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[g][i][e & 1] = fmaf(f[e], xr[i][ch * 8 + e], acc[g][i][e & 1]);
+        }
+      }
+    } else if (FMT == CSMB_WEIGHTS_BF16 && math && !c.aborted) {
       const unsigned char* b[GS];
 #pragma unroll
       for (int g = 0; g < GS; ++g)
@@ -496,7 +571,7 @@ __device__ __forceinline__ void load_act_slice(Ctx& c, const uint2* act, int F, 
 template <int R>
 __device__ void phase_linear(Ctx& c, const uint16_t* W, int N, int K, const float (&xr)[R][32], uint2* y, int ldy,
                              const uint2* res, int ldr) {
-  const Range r = cta_range(W, N, K, c.cta, c.G);
+  const Range r = cta_range(W, N, 0, N, K, c.cta, c.G);
   // this thread finalises output j = tid (rows*R <= 44): fetch its residual early (its producer phase is long over)
   const int j = c.tid;
   const bool mine = j < r.rows * R;
@@ -507,15 +582,19 @@ __device__ void phase_linear(Ctx& c, const uint16_t* W, int N, int K, const floa
   consume<R>(c, r, xr, c.part);
   mark(c, T_GEMV);
   csync();
-  if (mine) ll_st(y + (size_t)ri * ldy + r.row0 + rrow, rv + row_total(c.part + (size_t)ri * MAXU * 4, rrow, K / UNIT), cur_tag(c));
+  if (mine) {
+    float t = row_total(c.part + (size_t)ri * MAXU * 4, rrow, K / UNIT);
+    if (FMT == CSMB_WEIGHTS_E4M3) t *= __ldg(range_scales(W, 0, r) + rrow);   // weight-only FP8: per-output-channel scale on the finished dot product
+    ll_st(y + (size_t)ri * ldy + r.row0 + rrow, rv + t, cur_tag(c));
+  }
   mark(c, T_FIN);
 }
 
 // SwiGLU MLP first half: act[f] = silu(Wg[f,:].x) * (Wu[f,:].x)
 template <int R>
 __device__ void phase_gate_up(Ctx& c, const uint16_t* Wgu, int F, int K, const float (&xr)[R][32], uint2* act) {
-  const Range rg = cta_range(Wgu, F, K, c.cta, c.G);
-  const Range ru = cta_range(Wgu + (size_t)F * K, F, K, c.cta, c.G);
+  const Range rg = cta_range(Wgu, 2 * F, 0, F, K, c.cta, c.G);
+  const Range ru = cta_range(Wgu, 2 * F, F, F, K, c.cta, c.G);
   float* pg = c.part;
   float* pu = c.part + 2 * MAXU * 4;
   mark(c, T_LOAD);
@@ -527,7 +606,11 @@ __device__ void phase_gate_up(Ctx& c, const uint16_t* Wgu, int F, int K, const f
   const unsigned tag = cur_tag(c);
   for (int j = c.tid; j < rg.rows * R; j += NCT) {
     const int i = j / rg.rows, row = j % rg.rows;
-    const float g = row_total(pg + (size_t)i * MAXU * 4, row, KS), u = row_total(pu + (size_t)i * MAXU * 4, row, KS);
+    float g = row_total(pg + (size_t)i * MAXU * 4, row, KS), u = row_total(pu + (size_t)i * MAXU * 4, row, KS);
+    if (FMT == CSMB_WEIGHTS_E4M3) {
+      g *= __ldg(range_scales(Wgu, 0, rg) + row);
+      u *= __ldg(range_scales(Wgu, F, ru) + row);
+    }
     ll_st(act + (size_t)i * F + rg.row0 + row, (g / (1.f + expf(-g))) * u, tag);
   }
   mark(c, T_FIN);
@@ -990,11 +1073,11 @@ __device__ bool sched_range(const FrameParams& p, int idx, int cta, int G, Range
   auto layer_range = [&](const csmb_llama& L, int l, int k, int d) {
     const int nqkv = (L.n_heads + 2 * L.n_kv_heads) * L.head_dim;
     switch (k) {
-      case 0: return cta_range(L.wqkv[l], nqkv, d, cta, G);
-      case 1: return cta_range(L.wo[l], d, d, cta, G);
-      case 2: return cta_range(L.wgu[l], L.d_ff, d, cta, G);
-      case 3: return cta_range(L.wgu[l] + (size_t)L.d_ff * d, L.d_ff, d, cta, G);
-      default: return cta_range(L.wdown[l], d, L.d_ff, cta, G);
+      case 0: return cta_range(L.wqkv[l], nqkv, 0, nqkv, d, cta, G);
+      case 1: return cta_range(L.wo[l], d, 0, d, d, cta, G);
+      case 2: return cta_range(L.wgu[l], 2 * L.d_ff, 0, L.d_ff, d, cta, G);
+      case 3: return cta_range(L.wgu[l], 2 * L.d_ff, L.d_ff, L.d_ff, d, cta, G);
+      default: return cta_range(L.wdown[l], d, 0, d, L.d_ff, cta, G);
     }
   };
   const int nb = B.n_layers * 5;
@@ -1003,14 +1086,14 @@ __device__ bool sched_range(const FrameParams& p, int idx, int cta, int G, Range
     return true;
   }
   if (idx == nb) {
-    out = cta_range(p.m.c0_head, V, db, cta, G);
+    out = cta_range(p.m.c0_head, V, 0, V, db, cta, G);
     return true;
   }
   const int per_step = 2 + D.n_layers * 5;
   const int j = idx - nb - 1, step = j / per_step, t = j % per_step;
   if (step >= p.m.n_codebooks - 1) return false;
-  if (t == 0) out = cta_range(p.m.projection, dd, db, cta, G);
-  else if (t == per_step - 1) out = cta_range(p.m.audio_head_t + (size_t)step * V * dd, V, dd, cta, G);
+  if (t == 0) out = cta_range(p.m.projection, dd, 0, dd, db, cta, G);
+  else if (t == per_step - 1) out = cta_range(audio_head_ptr(p.m, step), V, 0, V, dd, cta, G);
   else out = layer_range(D, (t - 1) / 5, (t - 1) % 5, dd);
   return true;
 }
@@ -1026,9 +1109,11 @@ __device__ __forceinline__ void cursor_load(const FrameParams& p, Cursor& k, int
   k.nst = k.valid ? n_stages(k.r) : 0;
 }
 __device__ __forceinline__ void cursor_chunk(const Cursor& k, const char*& src, uint32_t& bytes) {
-  const size_t total = (size_t)k.r.rows * k.r.K * 2, off = (size_t)k.stage * STAGE_BYTES;
+  constexpr int wb = FMT == CSMB_WEIGHTS_E4M3 ? 1 : 2;
+  const size_t sb = (size_t)STAGE_BYTES / 2 * wb;   // bytes of a full stage in this range's weight format
+  const size_t total = (size_t)k.r.rows * k.r.K * wb, off = (size_t)k.stage * sb;
   src = reinterpret_cast<const char*>(k.r.p) + off;
-  bytes = (uint32_t)((total - off) < (size_t)STAGE_BYTES ? (total - off) : (size_t)STAGE_BYTES);
+  bytes = (uint32_t)((total - off) < sb ? (total - off) : sb);
 }
 __device__ __forceinline__ void cursor_advance(const FrameParams& p, Cursor& k, int cta, int G) {
   if (++k.stage >= k.nst) {
@@ -1062,6 +1147,7 @@ __device__ void producer_main(Ctx& c) {
   const int pf_max = p.pf_max, pf_interval = p.pf_interval;
   long long last_pf = clock64();
   unsigned n_pf = 0;
+  const uint64_t policy_keep = make_keep_policy((float)((p.dbg >> 4) & 7) * 0.125f);
   while (rc.valid && !c.aborted) {
     const int slot = c.q % NSTAGES;
     const uint32_t par = (c.q / NSTAGES) & 1;
@@ -1089,7 +1175,9 @@ __device__ void producer_main(Ctx& c) {
     uint32_t n;
     cursor_chunk(rc, src, n);
     mbar_arrive_expect_tx(&c.ring.full[slot], n);
-    bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src, n, &c.ring.full[slot], c.policy);
+    // dbg bits 4..6 (e4m3 only): keep k/8 of the decoder's lines in L2 across the 31 depth steps
+    const bool keep = FMT == CSMB_WEIGHTS_E4M3 && (p.dbg & 0x70) != 0 && rc.idx > p.m.backbone.n_layers * 5;
+    bulk_g2s(c.ring.data + (size_t)slot * STAGE_BYTES, src, n, &c.ring.full[slot], keep ? policy_keep : c.policy);
     cursor_advance(p, rc, c.cta, c.G);
     ++c.q;
     if (pq < c.q) {  // keep the prefetch cursor at or ahead of the ring cursor
@@ -1158,7 +1246,7 @@ __device__ void decoder_step(Ctx& c, int step, int pos0, float (&xr)[R][32]) {
   csync();
   float xh[1][32];
   norm_from_smem<1, 1>(c, c.sattn + (size_t)(R - 1) * dd, nw, D.eps, xh);
-  phase_linear<1>(c, p.m.audio_head_t + (size_t)(step - 1) * V * dd, V, dd, xh, p.logits, V, nullptr, 0);
+  phase_linear<1>(c, audio_head_ptr(p.m, step - 1), V, dd, xh, p.logits, V, nullptr, 0);
   c.phase++;
 }
 
@@ -1351,12 +1439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frame(const __grid_constant__ F
   }
 }
 
-}  // namespace csmb
-
-using namespace csmb;
-
-extern "C" {
-
+// ---------------------------------------------------------------------------------------------- host side (per format)
 static size_t frame_ws_words(const csmb_model* m) {
   const csmb_llama &B = m->backbone, &D = m->decoder;
   const size_t nqkv_b = (size_t)(B.n_heads + 2 * B.n_kv_heads) * B.head_dim, nqkv_d = (size_t)(D.n_heads + 2 * D.n_kv_heads) * D.head_dim;
@@ -1371,7 +1454,7 @@ static size_t frame_ws_words(const csmb_model* m) {
   return w;
 }
 
-size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
+size_t frame_workspace_bytes(const csmb_model* m, int device) {
   if (!m) return 0;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 384;
@@ -1379,7 +1462,7 @@ size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) {
   return frame_ws_words(m) * sizeof(uint2) + (size_t)m->backbone.d_model * sizeof(float) + dec_kv + 256 + 16384;
 }
 
-static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
+int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                         const int32_t* prev_frame, const float* h_in, const int32_t* pos, int32_t* frame,
                         const csmb_sampler* sampler, uint64_t draw_base, uint32_t seq, const csmb_frame_opts* opts,
                         void* workspace, size_t workspace_bytes, int32_t* status, int device, void* stream) {
@@ -1390,12 +1473,12 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   const bool shape_ok = B.d_model == 2048 && B.n_heads == 32 && B.n_kv_heads == 8 && B.head_dim == 64 &&
                         D.d_model == 1024 && D.n_heads == 8 && D.n_kv_heads == 2 && D.head_dim == 128 &&
                         D.d_ff == 8192 && B.d_ff == 8192 && m->n_codebooks <= 32 && m->n_codebooks >= 3 &&
-                        m->audio_vocab <= 9 * NCT && m->weight_format == CSMB_WEIGHTS_BF16;   // FP8 blobs: row-based path
+                        m->audio_vocab <= 9 * NCT;
   if (!shape_ok) return CSMB_ERR_UNSUPPORTED;
   // fused samplers: greedy; temperature with optional top-k, top-p and / or min-p.  Only min-p with min_tokens_to_keep > 1
   // (it needs the sorted order) stays on the per-op path (csmb_decode_frame).
   if (sampler->temperature != 0.f && sampler->min_p > 0.f && sampler->min_keep > 1) return CSMB_ERR_UNSUPPORTED;
-  CSMB_REQUIRE(workspace_bytes >= csmb_frame_workspace_bytes(m, device));
+  CSMB_REQUIRE(workspace_bytes >= frame_workspace_bytes(m, device));
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 0;
   CSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -1453,7 +1536,9 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   const int want_ctas = opts ? opts->ctas : 0;
 
   static const size_t dyn_smem = (size_t)NSTAGES * STAGE_BYTES + KVS_BYTES;  // ring + decoder KV staging
-  CSMB_CUDA(cudaFuncSetAttribute(k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+  CSMB_REQUIRE(m->weight_format == FMT);
+  const void* kern = (const void*)k_frame;
+  CSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   CSMB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(base), 0, 64, st));  // abort flag only; the nonce persists
   void* args[] = {&p};
   // fewest CTAs for which every linear's per-CTA slice fits the partial-sum buffer (MAXU units) and its rows fit one
@@ -1478,10 +1563,36 @@ static int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_str
   }
   while (grid < sms && !fits(grid)) ++grid;
   CSMB_REQUIRE(fits(grid));
-  CSMB_CUDA(cudaLaunchCooperativeKernel((void*)k_frame, dim3(grid), dim3(NTHREADS), args, dyn_smem, st));
+  CSMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NTHREADS), args, dyn_smem, st));
   count_launch();
   return CSMB_OK;
 }
+
+}  // namespace FK_NS
+}  // namespace csmb
+
+#if CSMB_FK_FMT == 0
+// the e4m3 instantiation of everything above lives in frame_kernel_e4m3.cu
+namespace csmb {
+namespace fk_e4m3 {
+int launch_frame(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table, const int32_t* prev_frame,
+                 const float* h_in, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler, uint64_t draw_base, uint32_t seq,
+                 const csmb_frame_opts* opts, void* workspace, size_t workspace_bytes, int32_t* status, int device, void* stream);
+}
+}  // namespace csmb
+
+using namespace csmb;
+
+// weight format of the model -> the kernel compiled for it
+template <typename... A>
+static int launch_frame(const csmb_model* m, A... a) {
+  if (m && m->weight_format == CSMB_WEIGHTS_E4M3) return fk_e4m3::launch_frame(m, a...);
+  return fk_bf16::launch_frame(m, a...);
+}
+
+extern "C" {
+
+size_t csmb_frame_workspace_bytes(const csmb_model* m, int device) { return fk_bf16::frame_workspace_bytes(m, device); }
 
 int csmb_frame_b1(const csmb_model* m, float* kv_pool, size_t kv_layer_stride, const int32_t* block_table,
                   const int32_t* prev_frame, const int32_t* pos, int32_t* frame, const csmb_sampler* sampler,
@@ -1509,3 +1620,4 @@ int csmb_frame_b1_depth(const csmb_model* m, const float* h_last, const int32_t*
 }
 
 }  // extern "C"
+#endif  // CSMB_FK_FMT == 0

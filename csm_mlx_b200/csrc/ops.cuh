@@ -16,8 +16,13 @@ int launch_rmsnorm(const float* x, int ldx, const float* w, float* y, int ldy, i
 int launch_linear(const float* x, int ldx, const uint16_t* W, float* y, int ldy, int R, int N, int K,
                   int accumulate, cudaStream_t st);
 // e4m3 blob (include/csm_b200.h, CSMB_WEIGHTS_E4M3): scales then bytes
-static inline size_t e4m3_scale_bytes(int N) { return ((size_t)N * 4 + 255) & ~(size_t)255; }
-static inline size_t e4m3_blob_bytes(int N, int K) { return e4m3_scale_bytes(N) + (((size_t)N * K + 255) & ~(size_t)255); }
+#ifdef __CUDACC__
+#define CSMB_HD __host__ __device__
+#else
+#define CSMB_HD
+#endif
+CSMB_HD static inline size_t e4m3_scale_bytes(int N) { return ((size_t)N * 4 + 255) & ~(size_t)255; }
+CSMB_HD static inline size_t e4m3_blob_bytes(int N, int K) { return e4m3_scale_bytes(N) + (((size_t)N * K + 255) & ~(size_t)255); }
 int launch_linear_e4m3(const float* x, int ldx, const void* blob, float* y, int ldy, int R, int N, int K, int accumulate,
                        cudaStream_t st);
 int launch_swiglu(const float* gu, float* out, int R, int F, cudaStream_t st);

@@ -224,7 +224,7 @@ class CSM:
         """In place: every Linear matrix (q|k|v, o, gate|up, down of both stacks, projection, codebook0_head, audio_head)
         becomes an E4M3 blob with one fp32 scale per output channel (``quantization.py``; /root/reference README.md:92-128 calls
         ``nn.quantize(csm)`` at this point).  Embeddings and norm weights are untouched.  Halves the streamed bytes of a frame;
-        served by the row-based GEMV path (the fused kernels decline a quantised model)."""
+        served by the batch-1 frame kernel and the row-based GEMV path (the tensor-core chain declines a quantised model)."""
         from . import quantization as qz
 
         self._require_loaded()

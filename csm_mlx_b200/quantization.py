@@ -4,8 +4,9 @@
 Format (include/csm_b200.h, CSMB_WEIGHTS_E4M3): a matrix ``W[N][K]`` becomes one blob — ``N`` fp32 per-output-channel scales
 (``max|W[n]| / 448``), padded to 256 bytes, then ``N * K`` OCP E4M3 bytes: ``W[n][k] ≈ scale[n] * e4m3[n][k]``.  Embedding
 tables and norm weights stay as they are (they are gathered / applied, not streamed as matrices).  A quantised model is served
-by the row-based GEMV kernels (``csmb_backbone_forward`` / ``csmb_depth_decode`` / ``csmb_decode_frame``: e4m3 widened to fp32
-in registers, fp32 accumulation, the scale applied to the finished dot product); the fused kernels decline it.
+by the batch-1 frame kernel (``csmb_frame_b1``: a second instantiation of the persistent kernel for one-byte weights) and by the
+row-based GEMV kernels (``csmb_backbone_forward`` / ``csmb_depth_decode`` / ``csmb_decode_frame``); both widen e4m3 to fp32 in
+registers, accumulate in fp32 and apply the scale to the finished dot product.  The tensor-core chain declines it.
 """
 from __future__ import annotations
 

@@ -396,7 +396,7 @@ class LMState:
                  d.num_attention_heads, d.num_key_value_heads, d.head_dim) == (2048, 32, 8, 64, 1024, 8, 2, 128)
         # in-kernel samplers of k_frame: greedy; temperature with top-k, top-p and / or min-p (not min-p with min_tokens_to_keep > 1)
         plain = sampler.temperature == 0 or not (sampler.min_p > 0 and sampler.min_tokens_to_keep > 1)
-        return bool(shape and plain and 3 <= self.model.n_audio_codebooks <= 32 and not self.model.quantized)
+        return bool(shape and plain and 3 <= self.model.n_audio_codebooks <= 32)   # bf16 and weight-only FP8 models alike
 
     def fused_supported(self, sampler: SamplerSpec) -> bool:
         return self.batch == 1 and self.slot_fused_supported(sampler)
@@ -408,6 +408,7 @@ class LMState:
             self.frame_status = torch.zeros((1,), device=self.device, dtype=torch.int32)  # sticky: first abort code ever
             o = _lib.FrameOpts()
             o.ctas = int(os.environ.get("CSMB_FRAME_CTAS", "0"))
+            o.flags = int(os.environ.get("CSMB_FRAME_FLAGS", "0"))   # A/B, debug (include/csm_b200.h csmb_frame_opts.flags)
             self._frame_opts = o
 
     def first_frame_fused(self, sampler: SamplerSpec) -> torch.Tensor:

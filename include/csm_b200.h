@@ -157,9 +157,10 @@ typedef struct {
  * A matrix [N][K] is stored as one blob: N fp32 per-output-channel scales, padded to 256 bytes, then N*K e4m3 bytes
  * (OCP FP8 E4M3, finite-only "fn" variant) row-major, the whole blob padded to 256 bytes:  W[n][k] = scale[n] * e4m3[n][k].
  * audio_head_t is n_codebooks-1 such blobs of [audio_vocab][d_d] back to back.  csmb_e4m3_blob_bytes gives the size.
- * Served by the row-based entry points (csmb_backbone_forward, csmb_depth_decode, csmb_decode_frame: GEMV kernels that
- * widen e4m3 -> fp32 in registers and apply the scale to the finished dot product); the fused paths (csmb_frame_b1*,
- * csmb_decode_frame_fast*, csmb_prefill_fast, csmb_build_proj_table) return CSMB_ERR_UNSUPPORTED for such a model. */
+ * Served by the batch-1 frame kernel (csmb_frame_b1*: a second instantiation of the persistent kernel streams the blobs at
+ * one byte per weight) and by the row-based entry points (csmb_backbone_forward, csmb_depth_decode, csmb_decode_frame: GEMV
+ * kernels); both widen e4m3 -> fp32 in registers and apply the scale to the finished dot product.  The tensor-core paths
+ * (csmb_decode_frame_fast*, csmb_prefill_fast, csmb_build_proj_table) return CSMB_ERR_UNSUPPORTED for such a model. */
 #define CSMB_WEIGHTS_BF16 0
 #define CSMB_WEIGHTS_E4M3 1
 size_t csmb_e4m3_blob_bytes(int N, int K);
@@ -294,7 +295,8 @@ typedef struct {
                                 into equal row slices (128 for csm_1b on a 148-SM B200).  The SMs left over let the codec's
                                 streaming step of the previous frame run beside the frame kernel on a second stream
                                 (generation.py:251 moved off the critical path). */
-  int flags;                 /* debug: bit 0 = skip the GEMV arithmetic (timing experiments only; results are wrong) */
+  int flags;                 /* debug: bit 0 = skip the GEMV arithmetic (timing experiments only; results are wrong); bits 4..6 =
+                                k (e4m3 models): the decoder's ring copies ask L2 to keep k/8 of their lines (A/B, same tokens) */
   int prefetch_stages;       /* L2 prefetch distance in 16 KiB stages per SM (0 = off) */
   int prefetch_interval;     /* SM cycles between prefetches (0 = 700) */
   unsigned long long* prof;  /* debug: DEVICE buffer [n_sms][16] u64 filled with per-CTA phase timers; null = off */

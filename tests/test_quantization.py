@@ -84,7 +84,10 @@ def test_quantized_model_halves_the_linear_bytes_and_declines_the_fused_kernels(
                               for ts in (st.wqkv, st.wo, st.wgu, st.wdown) for t in ts)
     assert 0.50 <= lin_bytes(model) / lin_bytes(model_1b) <= 0.51       # e4m3 bytes + one fp32 scale per output channel
     st = LMState(model, 1, max_len=48)
-    assert not st.fused_supported(SamplerSpec()) and not st.fast_supported(SamplerSpec())
+    # the batch-1 frame kernel reads e4m3 blobs; the batched tensor-core chain (and the prompt pass on its kernels) declines them
+    assert st.fused_supported(SamplerSpec()) and not st.fast_supported(SamplerSpec()) and not st._prefill_fast_ok()
+    st2 = LMState(model, 3, max_len=48)
+    assert not st2.fast_supported(SamplerSpec())
     with pytest.raises(RuntimeError):
         model.load_weights(csm_weights)
 
@@ -114,6 +117,25 @@ def test_quantized_teacher_forced_logits_vs_oracle_on_dequantised_weights(quanti
         worst = max(worst, float((st.c0_logits.cpu()[0] - ref[0]).abs().max()), float((lg.cpu()[0, 1:] - ref[1:]).abs().max()))
         st.backbone_step(fr)
     assert worst < 1e-4, worst
+
+
+@pytest.mark.gpu
+def test_quantized_frame_kernel_equals_row_based_path(quantized_pair, monkeypatch):
+    """The persistent frame kernel on e4m3 blobs (k_frame: the same units at one byte per weight, scale on the finished
+    dot product) and the row-based GEMV path (CSMB_DISABLE_FUSED=1) are two implementations of the quantised frame: same
+    greedy tokens over 10 frames; a batch of 3 (row-based path only) reproduces the single utterance."""
+    from csm_mlx_b200 import generation, tokenizers
+    from tests.workloads import cfg1_prompt_ids, prompt_ids
+
+    model, _ = quantized_pair
+    p0 = tokenizers.tokenize_text_segment(cfg1_prompt_ids(), 0)
+    (fused,) = generation.generate_tokens(model, [p0], 10, temperature=0.0)
+    monkeypatch.setenv("CSMB_DISABLE_FUSED", "1")
+    (rows,) = generation.generate_tokens(model, [p0], 10, temperature=0.0)
+    assert torch.equal(fused, rows)
+    others = [tokenizers.tokenize_text_segment(prompt_ids(500 + i, 7 + i), 1) for i in range(2)]
+    batch = generation.generate_tokens(model, [p0] + others, 4, temperature=0.0)
+    assert torch.equal(batch[0], rows[:4])
 
 
 @pytest.mark.gpu
