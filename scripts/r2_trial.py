@@ -87,10 +87,13 @@ def _chain():
 def _lanes():
     """G independent lanes of 64/G sequences, each a CUDA-graph replay of the chain on its own stream.  With a <= 100 KiB
     shared-memory budget two Linear CTAs fit one SM, so the lanes' latency-bound kernels can overlap."""
-    for smem in (0, 96, 64):
+    total = int(os.environ.get("R2_LANES_TOTAL", "64"))
+    for smem in (0, 96):
         setenv(CSMB_CHAIN_SMEM_KB=smem or None)
         for G in (1, 2, 4):
-            B = 64 // G
+            B = total // G
+            if B < 1:
+                continue
             streams = [torch.cuda.Stream(dev) for _ in range(G)]
             states, prevs = [], []
             for gi in range(G):
@@ -124,7 +127,7 @@ def _lanes():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
-            print(f"lanes smem_kb={smem or 200} G={G} x B={B}: {ms:.3f} ms per step of all 64 -> {64 * 0.08 / (ms / 1e3):.0f} audio-s/s",
+            print(f"lanes smem_kb={smem or 200} G={G} x B={B}: {ms:.3f} ms per step of all {total} -> {total * 0.08 / (ms / 1e3):.0f} audio-s/s",
                   flush=True)
             del states
     setenv(CSMB_CHAIN_SMEM_KB=None)
