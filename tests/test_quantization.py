@@ -163,3 +163,23 @@ def test_quantized_greedy_generation_vs_oracle(quantized_pair):
     assert f"{model.backbone.wqkv[0].dtype}" == "torch.uint8"
     # the bf16 model gives other tokens: the mode really changes the weights
     assert np.unique(got.numpy()).size > 32
+
+
+@pytest.mark.gpu
+def test_quantized_model_through_the_engine(quantized_pair, mimi_gpu):
+    """serving.Engine with a weight-only FP8 model: the chain declines it, the engine serves the requests on the row-based
+    path (continuous batching unchanged); every request's tokens equal the utterance generated alone."""
+    from csm_mlx_b200 import generation, tokenizers
+    from csm_mlx_b200.serving import Engine
+    from tests.workloads import prompt_ids
+
+    model, _ = quantized_pair
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(600 + i, 6 + 2 * i), i % 2) for i in range(3)]
+    eng = Engine(model, max_batch=2, max_len=64)          # 3 requests through 2 slots: the third is admitted mid-run
+    ids = [eng.submit_prompt(t, m, 4 + i) for i, (t, m) in enumerate(prompts)]
+    eng.run()
+    for i, rid in enumerate(ids):
+        (alone,) = generation.generate_tokens(model, [prompts[i]], 4 + i, temperature=0.0)
+        assert torch.equal(alone, eng.tokens(rid)), i
+    wav = eng.audio(ids[:1])[0]
+    assert wav.shape == (4 * 1920,) and bool(torch.isfinite(wav).all())
