@@ -95,6 +95,7 @@ struct GpArgs {
   // L2 prefetch hint: bytes [pf, pf + pf_bytes) are weights a LATER Linear of the chain streams; CTA c of n asks L2 for slice c
   const char* pf;
   unsigned pf_bytes;
+  int keep8;   // k: the weight stream asks L2 to keep k/8 of its lines (evict-last) instead of evict-first for all
 };
 
 // dynamic smem: [stage][ W 128x64 | Xhi RNx64 | Xlo RNx64 ] bf16, 1024-byte aligned tiles
@@ -145,7 +146,7 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   const int ni = nk < BF_NI ? nk : BF_NI;   // issuers with work
   uint32_t ncols = 32;   // RN % 16 == 0 and the epilogue loads 16 columns at a time: no load reads past an accumulator
   while ((int)ncols < BF_NI * 2 * RN) ncols <<= 1;
-  const uint64_t wpol = l2_policy_evict_first();
+  const uint64_t wpol = a.keep8 > 0 ? l2_policy_keep_fraction((float)a.keep8 * 0.125f) : l2_policy_evict_first();
   auto load_w = [&](unsigned char* dst, int kb, uint64_t* bar) {
     if (a.dbg & 32) {   // A/B: default L2 policy
       if (GU) {
@@ -1599,7 +1600,8 @@ static int bf_ring_depth(int fit, int dbg) {
 
 // y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
-                   const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, const void* pf = nullptr, size_t pf_bytes = 0) {
+                   const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, const void* pf = nullptr, size_t pf_bytes = 0,
+                   int keep8 = 0) {
   CSMB_REQUIRE(R > 0 && N > 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int S = bf_pick_split(N, K);
   CSMB_REQUIRE((size_t)S * R * N <= w.part_floats);
@@ -1612,7 +1614,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2);
-  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128 | 2048), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes};
+  GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128 | 2048), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
@@ -1623,7 +1625,7 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
 
 // SwiGLU MLP first half in one launch: w.hi2 / w.lo2 [R][F] = split(silu(x Wg^T) * (x Wu^T)), Wgu = gate rows then up rows
 static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K, cudaStream_t st, const void* pf = nullptr,
-                      size_t pf_bytes = 0) {
+                      size_t pf_bytes = 0, int keep8 = 0) {
   CSMB_REQUIRE(R > 0 && F % (TC_BM / 2) == 0 && K % TC_BK == 0 && (reinterpret_cast<uintptr_t>(Wgu) & 15) == 0);
   const int RN = R <= 128 ? ((R + 15) / 16) * 16 : 128;   // token rows per tile: 2 RN <= 256 accumulator columns (hi | lo)
   CUtensorMap mw, mhi, mlo;
@@ -1633,7 +1635,7 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
-  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128 | 2048), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes};
+  GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128 | 2048), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
   const size_t smem = stage * nstages + 1024;
   CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
@@ -1716,15 +1718,15 @@ static int bf_attn(const FastWs& w, const csmb_llama& L, PartIn qkv, float* pool
 // weight of the norm after the last layer, is applied to rows b*rps + rps-1 only (R -> B rows).
 static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool, size_t layer_stride,
                      const int32_t* block_table, int max_pages, const int32_t* pos_arr, int pos0, int rps, int B,
-                     float* y32_final, cudaStream_t st) {
+                     float* y32_final, cudaStream_t st, int keep8 = 0) {
   const int d = L.d_model, F = L.d_ff, R = B * rps;
   const int nqkv = (L.n_heads + 2 * L.n_kv_heads) * L.head_dim;
   int rc;
   PartIn part;
   for (int l = 0; l < L.n_layers; ++l) {
-    if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st))) return rc;
+    if ((rc = bf_gemm(w, L.wqkv[l], R, nqkv, d, &part, st, nullptr, nullptr, nullptr, 0, keep8))) return rc;
     if ((rc = bf_attn(w, L, part, pool + (size_t)l * layer_stride, block_table, max_pages, pos_arr, pos0, rps, B, st))) return rc;
-    if ((rc = bf_gemm(w, L.wo[l], R, d, L.n_heads * L.head_dim, &part, st))) return rc;
+    if ((rc = bf_gemm(w, L.wo[l], R, d, L.n_heads * L.head_dim, &part, st, nullptr, nullptr, nullptr, 0, keep8))) return rc;
     if ((rc = bf_norm(w, x, d, part, 2, L.norm_post[l], L.eps, nullptr, R, 1, 0, st))) return rc;
     if (w.cc.dbg & 4) {
       if ((rc = bf_gemm(w, L.wgu[l], R, 2 * F, d, &part, st))) return rc;
@@ -1732,9 +1734,9 @@ static int bf_layers(const FastWs& w, const csmb_llama& L, float* x, float* pool
       CSMB_CUDA(bf_launch(w.cc, k_swiglu_split, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, part, F, total4, w.hi2, w.lo2));
     } else {
       // its CTAs also pull the down matrix towards L2: the down Linear's CTAs only become resident as these leave
-      if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st, L.wdown[l], (size_t)d * F * 2))) return rc;
+      if ((rc = bf_gemm_gu(w, L.wgu[l], R, F, d, st, L.wdown[l], (size_t)d * F * 2, keep8))) return rc;
     }
-    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st, w.hi2, w.lo2))) return rc;
+    if ((rc = bf_gemm(w, L.wdown[l], R, d, F, &part, st, w.hi2, w.lo2, nullptr, 0, keep8))) return rc;
     if (l + 1 < L.n_layers) {
       if ((rc = bf_norm(w, x, d, part, 2, L.norm_in[l + 1], L.eps, nullptr, R, 1, 0, st))) return rc;
     } else {
@@ -1827,7 +1829,9 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
   CSMB_CUDA(bf_launch(w.cc, k_sample_embed, dim3(B), dim3(256), lg_smem, st, part, V, sa, pos, 0, frame, ncb, m->audio_emb, db, 1,
                       (const float*)w.h_last, w.hi, w.lo, 2, no_proj, lg_staged));
   lg_smem = lg_smem_of(dd, &lg_staged);
-  // ---- depth decoder (generation.py:56-90)
+  // ---- depth decoder (generation.py:56-90).  Its 222 MB of layer weights are streamed 31 times per frame-step: the Linears ask
+  // L2 to keep dec_keep8 / 8 of those lines (evict-last), so that that share of every later step comes from L2
+  const int dec_keep8 = (w.cc.dbg >> 12) & 7;
   for (int i = 1; i < ncb; ++i) {
     const int rps = (i == 1) ? 2 : 1, R = B * rps;
     if (i == 1 || ptab == nullptr) {
@@ -1836,7 +1840,7 @@ int csmb_decode_frame_fast_admit(const csmb_model* m, const csmb_batch* bt, cons
       if ((rc = bf_norm(w, w.dx, dd, part, 1, D.norm_in[0], D.eps, nullptr, R, 1, 0, st))) return rc;
     }
     if ((rc = bf_layers(w, D, w.dx, bt->dec_kv_pool, bt->dec_kv_layer_stride, nullptr, dec_pages, nullptr, i == 1 ? 0 : i, rps, B,
-                        nullptr, st)))
+                        nullptr, st, dec_keep8)))
       return rc;
     if ((rc = bf_gemm(w, m->audio_head_t + (size_t)(i - 1) * V * dd, B, V, dd, &part, st))) return rc;
     sa.draw_base = draw_base + (uint64_t)i;

@@ -97,6 +97,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// evict-last for `fraction` of the lines, evict-first for the rest: a matrix set that is streamed again and again (the depth
+// decoder: 31 times per frame) and is larger than L2 keeps that share of itself resident
+__device__ __forceinline__ uint64_t l2_policy_keep_fraction(float fraction) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+  return p;
+}
 __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(

@@ -225,7 +225,8 @@ typedef struct {
                                kernel (dependent L2 round trips) instead of the shared-memory staged ones, 16 = partial sums
                                with plain loads instead of cp.async staging, 32 = default L2 policy for the weight stream,
                                64 / 128 = no L2 prefetch of a Linear's own remaining / the next Linear's weights,
-                               256 = at most 8 pipeline stages */
+                               256 = at most 8 pipeline stages, bits 12..14 = k: the depth decoder's Linears ask L2 to keep
+                               k/8 of their weight lines (evict-last) across the 31 depth steps (measured slower; default 0) */
   int smem_kb;              /* shared-memory budget of a Linear CTA in KiB (48..200, 0 = 200): <= 100 lets two Linear CTAs
                                (of this or of another stream's chain) share an SM */
   const float* proj_table;  /* optional DEVICE table of csmb_build_proj_table: depth steps >= 2 read projection(embedding)
