@@ -123,7 +123,9 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[BF_MAX_STAGES], empty[BF_MAX_STAGES], acc_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ int gu_failed_s;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) gu_failed_s = 0;
 #ifdef CSMB_TIMELINE
   __shared__ unsigned tl_slot_s;
   if (tl_block0() && threadIdx.x == 0) tl_slot_s = tl_enter(GU ? 2u : 1u);
@@ -306,19 +308,6 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
           for (int j = 0; j < 16; ++j) mine[(size_t)(c0 + j) * 64] = o[j];
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ok) {
-        const int f0 = n0 / 2, te = threadIdx.x - 32 * (1 + BF_NI);  // 0 .. 127
-        const int rows = min(RN, a.R - r0);
-        for (int idx = te; idx < rows * 16; idx += 128) {
-          const int t = idx >> 4, f4 = (idx & 15) * 4;
-          const float4 g = *reinterpret_cast<const float4*>(ex + (size_t)t * 64 + f4);
-          const float4 u = *reinterpret_cast<const float4*>(ex + (size_t)(RN + t) * 64 + f4);
-          const size_t o = (size_t)(r0 + t) * a.F + f0 + f4;
-          store_split4(a.out_hi + o, a.out_lo + o, (g.x / (1.f + expf(-g.x))) * u.x, (g.y / (1.f + expf(-g.y))) * u.y,
-                       (g.z / (1.f + expf(-g.z))) * u.z, (g.w / (1.f + expf(-g.w))) * u.w);
-        }
-      }
     } else if (ok) {
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
       for (int c0 = 0; c0 < RN; c0 += 16) {
@@ -339,11 +328,29 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-#ifdef CSMB_TIMELINE
-    if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 4);
-#endif
+    if (GU && !ok) gu_failed_s = 1;   // a bounded wait timed out (a.err is set): the second half below stays off
   }
   __syncthreads();
+  if (GU) {
+    // Second half of the SwiGLU epilogue on ALL warps of the CTA (the producer and the MMA warps are done by now): the four
+    // epilogue warps alone are ALU-bound on the exponentials, divisions and hi / lo splits of up to 64 rows x 64 features.
+    const float* ex = reinterpret_cast<const float*>(smem);
+    if (gu_failed_s == 0) {
+      const int f0 = n0 / 2;
+      const int rows = min(RN, a.R - r0);
+      for (int idx = threadIdx.x; idx < rows * 16; idx += BF_THREADS) {
+        const int t = idx >> 4, f4 = (idx & 15) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(ex + (size_t)t * 64 + f4);
+        const float4 u = *reinterpret_cast<const float4*>(ex + (size_t)(RN + t) * 64 + f4);
+        const size_t o = (size_t)(r0 + t) * a.F + f0 + f4;
+        store_split4(a.out_hi + o, a.out_lo + o, (g.x / (1.f + expf(-g.x))) * u.x, (g.y / (1.f + expf(-g.y))) * u.y,
+                     (g.z / (1.f + expf(-g.z))) * u.z, (g.w / (1.f + expf(-g.w))) * u.w);
+      }
+    }
+  }
+#ifdef CSMB_TIMELINE
+  if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 4);
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }

@@ -20,10 +20,18 @@ bool tc_make_map_ld(CUtensorMap* m, const void* base, long long rows, int K, int
 #ifdef __CUDACC__
 
 // ---- bf16 hi/lo split of fp32 activations: x = hi + lo up to 2^-17 relative ---------------------------------------
+// Round to nearest even with the hardware conversion (cvt.rn.bf16[x2].f32: one instruction instead of ~5 integer ops per
+// value; for finite inputs the same bits as the integer form u += 0x7fff + ((u >> 16) & 1), which this replaced).
 __device__ __forceinline__ uint16_t f32_to_bf16_rn(float f) {
-  uint32_t u = __float_as_uint(f);
-  u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even (inputs are finite)
-  return (uint16_t)(u >> 16);
+  uint16_t h;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(f));
+  return h;
+}
+// two fp32 -> packed bf16 pair (element 0 in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
 }
 __device__ __forceinline__ void split_bf16(float f, uint16_t& h, uint16_t& l) {
   h = f32_to_bf16_rn(f);
@@ -31,13 +39,11 @@ __device__ __forceinline__ void split_bf16(float f, uint16_t& h, uint16_t& l) {
 }
 // four values -> 4 hi + 4 lo, 8-byte stores (dst 8-byte aligned)
 __device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, float a, float b, float c, float d) {
-  uint16_t h[4], l[4];
-  split_bf16(a, h[0], l[0]);
-  split_bf16(b, h[1], l[1]);
-  split_bf16(c, h[2], l[2]);
-  split_bf16(d, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-  *reinterpret_cast<uint2*>(lo) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+  const uint32_t h01 = pack_bf16x2_rn(a, b), h23 = pack_bf16x2_rn(c, d);
+  const uint32_t l01 = pack_bf16x2_rn(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
+  const uint32_t l23 = pack_bf16x2_rn(c - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
+  *reinterpret_cast<uint2*>(hi) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(lo) = make_uint2(l01, l23);
 }
 
 // ---- programmatic dependent launch (griddepcontrol): both are no-ops for a kernel launched without the attribute ----
@@ -181,19 +187,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// two fp32 -> packed bf16 pair (element 0 in the low half), round to nearest even: one cvt instead of ~10 integer ops
-__device__ __forceinline__ uint32_t pack_bf16x2_rn(float e0, float e1) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
-  return d;
-}
-// four values -> 4 hi + 4 lo (x = hi + lo up to 2^-17), 8-byte stores; the cvt form of store_split4
+// (the cvt form is now store_split4 itself; the name is kept for the codec's callers)
 __device__ __forceinline__ void store_split4_cvt(uint16_t* hi, uint16_t* lo, float a, float b, float c, float d) {
-  const uint32_t h01 = pack_bf16x2_rn(a, b), h23 = pack_bf16x2_rn(c, d);
-  const uint32_t l01 = pack_bf16x2_rn(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
-  const uint32_t l23 = pack_bf16x2_rn(c - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
-  *reinterpret_cast<uint2*>(hi) = make_uint2(h01, h23);
-  *reinterpret_cast<uint2*>(lo) = make_uint2(l01, l23);
+  store_split4(hi, lo, a, b, c, d);
 }
 
 #endif  // __CUDACC__
