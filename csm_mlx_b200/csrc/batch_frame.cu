@@ -32,7 +32,8 @@ constexpr int BF_MAX_STAGES = 10;
 #define CSMB_BF_NI 2
 #endif
 constexpr int BF_NI = CSMB_BF_NI;                 // MMA-issuing warps (= fp32 accumulators) per Linear CTA: 1 or 2
-constexpr int BF_THREADS = 32 * (1 + BF_NI + 4);  // warp 0: TMA producer; warps 1 .. BF_NI: MMA issuers; then 4 epilogue warps
+constexpr int BF_THREADS = 256;                  // warp 0: TMA producer; warps 1 .. BF_NI: MMA issuers; warps 3..6: epilogue; all 8 warps share the epilogue (below)
+static_assert(BF_NI <= 2, "warp roles below");
 static_assert(BF_MAX_STAGES % BF_NI == 0, "a pipeline stage must always be consumed by the same issuer");
 constexpr size_t BF_SMEM_BUDGET = 200 * 1024;
 
@@ -182,6 +183,10 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
+  // Warp roles: warp 0 = TMA producer, warps 1 .. BF_NI = MMA issuers (one lane each); then ALL eight warps run the epilogue —
+  // a warp reads the TMEM lane quarter warp % 4, so every quarter has two warps (3..6 take the even 16-column chunks of their
+  // quarter, 0, 1, 2 and 7 the odd ones): with 64 token rows the epilogue is four chunks of TMEM loads, adds and 16 row
+  // stores per thread, and four warps alone were its bottleneck (same sums, same stores: bit-identical).
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -262,14 +267,17 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       }
       umma_commit(&acc_full);
     }
-  } else {
-    // ===== epilogue: four warps -> TMEM lane quarters (warp % 4) =====
+  }
+  __syncwarp();
+  {
+    // ===== epilogue: TMEM lane quarter warp % 4; chunk parity by warp =====
     pdl_wait();  // `part` may still be read by the previous kernel of the stream
     const int quarter = warp & 3;
+    const int cpar = (warp >= 3 && warp <= 6) ? 0 : 1;   // which 16-column chunks of the quarter this warp takes
     const bool ok = tc_mbar_wait(&acc_full, 0, a.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef CSMB_TIMELINE
-    if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 3);
+    if (tl_block0() && threadIdx.x == 96) tl_mark(tl_slot_s, 3);
 #endif
     const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // 16 consecutive token columns c0 .. c0+15 of this thread's weight row: (sum of the issuers' W.hi) + (sum of their W.lo),
@@ -301,7 +309,7 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       float* ex = reinterpret_cast<float*>(smem);
       if (ok) {
         float* mine = ex + (size_t)(quarter >> 1) * RN * 64 + (quarter & 1) * 32 + lane;
-        for (int c0 = 0; c0 < RN; c0 += 16) {
+        for (int c0 = cpar * 16; c0 < RN; c0 += 32) {
           float o[16];
           load_cols(c0, o);
 #pragma unroll
@@ -310,7 +318,7 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       }
     } else if (ok) {
       float* dst0 = a.part + (size_t)blockIdx.z * a.R * a.N + n;
-      for (int c0 = 0; c0 < RN; c0 += 16) {
+      for (int c0 = cpar * 16; c0 < RN; c0 += 32) {
         float o[16];
         if (a.dbg & 2) {
 #pragma unroll
@@ -349,7 +357,7 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     }
   }
 #ifdef CSMB_TIMELINE
-  if (tl_block0() && threadIdx.x == 32 * (1 + BF_NI)) tl_mark(tl_slot_s, 4);
+  if (tl_block0() && threadIdx.x == 96) tl_mark(tl_slot_s, 4);
 #endif
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
