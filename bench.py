@@ -608,13 +608,17 @@ def run_ours(args):
                              f"chain + {last['eager_launches']} eagerly launched (admission prefill, Mimi decode)",
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE frame-step (all 1 047 launches) at 64 sequences from ncu
+                     # launch lists of scripts/ncu_fast.py (profiles/r02b_chain_ncu.md): 7.72 GB with --cache-control none (L2
+                     # warm, a kernel's replays partly hit L2), 12.46 GB with ncu's default cache flush before every launch (every
+                     # partial / plane / prefetched weight re-read from DRAM); the live step lies between, at the algorithmic bytes
+                     "traffic": 7.715e9 if B_rank == 64 else None, "traffic_cold_caches": 12.46e9 if B_rank == 64 else None,
                      "kernel": f"frame-step of the fused chain (csrc/batch_frame.cu) at {B_rank} sequences: one CUDA-graph replay = {graph_launches} launches "
                                "(csmb::k_gemm_part_t tcgen05 linears + fused element-wise kernels)",
                      "ms_per_frame_step": step_ms, "algorithmic_bytes_per_frame_step": alg,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "note": "bytes = bf16 weights streamed once per step for the whole batch (projection matrix only in depth step 1: "
-                             "projected-embedding table) + per-sequence KV / embedding terms; traffic: see profiles/r02_chain_ncu.md"},
+                             "projected-embedding table) + per-sequence KV / embedding terms; traffic: per frame-step like `achieved`, see profiles/r02b_chain_ncu.md"},
         "cpu_baseline": cpu,
         "tokens_checksum": checksum,
         "tokens_checksum_expected": CFG4_TOKENS_CHECKSUM,
