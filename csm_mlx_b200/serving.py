@@ -299,6 +299,10 @@ class Engine:
             codes[i, :, : t.shape[0]] = t.t()
         audio = mimi.decode(codes.to(self.model.device))
         if to_host:
-            audio = audio.to("cpu")
-            return [audio[i, 0, : 1920 * int(t.shape[0])].clone() for i, t in enumerate(toks)]
+            # one device-to-host copy into pinned memory (torch's caching host allocator: the block is reused once the
+            # caller drops the previous result); the returned tensors are views of that one buffer
+            host = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+            host.copy_(audio, non_blocking=True)
+            torch.cuda.current_stream(self.model.device).synchronize()
+            return [host[i, 0, : 1920 * int(t.shape[0])] for i, t in enumerate(toks)]
         return [audio[i, 0, : 1920 * int(t.shape[0])] for i, t in enumerate(toks)]
