@@ -199,12 +199,11 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
         tc_mbar_expect_tx(&full[kb], w_bytes + 2 * x_bytes);
         load_w(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
       }
-      // The ring holds NS of this CTA's nk weight blocks; the others would only be requested as stages drain, each refill
-      // paying the DRAM latency with at most NS x 16 KiB in flight (a latency-bound ~30 GB/s per CTA).  Ask L2 for them now
-      // (TMA tensor prefetch, same boxes) — the CTA is resident long before its producer kernel finishes and HBM idles
-      // through the small kernels in between — and for this CTA's slice of the next big Linear's matrix, whose CTAs cannot
-      // become resident before this kernel's CTAs leave.  Hints only: no result depends on them.
-      if (!(a.dbg & 64)) {
+      // L2 prefetch hints (no result depends on them).  (a) This CTA's slice of the NEXT big Linear's matrix, whose CTAs cannot
+      // become resident before this kernel's CTAs leave: +1 % at B <= 16, +1.5 % at B = 64.  (b) The CTA's own weight blocks
+      // beyond the ring (TMA tensor prefetch, same boxes): measured useless at small batches and -1.5 % at B = 64 on top of
+      // (a) — off unless flag 64 asks for it (A/B).
+      if (a.dbg & 64) {
         for (int kb = pre; kb < nk; ++kb) {
           if (GU) {
             tma_prefetch_2d(&map_w, (kb0 + kb) * TC_BK, n0 / 2);

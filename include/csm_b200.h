@@ -224,7 +224,8 @@ typedef struct {
                                Same tokens, other kernels / hints: 4 = SwiGLU as a separate launch, 8 = the round-1 attention
                                kernel (dependent L2 round trips) instead of the shared-memory staged ones, 16 = partial sums
                                with plain loads instead of cp.async staging, 32 = default L2 policy for the weight stream,
-                               64 / 128 = no L2 prefetch of a Linear's own remaining / the next Linear's weights,
+                               64 = also L2-prefetch a Linear CTA's own weight blocks beyond its ring, 128 = no L2 prefetch of
+                               the next big Linear's weights,
                                256 = at most 8 pipeline stages, bits 12..14 = k: the depth decoder's Linears ask L2 to keep
                                k/8 of their weight lines (evict-last) across the 31 depth steps (measured slower; default 0) */
   int smem_kb;              /* shared-memory budget of a Linear CTA in KiB (48..200, 0 = 200): <= 100 lets two Linear CTAs
