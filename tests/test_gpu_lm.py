@@ -347,6 +347,33 @@ def test_chain_staged_kernels_are_bit_identical_to_the_plain_ones(model_1b, devi
     assert int((shipped[1:] != shipped[:-1]).sum()) > 0
 
 
+def test_chain_chunked_attention_long_cache_equals_plain_kernel(model_1b, device, monkeypatch):
+    """k_attn_decode_chunked over many 64-position chunks (caches of 705 and 1 300 positions, a 9-row one beside them) against
+    the round-1 kernel (flag 8): identical tokens over 3 frames."""
+    spec = SamplerSpec(temperature=0.0)
+    prompts = [tokenizers.tokenize_text_segment(prompt_ids(400 + i, n), 0) for i, n in enumerate((703, 7, 1298))]
+
+    def run(f):
+        monkeypatch.setenv("CSMB_CHAIN_FLAGS", str(f))
+        st = LMState(model_1b, len(prompts), max_len=1312, row_invariant=True)
+        assert st.fast_supported(spec)
+        st.prefill([p[0] for p in prompts], [p[1] for p in prompts])
+        frame = torch.zeros((len(prompts), 32), device=device, dtype=torch.int32)
+        st.sample_c0(frame, spec)
+        st.depth_decode(frame, spec)
+        out, prev = [frame.clone()], frame
+        for _ in range(3):
+            nxt = torch.zeros_like(prev)
+            st.decode_frame(prev, nxt, spec)
+            out.append(nxt.clone())
+            prev = nxt
+        torch.cuda.synchronize()
+        st.check_status()
+        return torch.stack(out).cpu()
+
+    assert torch.equal(run(0), run(8))
+
+
 def test_chain_projected_embedding_table_is_bit_exact(model_1b, monkeypatch):
     """csmb_build_proj_table: depth steps >= 2 read projection(embed_audio(cb, token)) rows from a table built with the
     chain's own projection Linear instead of running that Linear (60 launches less per frame-step): identical tokens,
