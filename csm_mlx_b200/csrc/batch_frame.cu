@@ -116,7 +116,17 @@ struct GpArgs {
 // the number of stages is a multiple of it: a row's sums never depend on the row count, and a stage always belongs to the
 // same issuer (an mbarrier parity wait cannot tell the second from the third use of a stage apart, so one thread must see
 // every use of "its" stages in order).
-template <bool GU>
+//
+// PAIR = true (launched as clusters of two CTAs along the n-tile axis, csmb_chain_opts flag 4096 / bf_pair_wanted): the two
+// CTAs share the token operand through ONE tcgen05.mma.cta_group::2 of M = 256 per K step, issued by the pair's leader: CTA r
+// holds its own 128 weight rows and HALF of the stacked token operand (rank 0: the hi plane's RN rows, rank 1: the lo plane's)
+// at the same stage offsets, so a CTA pulls W + RN rows per K block instead of W + 2 RN — with 64 sequences the token planes
+// are half of what a CTA reads, every CTA re-reads all of them from L2, and the Linears of a 64-sequence step run at the L2 ->
+// SM fill rate (128 CTAs x 422 KB in 5.4 us = 10 TB/s of the ~12 TB/s the chip delivers).  Both CTAs' TMA copies count their
+// bytes on the LEADER's full barrier; the leader's commits are multicast to the empty / acc_full barriers of both CTAs; the
+// accumulator rows of a CTA's weight tile land in its own TMEM, so the epilogue is unchanged.  Same products summed in the
+// same order as PAIR = false: bit-identical outputs.
+template <bool GU, bool PAIR>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
               const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
@@ -138,7 +148,12 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   const int n0 = blockIdx.x * TC_BM, r0 = (a.dbg & 2048) ? (1 << 20) : blockIdx.y * a.RN;
   const int RN = a.RN;
   const uint32_t w_bytes = TC_BM * TC_BK * 2, x_bytes = (uint32_t)RN * TC_BK * 2;
-  const uint32_t x_off = w_bytes, stage_bytes = (w_bytes + 2 * x_bytes + 1023u) & ~1023u;
+  // a stage holds the weight tile and the token rows THIS CTA loads (PAIR: one plane); stage_tx = bytes counted on a full barrier
+  const uint32_t x_off = w_bytes, stage_bytes = (w_bytes + (PAIR ? 1u : 2u) * x_bytes + 1023u) & ~1023u;
+  const uint32_t stage_tx = PAIR ? 2u * (w_bytes + x_bytes) : w_bytes + 2u * x_bytes;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;          // rank 0 = the pair's leader (issues the MMAs)
+  const uint32_t full0 = PAIR ? cluster_map_shared(s32(&full[0]), 0u) : 0u;   // the leader's full[0] (cluster address)
+  const CUtensorMap* map_x = (PAIR && crank != 0u) ? &map_lo : &map_hi;       // PAIR: the plane this CTA loads
   const int nk_total = a.K / TC_BK, NS = a.nstages;
   const int kb0 = (int)(((long long)nk_total * blockIdx.z) / a.S), kb1 = (int)(((long long)nk_total * (blockIdx.z + 1)) / a.S);
   const int nk = kb1 - kb0;
@@ -151,7 +166,15 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
   while ((int)ncols < BF_NI * 2 * RN) ncols <<= 1;
   const uint64_t wpol = a.keep8 > 0 ? l2_policy_keep_fraction((float)a.keep8 * 0.125f) : l2_policy_evict_first();
   auto load_w = [&](unsigned char* dst, int kb, uint64_t* bar) {
-    if (a.dbg & 32) {   // A/B: default L2 policy
+    if (PAIR) {
+      const uint32_t fb = full0 + (uint32_t)((bar - full) * sizeof(uint64_t));
+      if (GU) {
+        tma_load_2d_pair_hint(dst, &map_w, kb * TC_BK, n0 / 2, fb, wpol);
+        tma_load_2d_pair_hint(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, fb, wpol);
+      } else {
+        tma_load_2d_pair_hint(dst, &map_w, kb * TC_BK, n0, fb, wpol);
+      }
+    } else if (a.dbg & 32) {   // A/B: default L2 policy
       if (GU) {
         tma_load_2d(dst, &map_w, kb * TC_BK, n0 / 2, bar);
         tma_load_2d(dst + (TC_BM / 2) * TC_BK * 2, &map_w, kb * TC_BK, a.F + n0 / 2, bar);
@@ -165,6 +188,15 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
       tma_load_2d_hint(dst, &map_w, kb * TC_BK, n0, bar, wpol);
     }
   };
+  // the token rows of K block kb into a stage (after griddepcontrol.wait: the previous kernel writes them)
+  auto load_x = [&](unsigned char* st, int kb, uint64_t* bar) {
+    if (PAIR) {
+      tma_load_2d_pair(st + x_off, map_x, kb * TC_BK, r0, full0 + (uint32_t)((bar - full) * sizeof(uint64_t)));
+    } else {
+      tma_load_2d(st + x_off, &map_hi, kb * TC_BK, r0, bar);
+      tma_load_2d(st + x_off + x_bytes, &map_lo, kb * TC_BK, r0, bar);
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < BF_MAX_STAGES; ++i) {
@@ -175,11 +207,17 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {   // both CTAs of the pair allocate the same columns (nothing else holds TMEM on an SM a Linear CTA fits on)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any copy or commit signals them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
@@ -191,12 +229,16 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      if (PAIR) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map_x) : "memory");
+      } else {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      }
       // weights do not depend on the previous kernel: fill the pipeline with them before waiting for it
       const int pre = nk < NS ? nk : NS;
       for (int kb = 0; kb < pre; ++kb) {
-        tc_mbar_expect_tx(&full[kb], w_bytes + 2 * x_bytes);
+        if (crank == 0u) tc_mbar_expect_tx(&full[kb], stage_tx);   // (the peer's bytes may land first: the phase still needs this arrival)
         load_w(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
       }
       // L2 prefetch hints (no result depends on them).  (a) This CTA's slice of the NEXT big Linear's matrix, whose CTAs cannot
@@ -226,27 +268,22 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 #ifdef CSMB_TIMELINE
       if (tl_block0()) tl_mark(tl_slot_s, 2);
 #endif
-      for (int kb = 0; kb < pre; ++kb) {
-        unsigned char* st = smem + (size_t)kb * stage_bytes;
-        tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[kb]);
-        tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[kb]);
-      }
+      for (int kb = 0; kb < pre; ++kb) load_x(smem + (size_t)kb * stage_bytes, kb0 + kb, &full[kb]);
       for (int kb = pre; kb < nk; ++kb) {
         const int s = kb % NS;
         const uint32_t par = (kb / NS) & 1;
         if (!tc_mbar_wait(&empty[s], par ^ 1, a.err)) break;
         unsigned char* st = smem + (size_t)s * stage_bytes;
-        tc_mbar_expect_tx(&full[s], w_bytes + 2 * x_bytes);
+        if (crank == 0u) tc_mbar_expect_tx(&full[s], stage_tx);
         load_w(st, kb0 + kb, &full[s]);
-        tma_load_2d(st + x_off, &map_hi, (kb0 + kb) * TC_BK, r0, &full[s]);
-        tma_load_2d(st + x_off + x_bytes, &map_lo, (kb0 + kb) * TC_BK, r0, &full[s]);
+        load_x(st, kb0 + kb, &full[s]);
       }
     }
   } else if (warp <= BF_NI) {
     // ===== MMA issuers: issuer i = warp - 1 takes K blocks i, i + BF_NI, ... into accumulator i =====
     const int iss = warp - 1;
-    if (lane == 0 && iss < ni) {
-      const uint32_t idesc = umma_idesc(2 * RN);
+    if (lane == 0 && iss < ni && crank == 0u) {
+      const uint32_t idesc = PAIR ? umma_idesc_pair(2 * RN) : umma_idesc(2 * RN);
       const uint32_t tacc = tmem_base + (uint32_t)(iss * 2 * RN);
       bool ok = true;
       for (int kb = iss; kb < nk && ok; kb += BF_NI) {
@@ -260,11 +297,14 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t koff = (uint64_t)((k * 32) >> 4);
-          umma_f16(tacc, da + koff, dx + koff, idesc, (kb != iss) || (k != 0));
+          if (PAIR) umma_f16_pair(tacc, da + koff, dx + koff, idesc, (kb != iss) || (k != 0));
+          else umma_f16(tacc, da + koff, dx + koff, idesc, (kb != iss) || (k != 0));
         }
-        umma_commit(&empty[s]);
+        if (PAIR) umma_commit_pair(&empty[s]);
+        else umma_commit(&empty[s]);
       }
-      umma_commit(&acc_full);
+      if (PAIR) umma_commit_pair(&acc_full);
+      else umma_commit(&acc_full);
     }
   }
   __syncwarp();
@@ -358,8 +398,10 @@ k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 #ifdef CSMB_TIMELINE
   if (tl_block0() && threadIdx.x == 96) tl_mark(tl_slot_s, 4);
 #endif
+  if (PAIR) cluster_sync_all();   // both CTAs are done with their accumulators and with each other's shared memory
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
 
@@ -1548,6 +1590,27 @@ static cudaError_t bf_launch(const ChainCfg& cc, void (*kern)(KArgs...), dim3 gr
   count_launch();
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+// the same as clusters of two CTAs along x (CTA pairs of one TPC: k_gemm_part_t<., true>)
+template <typename... KArgs, typename... Args>
+static cudaError_t bf_launch_pair(const ChainCfg& cc, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cc.pdl ? 2 : 1;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 struct FastWs {
   int* err;
@@ -1612,6 +1675,18 @@ static int bf_ring_depth(int fit, int dbg) {
   return n;
 }
 
+// CTA pairs (k_gemm_part_t<., true>) for a Linear of `tiles` n-tiles: opt-in per call (csmb_chain_opts flag 4096) while it is
+// being measured; needs an even number of n-tiles (a pair = two neighbouring tiles, same token rows, same K range).  Outputs
+// are bit-identical either way, so the choice may depend on anything.
+#ifndef CSMB_PAIR_MIN_ROWS
+#define CSMB_PAIR_MIN_ROWS 0   // > 0: every Linear over at least this many token rows runs as CTA pairs (prompt passes)
+#endif
+static bool bf_pair_wanted(const ChainCfg& cc, int tiles, bool gu, int R) {
+  if (tiles % 2 != 0) return false;
+  if (CSMB_PAIR_MIN_ROWS > 0 && R >= CSMB_PAIR_MIN_ROWS) return true;
+  return (cc.dbg & (gu ? 4096 : 8192)) != 0;
+}
+
 // y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
                    const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, const void* pf = nullptr, size_t pf_bytes = 0,
@@ -1624,15 +1699,21 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, xhi ? xhi : w.hi, R, K, RN) ||
       !tc_make_map(&mlo, xlo ? xlo : w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
-  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
+  const bool pair = bf_pair_wanted(w.cc, cdiv(N, TC_BM), false, R);
+  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + (pair ? 1 : 2) * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2);
   GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128 | 2048), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
   const size_t smem = stage * nstages + 1024;
-  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
-  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  if (pair) {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<false, true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  } else {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false, false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  }
   *out = PartIn{w.part, S, (size_t)R * N, N};
   return CSMB_OK;
 }
@@ -1645,15 +1726,21 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   CUtensorMap mw, mhi, mlo;
   if (!tc_make_map(&mw, Wgu, 2 * F, K, TC_BM / 2) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
-  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + 2 * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
+  const bool pair = bf_pair_wanted(w.cc, F / (TC_BM / 2), true, R);
+  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + (pair ? 1 : 2) * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
   int nstages = (int)(w.cc.smem / stage);
   nstages = bf_ring_depth(nstages, w.cc.dbg);
   CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
   GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128 | 2048), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
   const size_t smem = stage * nstages + 1024;
-  CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
-  CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  if (pair) {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<true, true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  } else {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
+    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true, false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  }
   return CSMB_OK;
 }
 

@@ -154,6 +154,68 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a 2-CTA cluster (one TPC) run ONE tcgen05.mma of M = 256 ---------------------
+// CTA r holds weight rows [128 r, 128 r + 128) of the A tile and half of the B operand's N rows at the SAME shared-memory
+// offsets; accumulator rows 128 r .. land in CTA r's own TMEM.  Only the leader (rank 0) issues the instruction; both CTAs load
+// their halves with the cta_group::2 form of the TMA copy, whose complete_tx goes to the LEADER's mbarrier; the leader's
+// commit is multicast to the barrier at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster (a superset of __syncthreads)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the executing CTA's shared-memory address `saddr` as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// box -> the executing CTA's shared memory; bytes are counted on the mbarrier at cluster address `bar_cluster`
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          s32(dst)),
+      "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(s32(dst)),
+      "l"(map), "r"(bar_cluster), "r"(x), "r"(y), "l"(policy)
+      : "memory");
+}
+// instruction descriptor as umma_idesc with M = 256 (pair)
+__device__ __forceinline__ uint32_t umma_idesc_pair(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)((2 * TC_BM) >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+          tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all earlier tcgen05.mma of this thread are complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns of the accumulator -> registers (waits for the load)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

@@ -38,6 +38,7 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
+print("checksum h_last / c0_logits:", st.h_last.double().sum().item().hex(), st.c0_logits.double().sum().item().hex(), flush=True)
 print(f"prefill rows={int(tok.shape[0])}: {ms:.3f} ms (GPU, staged inputs)  {2 * 973.1e6 * tok.shape[0] / (ms * 1e-3) / 1e12:.1f} TFLOP/s", flush=True)
 torch.cuda.cudart().cudaProfilerStart()
 st.reset()
