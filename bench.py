@@ -414,7 +414,27 @@ def context_config(model, mimi, dev):
         t_long, _ = timed(dev, long_pass, 2)
         stl.check_status()
         rows_l = int(tok_l.shape[0])
+        del stl
+        # the same conversation through the serving engine: the step that admits a turn, context KV prefilled (first turn:
+        # prefix-cache miss) vs copied from the KV prefix cache (next turn: hit); both include the frame-step itself
+        from csm_mlx_b200 import serving
+
+        eng = serving.Engine(model, max_batch=1, max_len=rows + 48)
+
+        def admission_step(text):
+            eng.submit(text, 0, segs, max_audio_length_ms=160)
+            t, _ = timed(dev, eng.step)
+            eng.run()
+            return t
+        admission_step("a first turn to warm up")                     # graph capture, allocations
+        eng.kv_cache = serving.KVPrefixCache()
+        t_miss = admission_step("and now the answer")
+        t_hit = admission_step("and one more answer")
+        kv_stats = (eng.kv_cache.hits, eng.kv_cache.misses, eng.kv_cache.nbytes)
+        eng.state.check_status()
+        del eng
         return {"prompt_rows": rows, "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
+                "engine_admission_step_ms": {"kv_prefix_miss": t_miss, "kv_prefix_hit": t_hit, "cache_hits_misses_bytes": kv_stats},
                 "prefill_tflops": 2 * 973.1e6 * rows / (t_pre * 1e-3) / 1e12, "ms_per_frame": t_f,
                 "prefill_long": {"prompt_rows": rows_l, "ms": t_long, "tflops": 2 * 973.1e6 * rows_l / (t_long * 1e-3) / 1e12},
                 "note": "prefill = host staging + backbone over all prompt rows on the chain's kernels (csmb_prefill_fast: one tcgen05 launch per "

@@ -9,7 +9,7 @@ from .generation import generate, generate_batch, generate_frame, make_cache, st
 from .models import CSM, ModelArgs, csm_1b, csm_tiny
 from .sample_utils import make_logits_processors, make_sampler
 from .segment import Segment
-from .serving import ContextCache, Engine
+from .serving import ContextCache, Engine, KVPrefixCache
 
 
 def _out_of_scope(name):

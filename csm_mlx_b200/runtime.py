@@ -328,16 +328,36 @@ class LMState:
         for s, n in zip(slots, lens):
             self.pos_host[s] += n
 
-    def arm_admission(self, slots: Sequence[int], tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor]) -> None:
+    def export_kv_prefix(self, slot: int, n_rows: int) -> torch.Tensor:
+        """A copy of the backbone KV pages that hold positions [0, n_rows) of ``slot`` ((layers, pages, page floats), stream
+        ordered).  The prompt pass is row-invariant, so these entries depend on the slot's first n_rows prompt rows only."""
+        n_pages = -(-int(n_rows) // _lib.PAGE)
+        p0 = slot * self.pages_per_seq
+        return self.kv_pool[:, p0:p0 + n_pages].clone()
+
+    def import_kv_prefix(self, slot: int, pages: torch.Tensor) -> None:
+        """Pages of ``export_kv_prefix`` (of any slot of any state of the same model) become the first pages of ``slot``."""
+        n_pages = int(pages.shape[1])
+        if n_pages > self.pages_per_seq or pages.shape[0] != self.kv_pool.shape[0] or pages.shape[2] != self.kv_pool.shape[2]:
+            raise ValueError("KV prefix does not fit this state")
+        p0 = slot * self.pages_per_seq
+        self.kv_pool[:, p0:p0 + n_pages].copy_(pages)
+
+    def arm_admission(self, slots: Sequence[int], tokens: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
+                      known_rows: Optional[Sequence[int]] = None) -> None:
         """Prepare the next fused-chain step so that the sequences in ``slots`` start from their prompts ((T, 33) rows
         each) while every other slot decodes normally: rows 0..T-2 are prefilled now, the embedded last row becomes the
-        slot's backbone input of the step (csmb_decode_frame_fast_admit) and its position is set to T-1."""
+        slot's backbone input of the step (csmb_decode_frame_fast_admit) and its position is set to T-1.
+        ``known_rows[i]`` leading rows of request i are already in the slot's KV pages (``import_kv_prefix``) and are skipped."""
         if self._fast_ws is None:
             raise _lib.CsmbError("arm_admission needs the fused chain (unsupported model shape, or disabled)")
         ncb = self.model.n_audio_codebooks
-        for s in slots:
-            self.pos_host[s] = 0
-        self.prefill_rows(slots, [t[:-1] for t in tokens], [m[:-1] for m in masks])
+        known = [0] * len(slots) if known_rows is None else [int(k) for k in known_rows]
+        for s, k, t in zip(slots, known, tokens):
+            if not 0 <= k <= int(t.shape[0]) - 1:
+                raise ValueError("known_rows must leave at least the last prompt row")
+            self.pos_host[s] = k
+        self.prefill_rows(slots, [t[k:-1] for t, k in zip(tokens, known)], [m[k:-1] for m, k in zip(masks, known)])
         n = len(slots)
         last_tok = torch.stack([t[-1].to(torch.int32) for t in tokens]).contiguous().to(self.device)
         last_msk = torch.stack([m[-1].to(torch.uint8) for m in masks]).contiguous().to(self.device)

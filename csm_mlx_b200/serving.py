@@ -18,6 +18,10 @@ fused kernel chain replayed as a CUDA graph) and ``mimi.Mimi``.
   sequence frees its slot, whose KV pages are simply overwritten by the next occupant.
 * ``ContextCache``: Mimi codes of context audio keyed by content, so a conversation's segments are encoded once
   (tokenizers.py:61-85 is re-run per turn by the reference).
+* ``KVPrefixCache``: the backbone KV pages of a prompt's context rows (everything before the text to speak) keyed by those
+  rows, so the next turn of a conversation with the same context copies ~64 KiB per row into its slot instead of running
+  the prompt pass over them again (generation.py:108-121 re-prefills the whole context every call).  The prompt pass is
+  row-invariant, so a request's tokens are the same with a hit, a miss or no cache.
 
 **Batch invariance.**  A request's greedy tokens do not depend on ``max_batch``, on which other requests share its steps,
 on when it is admitted or on how a job is sharded over GPUs: the engine's ``LMState`` is ``row_invariant`` (every Linear of
@@ -82,12 +86,49 @@ class ContextCache:
         return torch.cat([tt, at], 0), torch.cat([tm, am], 0)
 
 
+class KVPrefixCache:
+    """LRU cache: sha1 of a prompt's leading rows -> (device KV pages of ``LMState.export_kv_prefix``, number of rows)."""
+
+    def __init__(self, capacity: int = 8, max_bytes: int = 1 << 30):
+        self.capacity, self.max_bytes = int(capacity), int(max_bytes)
+        self._kv: "OrderedDict[str, Tuple[torch.Tensor, int]]" = OrderedDict()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def key(tokens: torch.Tensor, mask: torch.Tensor, n_rows: int) -> str:
+        t = tokens[:n_rows].to("cpu", torch.int32).contiguous().numpy().tobytes()
+        m = mask[:n_rows].to("cpu", torch.uint8).contiguous().numpy().tobytes()
+        return hashlib.sha1(t + m).hexdigest() + f":{int(n_rows)}"
+
+    @property
+    def nbytes(self) -> int:
+        return sum(int(p.numel()) * p.element_size() for p, _ in self._kv.values())
+
+    def get(self, key: str) -> Optional[torch.Tensor]:
+        hit = self._kv.get(key)
+        if hit is None:
+            self.misses += 1
+            return None
+        self._kv.move_to_end(key)
+        self.hits += 1
+        return hit[0]
+
+    def put(self, key: str, pages: torch.Tensor, n_rows: int) -> None:
+        if int(pages.numel()) * pages.element_size() > self.max_bytes:
+            return
+        self._kv[key] = (pages, int(n_rows))
+        self._kv.move_to_end(key)
+        while len(self._kv) > self.capacity or self.nbytes > self.max_bytes:
+            self._kv.popitem(last=False)
+
+
 @dataclass
 class Request:
     rid: int
     tokens: torch.Tensor           # (T, 33) int32 prompt rows
     mask: torch.Tensor             # (T, 33) bool
     max_frames: int
+    prefix_rows: int = 0           # leading rows shared with other requests (context segments): KV-prefix cache unit
     frames: List[torch.Tensor] = field(default_factory=list)   # (32,) int32 CPU rows, EOS excluded
     slot: int = -1
     issued: int = 0                # frames enqueued on the GPU so far
@@ -103,13 +144,16 @@ class Engine:
     """Fixed ``max_batch`` sequence slots over one ``LMState``; see the module docstring."""
 
     def __init__(self, model: CSM, max_batch: int = 64, max_len: int = MAX_SEQ_LEN, sampler: Optional[SamplerSpec] = None,
-                 context_cache: Optional[ContextCache] = None, solo_kernel: bool = False):
+                 context_cache: Optional[ContextCache] = None, solo_kernel: bool = False,
+                 kv_prefix_cache: Optional[KVPrefixCache] = None):
         self.model, self.B = model, int(max_batch)
         self.spec = sampler if sampler is not None else SamplerSpec(temperature=0.0)
         self.solo_kernel = bool(solo_kernel)
         self.state = LMState(model, self.B, max_len=max_len, row_invariant=True)
         self.ncb = model.n_audio_codebooks
         self.cache = context_cache if context_cache is not None else ContextCache(n_audio_codebooks=self.ncb)
+        # only prompts submitted with context rows (prefix_rows > 0) ever touch it; capacity=0 switches it off
+        self.kv_cache = kv_prefix_cache if kv_prefix_cache is not None else KVPrefixCache()
         self.queue: Deque[Request] = deque()
         self.slots: List[Optional[Request]] = [None] * self.B
         self.finished: Dict[int, Request] = {}
@@ -124,26 +168,35 @@ class Engine:
     # ------------------------------------------------------------------ requests
     def build_prompt(self, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
         """generation.py:108-121 with cached context tokenisation."""
+        tok, mask, _ = self._build_prompt(text, speaker, context)
+        return tok, mask
+
+    def _build_prompt(self, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor, int]:
         toks, masks = [], []
         for seg in context:
             t, m = self.cache.segment_rows(seg)
             toks.append(t)
             masks.append(m)
+        n_context = sum(int(t.shape[0]) for t in toks)
         t, m = tokenize_text_segment(text, speaker, n_audio_codebooks=self.ncb)
         toks.append(t)
         masks.append(m)
-        return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0)
+        return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0), n_context
 
     def submit(self, text: Union[str, Sequence[int]], speaker: int, context: Optional[Sequence[Segment]] = None,
                max_audio_length_ms: float = 90_000) -> int:
-        tok, mask = self.build_prompt(text, speaker, context or [])
-        return self.submit_prompt(tok, mask, int(max_audio_length_ms / 80))
+        tok, mask, n_context = self._build_prompt(text, speaker, context or [])
+        return self.submit_prompt(tok, mask, int(max_audio_length_ms / 80), prefix_rows=n_context)
 
-    def submit_prompt(self, tokens: torch.Tensor, mask: torch.Tensor, max_frames: int) -> int:
+    def submit_prompt(self, tokens: torch.Tensor, mask: torch.Tensor, max_frames: int, prefix_rows: int = 0) -> int:
+        """``prefix_rows``: the first that many rows are context other requests are likely to share (``submit`` passes the
+        rows of the context segments): their backbone KV is kept in / taken from the ``KVPrefixCache``."""
         _check_length(self.model, int(tokens.shape[0]), max_frames)           # generation.py:131-137
         if int(tokens.shape[0]) + max_frames + 1 > self.state.max_len:
             raise ValueError("request exceeds the KV pages reserved per slot (Engine(max_len=...))")
-        r = Request(self._next_id, tokens.to(torch.int32).cpu(), mask.cpu(), int(max_frames))
+        if not 0 <= int(prefix_rows) < int(tokens.shape[0]):
+            raise ValueError("prefix_rows must leave at least one prompt row")
+        r = Request(self._next_id, tokens.to(torch.int32).cpu(), mask.cpu(), int(max_frames), int(prefix_rows))
         self._next_id += 1
         self.queue.append(r)
         return r.rid
@@ -181,7 +234,7 @@ class Engine:
                     r.slot = b
                     self.slots[b] = r
                     reqs.append(r)
-                st.arm_admission(admit, [r.tokens for r in reqs], [r.mask for r in reqs])
+                self._admit_on_chain(admit, reqs)
                 self.admissions += len(admit)
             self._park_idle_slots()
             prev = self._prev if self._prev is not None else torch.zeros((self.B, self.ncb), device=st.device, dtype=torch.int32)
@@ -205,6 +258,24 @@ class Engine:
         self._pending = (slot, list(self.slots))
         self._prev = frame
         return newly_done
+
+    def _admit_on_chain(self, slots: List[int], reqs: List[Request]) -> None:
+        """arm_admission with the context rows' KV served from / stored into the prefix cache."""
+        st, kvc = self.state, self.kv_cache
+        use = [kvc.capacity > 0 and r.prefix_rows > 0 for r in reqs]
+        keys = [KVPrefixCache.key(r.tokens, r.mask, r.prefix_rows) if u else None for r, u in zip(reqs, use)]
+        known = []
+        for b, r, k in zip(slots, reqs, keys):
+            pages = kvc.get(k) if k is not None else None
+            if pages is not None:
+                st.import_kv_prefix(b, pages)
+                known.append(r.prefix_rows)
+            else:
+                known.append(0)
+        st.arm_admission(slots, [r.tokens for r in reqs], [r.mask for r in reqs], known_rows=known)
+        for b, r, k, n in zip(slots, reqs, keys, known):
+            if k is not None and n == 0:        # a miss: the rows were just prefilled into the slot's pages (stream ordered)
+                kvc.put(k, st.export_kv_prefix(b, r.prefix_rows), r.prefix_rows)
 
     def _drain(self) -> List[Request]:
         done: List[Request] = []

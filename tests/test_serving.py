@@ -111,6 +111,61 @@ def test_engine_context_segments_use_the_cache(model_1b, mimi_gpu):
         tokenizers.set_text_tokenizer(None)
 
 
+def test_kv_prefix_cache_is_an_lru_keyed_by_the_rows():
+    c = serving.KVPrefixCache(capacity=2, max_bytes=1 << 20)
+    tok = torch.arange(33 * 6, dtype=torch.int32).reshape(6, 33)
+    mask = torch.ones((6, 33), dtype=torch.bool)
+    k3, k4 = c.key(tok, mask, 3), c.key(tok, mask, 4)
+    other = tok.clone()
+    other[2, 5] += 1
+    assert len({k3, k4, c.key(other, mask, 3), c.key(tok, ~mask, 3)}) == 4 and c.key(other, mask, 2) == c.key(tok, mask, 2)
+    assert c.get(k3) is None and (c.hits, c.misses) == (0, 1)
+    c.put(k3, torch.zeros((2, 1, 8)), 3)
+    c.put(k4, torch.ones((2, 1, 8)), 4)
+    assert float(c.get(k3).sum()) == 0.0                     # k3 is now the most recently used
+    c.put("third", torch.zeros((2, 1, 8)), 1)
+    assert c.get(k4) is None and c.get(k3) is not None and c.nbytes == 2 * 2 * 8 * 4
+    c.put("huge", torch.zeros((1 << 19,)), 1)                # larger than max_bytes: not kept
+    assert c.get("huge") is None and c.get(k3) is not None
+
+
+@pytest.mark.gpu
+def test_engine_kv_prefix_cache_hit_equals_miss_equals_no_cache(model_1b, mimi_gpu, device):
+    """Second turn of a conversation: the context rows' backbone KV comes from the prefix cache (a copy of 64 KiB per row,
+    no prompt pass over them).  Tokens are identical to the first-turn (miss) engine and to an engine without the cache, for
+    a context whose length is not a multiple of the 16-token KV page; slots differ between the turns."""
+    from csm_mlx_b200 import Segment
+
+    tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+    try:
+        ctx = [Segment(0, "the first context sentence", synthetic_audio(11, 1.3)), Segment(1, "a reply", synthetic_audio(12, 0.7))]
+        turns = ["what shall we talk about", "something else entirely, and longer than before"]
+
+        def run(engine, extra_first):
+            out = []
+            for i, text in enumerate(turns):
+                rids = [engine.submit(text, 1, ctx, max_audio_length_ms=400)]
+                if i == 0 and extra_first:   # occupies slot 1 during the first turn only, so that turn two lands in another slot
+                    rids.insert(0, engine.submit(prompt_ids(5, 9), 0, [], max_audio_length_ms=400))
+                engine.run()
+                out.append(engine.tokens(rids[-1]).clone())
+            return out
+
+        cached = serving.Engine(model_1b, max_batch=2, max_len=256)
+        got = run(cached, extra_first=True)
+        n_ctx = cached._build_prompt(turns[0], 1, ctx)[2]
+        assert n_ctx % 16 != 0 and n_ctx > 32
+        assert (cached.kv_cache.hits, cached.kv_cache.misses) == (1, 1) and cached.kv_cache.nbytes == -(-n_ctx // 16) * (1 << 20)
+        plain = serving.Engine(model_1b, max_batch=2, max_len=256, kv_prefix_cache=serving.KVPrefixCache(capacity=0))
+        want = run(plain, extra_first=False)
+        assert (plain.kv_cache.hits, plain.kv_cache.misses) == (0, 0)
+        for g, w in zip(got, want):
+            assert g.shape == (5, 32) and torch.equal(g, w)
+        cached.state.check_status()
+    finally:
+        tokenizers.set_text_tokenizer(None)
+
+
 @pytest.mark.gpu
 def test_engine_rejects_oversized_requests(model_1b):
     eng = serving.Engine(model_1b, max_batch=2, max_len=64)
