@@ -98,6 +98,7 @@ class CSM:
             if torch.cuda.is_available() else torch.device("cuda")
         self._desc: Optional[_lib.Model] = None
         self._proj_table: Optional[torch.Tensor] = None
+        self.weights_version = 0   # bumped whenever the weights change: caches of derived values (KV prefixes) key on it
         self._loaded = False
         self.quantized = False   # quantize_weights(): the Linear matrices are weight-only FP8 blobs
 
@@ -185,6 +186,7 @@ class CSM:
                 raise RuntimeError("load_weights() on a quantised model: load into a fresh CSM and quantise again")
             cur = self.parameters()
             self._proj_table = None  # derived from projection / audio_embeddings: rebuilt on next use
+            self.weights_version += 1
             for k, v in known.items():
                 if k == "audio_head":
                     self._audio_head_t.copy_(v.transpose(1, 2).to(self._audio_head_t.dtype))
@@ -218,6 +220,7 @@ class CSM:
                                             MAX_SEQ_LEN))
         self._loaded = True
         self._desc = None
+        self.weights_version += 1
 
     # ------------------------------------------------------------------ weight-only FP8 (nn.quantize analogue)
     def quantize_weights(self) -> "CSM":
@@ -250,6 +253,7 @@ class CSM:
         self.quantized = True
         self._proj_table = None
         self._desc = None
+        self.weights_version += 1
         return self
 
     def _dequantized_parameters(self) -> Dict[str, torch.Tensor]:

@@ -95,10 +95,11 @@ class KVPrefixCache:
         self.hits = self.misses = 0
 
     @staticmethod
-    def key(tokens: torch.Tensor, mask: torch.Tensor, n_rows: int) -> str:
+    def key(tokens: torch.Tensor, mask: torch.Tensor, n_rows: int, weights_version: int = 0) -> str:
+        """``weights_version``: ``CSM.weights_version`` — KV entries are a function of the rows AND the weights."""
         t = tokens[:n_rows].to("cpu", torch.int32).contiguous().numpy().tobytes()
         m = mask[:n_rows].to("cpu", torch.uint8).contiguous().numpy().tobytes()
-        return hashlib.sha1(t + m).hexdigest() + f":{int(n_rows)}"
+        return hashlib.sha1(t + m).hexdigest() + f":{int(n_rows)}:{int(weights_version)}"
 
     @property
     def nbytes(self) -> int:
@@ -263,7 +264,8 @@ class Engine:
         """arm_admission with the context rows' KV served from / stored into the prefix cache."""
         st, kvc = self.state, self.kv_cache
         use = [kvc.capacity > 0 and r.prefix_rows > 0 for r in reqs]
-        keys = [KVPrefixCache.key(r.tokens, r.mask, r.prefix_rows) if u else None for r, u in zip(reqs, use)]
+        ver = int(getattr(self.model, "weights_version", 0))
+        keys = [KVPrefixCache.key(r.tokens, r.mask, r.prefix_rows, ver) if u else None for r, u in zip(reqs, use)]
         known = []
         for b, r, k in zip(slots, reqs, keys):
             pages = kvc.get(k) if k is not None else None
