@@ -433,8 +433,29 @@ def context_config(model, mimi, dev):
         kv_stats = (eng.kv_cache.hits, eng.kv_cache.misses, eng.kv_cache.nbytes)
         eng.state.check_status()
         del eng
+
+        # time to the first 80 ms chunk of a turn through stream_generate (host clock): context seen for the first time
+        # (Mimi encode of both clips + prompt pass over all rows) vs the next turn (codes and KV prefix from the model's caches)
+        def first_chunk_ms(text):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            g = generation.stream_generate(model, text, 0, segs, max_audio_length_ms=400, temperature=0.0)
+            next(g)
+            t = 1e3 * (time.perf_counter() - t0)
+            g.close()
+            torch.cuda.synchronize(dev)
+            return t
+        first_chunk_ms("warm up the streaming path")
+        cold, warm = [], []
+        for i in range(3):
+            generation.set_conversation_cache(model)
+            cold.append(first_chunk_ms("a turn with a context never seen %d" % i))
+            warm.append(first_chunk_ms("the following turn of it %d" % i))
+        generation.set_conversation_cache(model)
         return {"prompt_rows": rows, "mimi_encode_ms_total": t_enc, "prefill_ms": t_pre,
                 "engine_admission_step_ms": {"kv_prefix_miss": t_miss, "kv_prefix_hit": t_hit, "cache_hits_misses_bytes": kv_stats},
+                "stream_first_chunk_ms": {"context_first_seen": statistics.median(cold), "next_turn_same_context": statistics.median(warm),
+                                          "what": "call -> first 1 920 samples on the host through stream_generate with the 2 x 5 s context"},
                 "prefill_tflops": 2 * 973.1e6 * rows / (t_pre * 1e-3) / 1e12, "ms_per_frame": t_f,
                 "prefill_long": {"prompt_rows": rows_l, "ms": t_long, "tflops": 2 * 973.1e6 * rows_l / (t_long * 1e-3) / 1e12},
                 "note": "prefill = host staging + backbone over all prompt rows on the chain's kernels (csmb_prefill_fast: one tcgen05 launch per "

@@ -9,6 +9,11 @@ Differences from the reference, all on the host side and deliberate:
   for EOS on the host, so the GPU never waits for Python; a frame generated past EOS is discarded.
 * ``generate_batch`` (not in the reference, which is batch-1 by construction, generation.py:124,156) runs B
   independent utterances in lock-step for the request-sharded throughput configuration.
+* conversation caches (``caches.py``): the reference Mimi-encodes and prefills every context segment on every call
+  (generation.py:108-121).  Here a model remembers the codes of the segments it has seen and the backbone KV pages of a
+  prompt's context rows; the next turn with the same context copies the pages and prefills only the new text rows — same
+  tokens (row-invariant prompt pass), a few milliseconds less before the first chunk.  ``set_conversation_cache(model,
+  enabled=False)`` or ``CSMB_DISABLE_CONV_CACHE=1`` switches it off.
 """
 
 from __future__ import annotations
@@ -19,16 +24,35 @@ from typing import Callable, Generator, List, Optional, Sequence, Tuple, Union
 
 import torch
 
+from .caches import ContextCache, KVPrefixCache
 from .config import MAX_SEQ_LEN
 from .models import CSM
 from .runtime import LMState, SamplerSpec
 from .sample_utils import DeviceSampler
 from .segment import Segment
-from .tokenizers import get_audio_tokenizer, tokenize_segment, tokenize_text_segment
+from .tokenizers import get_audio_tokenizer, tokenize_text_segment
 
 default_stream = None  # the reference exposes an mx.Stream here (generation.py:19); CUDA streams come from torch
 
 LogitsProcessor = Callable[[torch.Tensor, torch.Tensor], torch.Tensor]
+
+
+def set_conversation_cache(model: CSM, enabled: bool = True, segments: int = 16, prefixes: int = 4,
+                           prefix_bytes: int = 512 << 20) -> None:
+    """(Re)creates or drops the model's conversation caches: up to ``segments`` tokenised context segments (host memory)
+    and up to ``prefixes`` context KV prefixes (device memory, at most ``prefix_bytes``: 64 KiB per context row)."""
+    if enabled:
+        model.__dict__["_conv_cache"] = (ContextCache(segments, model.n_audio_codebooks), KVPrefixCache(prefixes, prefix_bytes))
+    else:
+        model.__dict__["_conv_cache"] = None
+
+
+def _conv_cache(model: CSM) -> Optional[Tuple[ContextCache, KVPrefixCache]]:
+    if os.environ.get("CSMB_DISABLE_CONV_CACHE", "0") == "1":
+        return None
+    if "_conv_cache" not in model.__dict__:
+        set_conversation_cache(model)
+    return model.__dict__["_conv_cache"]
 
 
 def make_cache(model: CSM, batch: int = 1, max_len: int = MAX_SEQ_LEN) -> LMState:
@@ -105,9 +129,11 @@ class _Session:
     """One lock-step generation over B utterances: prefill once, then a frame per ``step()``."""
 
     def __init__(self, model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tensor]], max_audio_frames: int,
-                 spec: SamplerSpec, host_sampler, logits_processors):
+                 spec: SamplerSpec, host_sampler, logits_processors, prefix_rows: Optional[Sequence[int]] = None):
         self.model, self.spec, self.host_sampler, self.procs = model, spec, host_sampler, logits_processors
         B = len(prompts)
+        # leading rows of each prompt that are context (shared by the turns of a conversation): KV prefix cache unit
+        self.prefix_rows = [0] * B if prefix_rows is None else [int(p) for p in prefix_rows]
         longest = max(int(p[0].shape[0]) for p in prompts)
         self.state = LMState.acquire(model, B, max_len=longest + max_audio_frames + 1)
         self.prompts = prompts
@@ -121,7 +147,7 @@ class _Session:
         frame = torch.zeros((self.B, model.n_audio_codebooks), device=model.device, dtype=torch.int32)
         plain = self.host_sampler is None and not self.procs
         if self.prev is None:
-            st.prefill([p[0] for p in self.prompts], [p[1] for p in self.prompts])
+            self._prefill()
             if plain and self.fused and st.fused_supported(self.spec):
                 frame = st.first_frame_fused(self.spec)
             else:
@@ -136,6 +162,29 @@ class _Session:
             _frame_after_backbone(st, frame, self.spec, self.host_sampler, self.procs, self.c0_history)
         self.prev = frame
         return frame
+
+    def _prefill(self) -> None:
+        """The prompt pass (generation.py:34-42, T > 1); context rows whose KV pages are in the model's prefix cache are
+        copied instead of recomputed, and a context seen for the first time is remembered."""
+        st = self.state
+        cc = _conv_cache(self.model)
+        kvc = cc[1] if cc is not None and st._prefill_fast_ok() else None   # the per-op prompt pass is not row-invariant
+        known, keys = [0] * self.B, [None] * self.B
+        if kvc is not None:
+            ver = int(getattr(self.model, "weights_version", 0))
+            for b, ((tok, mask), p) in enumerate(zip(self.prompts, self.prefix_rows)):
+                if 0 < p < int(tok.shape[0]) and kvc.capacity > 0:
+                    keys[b] = KVPrefixCache.key(tok, mask, p, ver)
+                    pages = kvc.get(keys[b])
+                    if pages is not None and pages.device == st.kv_pool.device:
+                        st.import_kv_prefix(b, pages)
+                        st.pos_host[b] = p
+                        known[b] = p
+        st.prefill([p[0][k:] for p, k in zip(self.prompts, known)], [p[1][k:] for p, k in zip(self.prompts, known)])
+        if kvc is not None:
+            for b, (k, key) in enumerate(zip(known, keys)):
+                if key is not None and k == 0:
+                    kvc.put(key, st.export_kv_prefix(b, self.prefix_rows[b]), self.prefix_rows[b])
 
     def status_word(self) -> torch.Tensor:
         return self.state.status_word()
@@ -157,15 +206,25 @@ class _Session:
 
 def _build_prompt(model: CSM, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor]:
     """generation.py:108-121."""
+    tok, mask, _ = _build_prompt_ex(model, text, speaker, context)
+    return tok, mask
+
+
+def _build_prompt_ex(model: CSM, text, speaker: int, context: Sequence[Segment]) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """-> (rows, mask, number of context rows).  Context segments are tokenised through the model's ``ContextCache`` (the rows
+    of ``tokenize_segment``, tokenizers.py:88-102; the Mimi encode of a segment's audio runs once per distinct clip)."""
+    cc = _conv_cache(model)
+    seg_cache = cc[0] if cc is not None else ContextCache(0, model.n_audio_codebooks)
     toks, masks = [], []
     for seg in context:
-        t, m = tokenize_segment(seg, n_audio_codebooks=model.n_audio_codebooks)
+        t, m = seg_cache.segment_rows(seg)
         toks.append(t)
         masks.append(m)
+    n_context = sum(int(t.shape[0]) for t in toks)
     t, m = tokenize_text_segment(text, speaker, n_audio_codebooks=model.n_audio_codebooks)
     toks.append(t)
     masks.append(m)
-    return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0)
+    return torch.cat(toks, 0).to(torch.int32), torch.cat(masks, 0), n_context
 
 
 def _check_length(model: CSM, n_rows: int, max_audio_frames: int) -> None:
@@ -231,14 +290,15 @@ class _CodecLane:
 
 
 def generate_tokens(model: CSM, prompts: Sequence[Tuple[torch.Tensor, torch.Tensor]], max_audio_frames: int, *,
-                    temperature: float = 0.8, sampler=None, logits_processors=None, seed: Optional[int] = None
-                    ) -> List[torch.Tensor]:
+                    temperature: float = 0.8, sampler=None, logits_processors=None, seed: Optional[int] = None,
+                    prefix_rows: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
     """The frame loop of generation.py:139-161 for B utterances in lock-step: returns, per utterance, the
-    (F_b, 32) int32 CPU tensor of frames before its first all-zero (EOS) frame."""
+    (F_b, 32) int32 CPU tensor of frames before its first all-zero (EOS) frame.  ``prefix_rows[b]``: leading rows of prompt b
+    that are conversation context (KV prefix cache unit; 0 = none)."""
     for tok, _ in prompts:
         _check_length(model, int(tok.shape[0]), max_audio_frames)
     spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
-    sess = _Session(model, prompts, max_audio_frames, spec, host_sampler, logits_processors)
+    sess = _Session(model, prompts, max_audio_frames, spec, host_sampler, logits_processors, prefix_rows)
     B, ncb = len(prompts), model.n_audio_codebooks
     mirror = _HostMirror([((B, ncb), torch.int32), ((1,), torch.int32)], model.device)
     out: List[List[torch.Tensor]] = [[] for _ in range(B)]
@@ -277,9 +337,9 @@ def generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, context:
              seed: Optional[int] = None) -> torch.Tensor:
     """generation.py:95-178 -> 1-D float32 audio ``(1920*F,)`` (CPU tensor; ``np.asarray`` works on it)."""
     max_audio_frames = int(max_audio_length_ms / 80)
-    prompt = _build_prompt(model, text, speaker, context)
-    (frames,) = generate_tokens(model, [prompt], max_audio_frames, temperature=temperature, sampler=sampler,
-                                logits_processors=logits_processors, seed=seed)
+    tok, mask, n_context = _build_prompt_ex(model, text, speaker, context)
+    (frames,) = generate_tokens(model, [(tok, mask)], max_audio_frames, temperature=temperature, sampler=sampler,
+                                logits_processors=logits_processors, seed=seed, prefix_rows=[n_context])
     if frames.shape[0] == 0:
         print("[WARN] No samples generated.")
         return torch.zeros((0,), dtype=torch.float32)
@@ -297,8 +357,10 @@ def generate_batch(model: CSM, texts: Sequence[Union[str, Sequence[int]]], speak
     1-D float32 CPU audio tensors (and the per-utterance (F,32) token tensors if ``return_tokens``)."""
     max_audio_frames = int(max_audio_length_ms / 80)
     contexts = contexts if contexts is not None else [[] for _ in texts]
-    prompts = [_build_prompt(model, t, s, c) for t, s, c in zip(texts, speakers, contexts)]
-    frames = generate_tokens(model, prompts, max_audio_frames, temperature=temperature, sampler=sampler, seed=seed)
+    built = [_build_prompt_ex(model, t, s, c) for t, s, c in zip(texts, speakers, contexts)]
+    prompts = [(b[0], b[1]) for b in built]
+    frames = generate_tokens(model, prompts, max_audio_frames, temperature=temperature, sampler=sampler, seed=seed,
+                             prefix_rows=[b[2] for b in built])
     mimi = get_audio_tokenizer(model.n_audio_codebooks)
     Fmax = max((int(f.shape[0]) for f in frames), default=0)
     audios: List[torch.Tensor] = []
@@ -320,10 +382,11 @@ def stream_generate(model: CSM, text: Union[str, Sequence[int]], speaker: int, c
     """generation.py:181-258: yields one ``(1920,)`` float32 CPU chunk per generated frame.  Each generator owns
     its codec streaming state (the reference shares one global Mimi state, tokenizers.py:14-21)."""
     max_audio_frames = int(max_audio_length_ms / 80)
-    prompt = _build_prompt(model, text, speaker, context)
+    tok, mask, n_context = _build_prompt_ex(model, text, speaker, context)
+    prompt = (tok, mask)
     _check_length(model, int(prompt[0].shape[0]), max_audio_frames)
     spec, host_sampler = _resolve_sampler(temperature, sampler, seed)
-    sess = _Session(model, [prompt], max_audio_frames, spec, host_sampler, logits_processors)
+    sess = _Session(model, [prompt], max_audio_frames, spec, host_sampler, logits_processors, [n_context])
     ncb = model.n_audio_codebooks
     mimi = get_audio_tokenizer(ncb)
     lane = _CodecLane(mimi.acquire_decode_stream(batch=1), model.device)

@@ -64,6 +64,31 @@ def test_generate_with_segment_context(model_1b, mimi_gpu, oracle_1b, mimi_weigh
         tokenizers.set_text_tokenizer(None)
 
 
+def test_conversation_caches_do_not_change_what_generate_returns(model_1b, mimi_gpu, monkeypatch):
+    """Two turns of a conversation through generate(): the second turn takes the context segments' codes from the model's
+    ContextCache and the context rows' backbone KV from its KVPrefixCache (generation.py:108-121 recomputes both per call).
+    Audio identical, sample for sample, to the same two calls with CSMB_DISABLE_CONV_CACHE=1."""
+    tokenizers.set_text_tokenizer(tokenizers.SyntheticTextTokenizer())
+    try:
+        ctx = [Segment(0, "so how was the trip", synthetic_audio(21, 1.1)), Segment(1, "long, but fine", synthetic_audio(22, 0.9))]
+        turns = ["tell me more about it", "and what happens next"]
+        generation.set_conversation_cache(model_1b)                      # fresh caches
+        cached = [generate(model_1b, t, 1, ctx, max_audio_length_ms=400, temperature=0.0) for t in turns]
+        segs, kv = model_1b.__dict__["_conv_cache"]
+        assert (segs.hits, segs.misses) == (2, 2) and (kv.hits, kv.misses) == (1, 1)
+        chunks = list(stream_generate(model_1b, turns[1], 1, ctx, max_audio_length_ms=400, temperature=0.0))
+        assert kv.hits == 2 and snr_db(cached[1], torch.cat(chunks)) > 80
+        monkeypatch.setenv("CSMB_DISABLE_CONV_CACHE", "1")
+        plain = [generate(model_1b, t, 1, ctx, max_audio_length_ms=400, temperature=0.0) for t in turns]
+        assert (kv.hits, kv.misses) == (2, 1)
+        for a, b in zip(cached, plain):
+            assert a.shape == (5 * 1920,) and torch.equal(a, b)
+        assert not torch.equal(cached[0], cached[1])
+    finally:
+        generation.set_conversation_cache(model_1b)
+        tokenizers.set_text_tokenizer(None)
+
+
 def test_sampler_argument_forms(model_1b, mimi_gpu):
     ids = cfg1_prompt_ids()
     a = generate(model_1b, ids, 0, [], max_audio_length_ms=160, sampler=csm_mlx.make_sampler(temp=0.8, top_k=50, seed=3))

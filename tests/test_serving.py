@@ -28,7 +28,9 @@ def test_context_cache_encodes_each_audio_once(monkeypatch):
         tok[:, 0] = int(audio.numel())
         return tok, torch.ones((n, n_audio_codebooks + 1), dtype=torch.bool)
 
-    monkeypatch.setattr(serving, "tokenize_audio", fake_tokenize_audio)
+    from csm_mlx_b200 import caches
+
+    monkeypatch.setattr(caches, "tokenize_audio", fake_tokenize_audio)
     cache = serving.ContextCache(capacity=2)
     a, b, c = torch.ones(100), torch.ones(200), torch.full((100,), 2.0)
     r1 = cache.audio_rows(a)
