@@ -566,7 +566,11 @@ def run_ours(args):
         dev_times.append(last["event_s"])
     barrier()
     clk = clocks.stop()
-    job(False)
+    # untimed: two results alive at once, as in the timed loop below (this one and the previous one), so that the caching
+    # pinned-host allocator owns both 61 MB result blocks before the clock starts (steady state of a serving process)
+    warm_a = job(False)
+    warm_b = job(False)
+    del warm_a, warm_b
     e2e_times = []
     for _ in range(args.steps):
         barrier()
