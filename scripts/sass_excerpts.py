@@ -8,11 +8,12 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "csm_mlx_b200", "libcsm_b200.so")
-KERNELS = {"k_gemm_part_t<false>": "gemm_part", "k_gemm_part_t<true>": "gemm_part_swiglu", "k_linear_tc": "linear_tc",
+KERNELS = {"k_gemm_part_t<false, false>": "gemm_part", "k_gemm_part_t<true, false>": "gemm_part_swiglu",
+           "k_gemm_part_t<true, true>": "gemm_part_swiglu_cta_pair", "k_linear_tc": "linear_tc",
            "fk_bf16::k_frame(": "frame", "fk_e4m3::k_frame(": "frame_e4m3", "k_gemm_tc3": "gemm_tc3",
            "k_attn_decode_small<128>": "attn_decode_small", "k_attn_decode_chunked<64>": "attn_decode_chunked",
            "k_resid_norm_split<1>": "resid_norm_split"}
-KEY = re.compile(r"UTCHMMA|UTCBAR|UTMALDG|UBLKCP|UBLKPF|LDTM|UTCATOMSWS|SYNCS\.(ARRIVE|EXCH|PHASECHK)|ACQBULK|PREEXIT|UTMAPF|FENCE\.VIEW\.ASYNC|F2FP\.BF16|LDGSTS|LDGDEPBAR|DEPBAR|F2FP\.F16\.E4M3|F2F")
+KEY = re.compile(r"UTCHMMA|UTCBAR|UTMALDG|UCGABAR|UBLKCP|UBLKPF|LDTM|UTCATOMSWS|SYNCS\.(ARRIVE|EXCH|PHASECHK)|ACQBULK|PREEXIT|UTMAPF|FENCE\.VIEW\.ASYNC|F2FP\.BF16|LDGSTS|LDGDEPBAR|DEPBAR|F2FP\.F16\.E4M3|F2F")
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 blocks = re.split(r"\n\s*Function : ", sass)
