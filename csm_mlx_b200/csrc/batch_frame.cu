@@ -117,7 +117,7 @@ struct GpArgs {
 // same issuer (an mbarrier parity wait cannot tell the second from the third use of a stage apart, so one thread must see
 // every use of "its" stages in order).
 //
-// PAIR = true (launched as clusters of two CTAs along the n-tile axis, csmb_chain_opts flag 4096 / bf_pair_wanted): the two
+// MODE 1 = PAIR (launched as clusters of two CTAs along the n-tile axis, csmb_chain_opts flags 65536 / 131072, bf_mode): the two
 // CTAs share the token operand through ONE tcgen05.mma.cta_group::2 of M = 256 per K step, issued by the pair's leader: CTA r
 // holds its own 128 weight rows and HALF of the stacked token operand (rank 0: the hi plane's RN rows, rank 1: the lo plane's)
 // at the same stage offsets, so a CTA pulls W + RN rows per K block instead of W + 2 RN — with 64 sequences the token planes
@@ -125,11 +125,16 @@ struct GpArgs {
 // SM fill rate (128 CTAs x 422 KB in 5.4 us = 10 TB/s of the ~12 TB/s the chip delivers).  Both CTAs' TMA copies count their
 // bytes on the LEADER's full barrier; the leader's commits are multicast to the empty / acc_full barriers of both CTAs; the
 // accumulator rows of a CTA's weight tile land in its own TMEM, so the epilogue is unchanged.  Same products summed in the
-// same order as PAIR = false: bit-identical outputs.
-template <bool GU, bool PAIR>
+// same order as MODE 0: bit-identical outputs.
+//
+// (A third mode — the last weight K blocks of a CTA parked in free tensor-memory columns before the previous kernel finishes and
+// consumed as tcgen05.mma with A from TMEM — was built, bit-identical, and measured slower: profiles/r02_tmem_weights.md,
+// r02_tmem_weights_experiment.patch.)
+template <bool GU, int MODE>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 k_gemm_part_t(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_hi,
               const __grid_constant__ CUtensorMap map_lo, const GpArgs a) {
+  constexpr bool PAIR = MODE == 1;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[BF_MAX_STAGES], empty[BF_MAX_STAGES], acc_full;
@@ -1681,11 +1686,21 @@ static int bf_ring_depth(int fit, int dbg) {
 #ifndef CSMB_PAIR_MIN_ROWS
 #define CSMB_PAIR_MIN_ROWS 0   // > 0: every Linear over at least this many token rows runs as CTA pairs (prompt passes)
 #endif
-static bool bf_pair_wanted(const ChainCfg& cc, int tiles, bool gu, int R) {
-  if (tiles % 2 != 0) return false;
-  if (CSMB_PAIR_MIN_ROWS > 0 && R >= CSMB_PAIR_MIN_ROWS) return true;
-  return (cc.dbg & (gu ? 4096 : 8192)) != 0;
+// -> MODE of k_gemm_part_t: 0 = single CTAs (shipped), 1 = CTA pairs
+static int bf_mode(const ChainCfg& cc, int tiles, bool gu, int R) {
+  if (tiles % 2 == 0 && ((CSMB_PAIR_MIN_ROWS > 0 && R >= CSMB_PAIR_MIN_ROWS) || (cc.dbg & (gu ? 65536 : 131072)) != 0)) return 1;
+  return 0;
 }
+// shared memory of a Linear CTA: ring stage size, ring depth and the dynamic allocation for a MODE
+struct BfSmem { size_t stage; int nstages; size_t bytes; };
+static BfSmem bf_smem(const ChainCfg& cc, int RN, int mode) {
+  BfSmem r;
+  r.stage = ((size_t)TC_BM * TC_BK * 2 + (mode == 1 ? 1 : 2) * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
+  r.nstages = bf_ring_depth((int)(cc.smem / r.stage), cc.dbg);
+  r.bytes = r.stage * r.nstages + 1024;
+  return r;
+}
+constexpr int BF_SMEM_ATTR = (int)(BF_SMEM_BUDGET + 1024);   // cudaFuncAttributeMaxDynamicSharedMemorySize of the Linears
 
 // y = x W^T for the R rows whose planes are xhi / xlo -> split-K partials in w.part
 static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, PartIn* out, cudaStream_t st,
@@ -1699,20 +1714,19 @@ static int bf_gemm(const FastWs& w, const uint16_t* W, int R, int N, int K, Part
   if (!tc_make_map(&mw, W, N, K, TC_BM) || !tc_make_map(&mhi, xhi ? xhi : w.hi, R, K, RN) ||
       !tc_make_map(&mlo, xlo ? xlo : w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
-  const bool pair = bf_pair_wanted(w.cc, cdiv(N, TC_BM), false, R);
-  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + (pair ? 1 : 2) * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
-  int nstages = (int)(w.cc.smem / stage);
-  nstages = bf_ring_depth(nstages, w.cc.dbg);
+  const int mode = bf_mode(w.cc, cdiv(N, TC_BM), false, R);
+  const BfSmem sm = bf_smem(w.cc, RN, mode);
+  const int nstages = sm.nstages;
   CSMB_REQUIRE(nstages >= 2);
   GpArgs a{w.part, R, N, K, RN, nstages, S, w.err, w.cc.dbg & (3 | 32 | 64 | 128 | 2048), 0, nullptr, nullptr, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
-  const size_t smem = stage * nstages + 1024;
+  const size_t smem = sm.bytes;
   dim3 grid(cdiv(N, TC_BM), cdiv(R, RN), S);
-  if (pair) {
-    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
-    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<false, true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  if (mode == 1) {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_ATTR));
+    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<false, 1>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   } else {
-    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
-    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false, false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_ATTR));
+    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<false, 0>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   }
   *out = PartIn{w.part, S, (size_t)R * N, N};
   return CSMB_OK;
@@ -1726,20 +1740,19 @@ static int bf_gemm_gu(const FastWs& w, const uint16_t* Wgu, int R, int F, int K,
   CUtensorMap mw, mhi, mlo;
   if (!tc_make_map(&mw, Wgu, 2 * F, K, TC_BM / 2) || !tc_make_map(&mhi, w.hi, R, K, RN) || !tc_make_map(&mlo, w.lo, R, K, RN))
     return CSMB_ERR_UNSUPPORTED;
-  const bool pair = bf_pair_wanted(w.cc, F / (TC_BM / 2), true, R);
-  const size_t stage = ((size_t)TC_BM * TC_BK * 2 + (pair ? 1 : 2) * (size_t)RN * TC_BK * 2 + 1023) & ~(size_t)1023;
-  int nstages = (int)(w.cc.smem / stage);
-  nstages = bf_ring_depth(nstages, w.cc.dbg);
-  CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * stage >= (size_t)2 * RN * 64 * sizeof(float));
+  const int mode = bf_mode(w.cc, F / (TC_BM / 2), true, R);
+  const BfSmem sm = bf_smem(w.cc, RN, mode);
+  const int nstages = sm.nstages;
+  CSMB_REQUIRE(nstages >= 2 && (size_t)nstages * sm.stage >= (size_t)2 * RN * 64 * sizeof(float));
   GpArgs a{nullptr, R, 2 * F, K, RN, nstages, 1, w.err, w.cc.dbg & (32 | 64 | 128 | 2048), F, w.hi2, w.lo2, static_cast<const char*>(pf), (unsigned)pf_bytes, keep8};
-  const size_t smem = stage * nstages + 1024;
+  const size_t smem = sm.bytes;
   dim3 grid(F / (TC_BM / 2), cdiv(R, RN), 1);
-  if (pair) {
-    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
-    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<true, true>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+  if (mode == 1) {
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_ATTR));
+    CSMB_CUDA(bf_launch_pair(w.cc, k_gemm_part_t<true, 1>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   } else {
-    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BF_SMEM_BUDGET + 1024)));
-    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true, false>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
+    CSMB_CUDA(cudaFuncSetAttribute(k_gemm_part_t<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_ATTR));
+    CSMB_CUDA(bf_launch(w.cc, k_gemm_part_t<true, 0>, grid, dim3(BF_THREADS), smem, st, mw, mhi, mlo, a));
   }
   return CSMB_OK;
 }

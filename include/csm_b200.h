@@ -228,9 +228,9 @@ typedef struct {
                                the next big Linear's weights,
                                256 = at most 8 pipeline stages, bits 12..14 = k: the depth decoder's Linears ask L2 to keep
                                k/8 of their weight lines (evict-last) across the 31 depth steps (measured slower; default 0),
-                               4096 = the gate|up Linears, 8192 = the other Linears with an even number of n-tiles run as CTA
-                               pairs (2-CTA clusters, one tcgen05.mma.cta_group::2 of M = 256 per K step, each CTA loads half
-                               of the token operand; bit-identical, measured no faster: profiles/r02_cta_pair.md) */
+                               65536 = the gate|up Linears, 131072 = the other Linears with an even number of n-tiles run
+                               as CTA pairs (2-CTA clusters, one tcgen05.mma.cta_group::2 of M = 256 per K step, each CTA loads
+                               half of the token operand; bit-identical, measured no faster: profiles/r02_cta_pair.md) */
   int smem_kb;              /* shared-memory budget of a Linear CTA in KiB (48..200, 0 = 200): <= 100 lets two Linear CTAs
                                (of this or of another stream's chain) share an SM */
   const float* proj_table;  /* optional DEVICE table of csmb_build_proj_table: depth steps >= 2 read projection(embedding)

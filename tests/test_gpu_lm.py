@@ -313,12 +313,12 @@ def test_chain_swiglu_epilogue_equals_separate_launch(model_1b, device, monkeypa
     assert int((fused[1:] != fused[:-1]).sum()) > 0  # frames differ from step to step: the loop really decoded
 
 
-@pytest.mark.parametrize("flags", [8, 16, 32 | 64 | 128 | 256, 4096 | 8192])
+@pytest.mark.parametrize("flags", [8, 16, 32 | 64 | 128 | 256, 65536 | 131072])
 def test_chain_staged_kernels_are_bit_identical_to_the_plain_ones(model_1b, device, monkeypatch, flags):
     """The shared-memory staged kernels of the chain (k_attn_decode_small: the depth decoder's whole cache requested at once
     with cp.async; k_attn_decode_chunked: the backbone's cache in 64-position chunks; cp.async staged split-K partial sums in
     the norm / sampling kernels) and its L2 hints do the round-1 kernels' sums in the same order: identical tokens against
-    csmb_chain_opts.flags 8 (plain attention kernel), 16 (plain partial sums), the hints switched off, and 4096 | 8192 (every
+    csmb_chain_opts.flags 8 (plain attention kernel), 16 (plain partial sums), the hints switched off, and 65536 | 131072 (every
     Linear with an even number of n-tiles as CTA pairs: one tcgen05.mma.cta_group::2 of M = 256 per K step) — for ragged
     prompts whose caches cross the 64- and 128-position chunk boundaries while decoding (3 sequences, 6 frames)."""
     spec = SamplerSpec(temperature=0.0)
